@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the REAL reference
+(/root/reference, imported in place through oracle/ref_harness.py) on small seeded inputs.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python oracle/make_golden.py
+
+Each fixture stores the inputs, the unmodified reference's batch output
+(graph2pi.get_pimg_for_all_edges -> pi_sg, cnt_compute; riccidist2dgm.py:362-370) and, per target,
+the reference's own stage functions run on the canonically ordered vicinity
+(perturb_filter_function / Union_find / Accelerate_PD, accelerated_PD.py:6,26,115).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "tlc-gnn_b200"))
+
+import ref_harness as rh  # noqa: E402
+from tlc_b200 import graphgen as gg  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def ragged(list_of_arrays, dtype):
+    off = np.zeros(len(list_of_arrays) + 1, dtype=np.int64)
+    for i, a in enumerate(list_of_arrays):
+        off[i + 1] = off[i] + len(a)
+    flat = np.concatenate([np.asarray(a, dtype=dtype).reshape(-1) for a in list_of_arrays]) if list_of_arrays else np.zeros(0, dtype)
+    return flat, off
+
+
+def make_case(tag, edges, kappa, targets, hop, descriptor="sum", stage_targets=None):
+    edges = np.asarray(edges, dtype=np.int64)
+    targets = np.asarray(targets, dtype=np.int64)
+    kl = [float(k) for k in kappa]
+    out = dict(edges=edges, kappa=np.asarray(kappa, dtype=np.float64), targets=targets, hop=np.int64(hop),
+               descriptor=np.array(descriptor))
+    for ext in (False, True):
+        pi, cnt, obj = rh.run_batch(edges, kl, targets, hop, ext, descriptor=descriptor)
+        out["pi_ext%d" % ext] = pi
+        out["cnt_ext%d" % ext] = np.int64(cnt)
+    # per-target stages in canonical order, through the reference's own functions
+    st_idx = list(range(len(targets))) if stage_targets is None else list(stage_targets)
+    nodes, fvals, pd0, pos, neg, pd1, ncomp = [], [], [], [], [], [], []
+    for i in st_idx:
+        u, v = int(targets[i, 0]), int(targets[i, 1])
+        if u not in obj.dict_node or v not in obj.dict_node:
+            r = dict(nodes=[], ncomp=-1)
+        else:
+            try:
+                r = rh.run_one_stages(obj, u, v, hop, descriptor=descriptor, norm=True, canonical=True)
+            except BaseException:  # the batch driver swallows these too (riccidist2dgm.py:356-357)
+                r = dict(nodes=[], ncomp=-2)
+        ncomp.append(r["ncomp"])
+        nodes.append(r["nodes"])
+        ok = r["ncomp"] == 1 and "PD0" in r
+        fvals.append([r["fval"][x] for x in r["nodes"]] if ok else [])
+        pd0.append(np.asarray(r["PD0"], dtype=np.float64).reshape(-1) if ok else [])
+        pos.append(np.asarray(r["Pos"], dtype=np.int64).reshape(-1) if ok else [])
+        neg.append(np.asarray(r["Neg"], dtype=np.int64).reshape(-1) if ok else [])
+        pd1.append(np.asarray(r["PD1"], dtype=np.float64).reshape(-1) if ok and r["PD1"] is not None else [])
+    out["stage_idx"] = np.asarray(st_idx, dtype=np.int64)
+    out["stage_ncomp"] = np.asarray(ncomp, dtype=np.int64)
+    for name, lst, dt in (("nodes", nodes, np.int64), ("fval", fvals, np.float64), ("pd0", pd0, np.float64),
+                          ("pos", pos, np.int64), ("neg", neg, np.int64), ("pd1", pd1, np.float64)):
+        flat, off = ragged(lst, dt)
+        out["stage_%s" % name] = flat
+        out["stage_%s_off" % name] = off
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **out)
+    print("wrote", tag, "targets", len(targets), "cnt", int(out["cnt_ext0"]), int(out["cnt_ext1"]))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    if "--pimg-only" not in sys.argv:
+        graph_cases()
+    pimg_cases()
+
+
+def graph_cases():
+    # (1) SURVEY.md B.3 toy graph incl. every status class reachable on it
+    toy = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (1, 6), (2, 6)]
+    make_case("toy7_hop2", toy, [0] * 7, [(1, 2), (0, 3), (0, 5), (0, 99), (2, 1), (6, 1), (3, 3)], 2)
+    make_case("toy7_hop1", toy, [0] * 7, [(4, 5), (1, 2), (1, 6), (0, 1)], 1)
+    # (2) Cora-shaped, hop-distance filtration (heavy ties)
+    c = gg.make_config("cora", scale=0.25)
+    rng = np.random.default_rng(11)
+    idx = rng.choice(len(c["edges"]), 120, replace=False)
+    neg = gg.negative_pairs(c["N"], c["edges"], 30, seed=201)
+    make_case("cora_q_hop2", c["edges"], [0] * len(c["edges"]), np.concatenate([c["edges"][idx], neg]), 2)
+    # (3) PubMed-shaped, dyadic Ricci
+    c = gg.make_config("pubmed", scale=0.05)
+    idx = np.random.default_rng(12).choice(len(c["edges"]), 80, replace=False)
+    make_case("pubmed_s_hop2_dyadic", c["edges"], c["kappa"], c["edges"][idx], 2)
+    # (4) PubMed-shaped, continuous Ricci (C2b: F4 / F5 territory)
+    c = gg.make_config("pubmed", scale=0.05, continuous=True)
+    make_case("pubmed_s_hop2_cont", c["edges"], c["kappa"], c["edges"][idx], 2)
+    # (5) Computers-shaped (dense), hop 1 = the reference's own setting + a few hop 2
+    c = gg.make_config("computers", scale=0.02)
+    idx = np.random.default_rng(13).choice(len(c["edges"]), 60, replace=False)
+    make_case("computers_s_hop1", c["edges"], c["kappa"], c["edges"][idx], 1)
+    make_case("computers_s_hop2", c["edges"], c["kappa"], c["edges"][idx[:12]], 2)
+    # (6) descriptors min / max
+    c = gg.make_config("pubmed", scale=0.03)
+    idx = np.random.default_rng(14).choice(len(c["edges"]), 30, replace=False)
+    make_case("pubmed_s_min", c["edges"], c["kappa"], c["edges"][idx], 2, descriptor="min")
+    make_case("pubmed_s_max", c["edges"], c["kappa"], c["edges"][idx], 2, descriptor="max")
+
+
+def pimg_cases():
+    # (7) the reference tree's only PD->PI golden vector is a comment at KD/pimg.py:450-505; the
+    # image of that diagram by the real sg2dgm PersistenceImager at full precision:
+    ref = rh.load()
+    PD = np.array([[0.0913, 0.0913], [0.1294, 0.1294], [0.1606, 0.1606], [0.1628, 0.1628], [0.0801, 0.1628],
+                   [0.1993, 0.1993], [0.1186, 0.1993], [0.1189, 0.1993], [0.2081, 0.2081], [0.1294, 0.2081],
+                   [0.0800, 0.2081], [0.3562, 0.3562]] + [[0.0784, 0.3562]] * 3 + [[0.0798, 0.3562], [1.0, 1.0]] +
+                  [[0.0391, 1.0]] * 8 + [[0.0784, 1.0], [0.0913, 1.0], [0.0798, 0.2081]] + [[0.0784, 0.3562]] * 3 +
+                  [[0.0391, 1.0]] * 15)
+    gt4 = np.array([0.1209, 0.1381, 0.1520, 0.1610, 0.1642, 0.1173, 0.1340, 0.1474, 0.1561, 0.1592, 0.1093, 0.1249,
+                    0.1374, 0.1455, 0.1483, 0.0979, 0.1119, 0.1230, 0.1303, 0.1328, 0.0843, 0.0963, 0.1059, 0.1121,
+                    0.1143])
+    img = ref.pimg.PersistenceImager(resolution=5).transform(PD).reshape(-1)
+    assert PD.shape == (46, 2) and np.max(np.abs(img - gt4)) < 6e-5
+    rng = np.random.default_rng(5)
+    rnd = [rng.uniform(0, 1, size=(k, 2)) for k in (1, 7, 40)]
+    rnd.append(rng.uniform(-0.5, 3.0, size=(25, 2)))  # outside [0,1]: legal, Gaussian tails
+    res7 = ref.pimg.PersistenceImager(resolution=7).transform(rnd[2]).reshape(-1)
+    np.savez_compressed(os.path.join(OUT, "pimg_vectors.npz"), PD=PD, gt4=gt4, img=img,
+                        rnd0=rnd[0], rnd1=rnd[1], rnd2=rnd[2], rnd3=rnd[3],
+                        img0=ref.pimg.PersistenceImager(resolution=5).transform(rnd[0]).reshape(-1),
+                        img1=ref.pimg.PersistenceImager(resolution=5).transform(rnd[1]).reshape(-1),
+                        img2=ref.pimg.PersistenceImager(resolution=5).transform(rnd[2]).reshape(-1),
+                        img3=ref.pimg.PersistenceImager(resolution=5).transform(rnd[3]).reshape(-1), img2_res7=res7)
+    print("wrote pimg_vectors")
+
+
+if __name__ == "__main__":
+    main()
