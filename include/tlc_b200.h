@@ -1,0 +1,155 @@
+/* tlc_b200.h -- C-ABI of libtlc_b200.so: the B200 (sm_100a) implementation of TLC-GNN's per-target
+ * topological feature path (vicinity -> filtration -> 0-dim ordinary/extended persistence [+ 1-dim
+ * loops] -> persistence image).
+ *
+ * The reference (pkuyzy/TLC-GNN) has no FFI: its boundary is the Python package `sg2dgm`.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference root); the
+ * Python mirror in tlc-gnn_b200/sg2dgm/ binds them with ctypes.
+ *
+ * Conventions: plain pointers and sizes only.  "host" pointers are ordinary host memory, "dev"
+ * pointers are CUDA device memory on the graph's device.  Every function returns 0 on success or a
+ * negative tlc_rc; tlc_last_error() returns a thread-local message for the last failure.
+ * Per-target outcomes never fail a call: they are reported in a uint8 status array
+ * (riccidist2dgm.py:352-357 swallows per-edge exceptions into zero rows).
+ */
+#ifndef TLC_B200_H
+#define TLC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes ---- */
+#define TLC_OK 0
+#define TLC_E_INVALID (-1) /* bad argument */
+#define TLC_E_CUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define TLC_E_NOMEM (-3)   /* host or device allocation failed / one vicinity exceeds the arena */
+#define TLC_E_NODEVICE (-4)
+#define TLC_E_CAPACITY (-5) /* caller-provided output capacity too small */
+
+/* ---- vicinity mode ---- */
+#define TLC_MODE_EDGE 0 /* ball(u) & ball(v), induced          riccidist2dgm.py:311-316 */
+#define TLC_MODE_NODE 1 /* ball(u) (PDGNN generators)          Knowledge_Distillation/data_utils_NC.py:97-100 */
+
+/* ---- descriptor: which node attribute is the filtration     riccidist2dgm.py:47-49 ---- */
+#define TLC_DESC_MIN 0
+#define TLC_DESC_MAX 1
+#define TLC_DESC_SUM 2
+
+/* ---- flags ---- */
+#define TLC_F_NORM 1u       /* build_fv(norm=True)                       riccidist2dgm.py:50-56 */
+#define TLC_F_EXTENDED 2u   /* + Accelerate_PD (1-dim extended pairs)    riccidist2dgm.py:323-326 */
+#define TLC_F_KEEP_ZERO 4u  /* KD copy: emit zero-persistence pairs      KD/accelerated_PD.py:68-69,108-109,169-170 */
+#define TLC_F_NORM_EPS 8u   /* KD: divide by (max + 1e-10)               KD/data_utils_NC.py:54 */
+#define TLC_F_SUM_PLAIN 16u /* path sums left-to-right (CPython <= 3.11); default Neumaier (CPython >= 3.12 sum()) */
+
+/* ---- pair kinds, in the reference's concatenation order    accelerated_PD.py:110, riccidist2dgm.py:328 ---- */
+#define TLC_K_UP 0      /* PD_up   : 0-dim ordinary                 accelerated_PD.py:65-66 */
+#define TLC_K_ESS 1     /* [min,max]                                accelerated_PD.py:110   */
+#define TLC_K_DOWN 2    /* PD_down : relative                       accelerated_PD.py:105-106 */
+#define TLC_K_ESS_REV 3 /* [max,min]                                accelerated_PD.py:110   */
+#define TLC_K_ONE 4     /* PD_one  : 1-dim extended (loops)         accelerated_PD.py:164-165 */
+
+/* ---- per-target status ---- */
+#define TLC_ST_OK 0
+#define TLC_ST_TRIVIAL 1        /* roots outside the vicinity: all values equal, image zero, counted */
+#define TLC_ST_EMPTY 2          /* empty vicinity                          riccidist2dgm.py:318 */
+#define TLC_ST_DISCONNECTED 3   /* >1 component                            riccidist2dgm.py:318 */
+#define TLC_ST_DEGENERATE 4     /* normaliser 0 (vicinity == {u,v})        riccidist2dgm.py:54-56 */
+#define TLC_ST_UNKNOWN_NODE 5   /* id not in the graph / isolated          riccidist2dgm.py:353 */
+#define TLC_ST_BAD_DESCRIPTOR 6 /* attribute missing                       accelerated_PD.py:13 */
+#define TLC_ST_NO_TREE_EDGES 7  /* single vertex + extended flag           accelerated_PD.py:122 */
+
+typedef struct {
+  int32_t hop;        /* BFS depth limit                                   riccidist2dgm.py:310 */
+  int32_t mode;       /* TLC_MODE_*                                                             */
+  int32_t descriptor; /* TLC_DESC_*                                                             */
+  int32_t resolution; /* image is resolution x resolution (1..16)          PersistenceImager.pyx:207 */
+  uint32_t flags;     /* TLC_F_*                                                                */
+  uint32_t img_mask;  /* bit k set: pairs of kind k are rasterised                              */
+} tlc_params;
+
+typedef struct tlc_graph tlc_graph; /* opaque: CSR + curvature resident in HBM, scratch arena, stream */
+
+/* graph2pi.__init__ (riccidist2dgm.py:216-226): node ids are the reference's integer relabelling
+ * (first appearance order); rowptr[N+1], col[nnz] ascending inside each row, kappa[nnz] = Ricci
+ * curvature of the directed edge (weight = kappa + 1, :225).  All host pointers; copied to `device`.
+ * arena_bytes = 0 picks a default (TLC_ARENA_GB env or 24 GiB, clamped to free memory). */
+int tlc_graph_create(int32_t N, int64_t nnz, const int32_t *rowptr, const int32_t *col, const double *kappa,
+                     int device, uint64_t arena_bytes, tlc_graph **out);
+int tlc_graph_destroy(tlc_graph *g);
+
+/* graph2pi.get_pimg_for_all_edges (riccidist2dgm.py:362-370) for a whole batch, HOST buffers.
+ * targets[E][2] are graph ids (-1 = label unknown to dict_node).  out_pi[E][res*res] float64 rows
+ * (zero for failed targets, as :363 pre-zeroes), out_status[E] (may be NULL), *cnt_compute (may be
+ * NULL) = number of targets the reference would have counted (:354). */
+int tlc_vicinity_pi(tlc_graph *g, const int32_t *targets, int64_t E, const tlc_params *p, double *out_pi,
+                    uint8_t *out_status, int64_t *cnt_compute);
+
+/* same, DEVICE buffers (inputs already resident; no host<->device copies of payload).
+ * dev_out_pi is float64[E][res*res]; dev_out_pi_f32 (may be NULL) additionally receives float32
+ * rows (the layout that is all-gathered across GPUs). */
+int tlc_vicinity_pi_dev(tlc_graph *g, const int32_t *dev_targets, int64_t E, const tlc_params *p, double *dev_out_pi,
+                        float *dev_out_pi_f32, uint8_t *dev_out_status, int64_t *cnt_compute);
+
+/* vicinity sizes only (kernel 1, counting pass): n[E] vertices, m[E] induced edges, host buffers.
+ * Lets a caller size diagram buffers: pairs(e) <= n + m + 1. */
+int tlc_vicinity_sizes(tlc_graph *g, const int32_t *targets, int64_t E, const tlc_params *p, int32_t *out_n,
+                       int32_t *out_m, uint8_t *out_status);
+
+/* every intermediate of the path for a (small) batch, HOST buffers, for stage-level parity:
+ *   voff[E+1], eoff[E+1], poff[E+1]  : exclusive offsets of the per-target segments
+ *   vert[sum n]   graph ids ascending                     (kernel 1; riccidist2dgm.py:311-316)
+ *   elo,ehi[sum m] local ids, lexicographic; ew = kappa+1 (kernel 1)
+ *   fval[sum n]   filtration values                       (kernel 1b; riccidist2dgm.py:20-61)
+ *   ord_asc, ord_desc[sum m] edge index in sweep order    (kernel 2; accelerated_PD.py:40-41,76-77)
+ *   pairs: npairs[E]; pkind/pbv/pdv/pbirth/pdeath at poff (kernel 3/3b; local vertex ids)
+ *   pos/neg edge indices in sweep order at eoff / voff; npos[E], nneg[E]
+ *   pi[E][res*res], status[E]
+ * Any output pointer may be NULL.  cap_v/cap_e/cap_p are the capacities of the segment buffers
+ * (TLC_E_CAPACITY if exceeded; use tlc_vicinity_sizes first). */
+typedef struct {
+  int64_t cap_v, cap_e, cap_p;
+  int64_t *voff, *eoff, *poff;
+  int32_t *n, *m, *lu, *lv, *npairs, *npos, *nneg;
+  int32_t *vert, *elo, *ehi;
+  double *ew, *fval;
+  int32_t *ord_asc, *ord_desc;
+  int32_t *pkind, *pbv, *pdv;
+  double *pbirth, *pdeath;
+  int32_t *pos, *neg;
+  double *pi;
+  uint8_t *status;
+} tlc_detail;
+int tlc_vicinity_detail(tlc_graph *g, const int32_t *targets, int64_t E, const tlc_params *p, tlc_detail *out);
+
+/* Union_find(simplex_filter) + Accelerate_PD(Pos, Neg, simplex_filter) on ONE caller-supplied graph
+ * (accelerated_PD.py:26,115; KD/accelerated_PD.py:25,120): n vertices with filtration fval[n], m edges
+ * (a[i], b[i]) in the caller's dict order (that order is the tie-break).  flags: TLC_F_EXTENDED,
+ * TLC_F_KEEP_ZERO.  Outputs as in tlc_detail (pairs capacity n+m+1; pos capacity m; neg capacity n).
+ * Host buffers; runs kernels 2, 3, 3b on `device`. */
+int tlc_union_find(int device, int32_t n, int32_t m, const double *fval, const int32_t *a, const int32_t *b,
+                   uint32_t flags, int32_t *npairs, int32_t *pkind, int32_t *pbv, int32_t *pdv, double *pbirth,
+                   double *pdeath, int32_t *npos, int32_t *pos, int32_t *nneg, int32_t *neg, uint8_t *status);
+
+/* PersistenceImager(resolution).transform(dgm, skew=True) (PersistenceImager.pyx:352-388): host
+ * dgm[K][2] (birth, death) float64 -> out[res*res] float64, runs kernel 4 on `device`. */
+int tlc_pimg_transform(int device, const double *dgm, int64_t K, int32_t resolution, double *out);
+
+/* introspection */
+const char *tlc_last_error(void);
+const char *tlc_version(void);
+/* kernels launched by this library since load (the bench's gpu_launches counter) */
+int64_t tlc_launch_count(void);
+/* per-stage device time of the last tlc_vicinity_pi* call on this graph, ms, summed over chunks:
+ * out[0..7] = sizes, fill, filtration, sort, union-find, loops, image, total; returns #chunks.
+ * Only measured when the environment variable TLC_STAGE_TIMING=1 (adds event records). */
+int tlc_last_stage_ms(tlc_graph *g, double *out8);
+/* algorithmic bytes (compulsory bytes B_e) summed over the targets of the last call */
+int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_bfs, double *bytes_uf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,123 @@
+"""CUDA path (through the C-ABI) vs the oracle: bit-exact integers / float64 values, images 1e-5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as orc
+from helpers import GRAPH_CASES, load_case, rel_err
+from tlc_b200 import _lib as L
+from tlc_b200 import api, graphgen as gg
+
+IMG_TOL = 1e-5  # north_star: persistence images within 1e-5 relative
+
+
+def compare_detail(g, og, targets, hop, descriptor, flags, oflags, mode=L.MODE_EDGE):
+    d = g.vicinity_detail(targets, hop=hop, mode=mode, descriptor=descriptor, flags=flags)
+    for i, (u, v) in enumerate(targets):
+        a = g.per_target(d, i)
+        o = og.run_one(int(u), int(v), hop=hop, mode=mode, descriptor=descriptor, flags=oflags)
+        ctx = "target %d (%d,%d) status gpu %d oracle %d n %d m %d" % (i, u, v, a["status"], o["status"], o["n"], o["m"])
+        assert a["status"] == o["status"], ctx
+        assert a["n"] == o["n"] and a["m"] == o["m"], ctx
+        if o["status"] in (5,):
+            continue
+        assert np.array_equal(a["vert"], o["vert"]), ctx              # kernel 1: vertex set, canonical order
+        assert np.array_equal(a["elo"], o["elo"]) and np.array_equal(a["ehi"], o["ehi"]), ctx
+        assert np.array_equal(a["ew"], o["ew"]), ctx
+        if o["status"] > 1 and o["status"] != 7:
+            continue
+        assert (a["lu"], a["lv"]) == (o["lu"], o["lv"]), ctx
+        assert np.array_equal(a["fval"], o["fval"]), ctx              # kernel 1b: bit-exact float64
+        assert np.array_equal(a["ord_asc"], o["ord_asc"]), ctx        # kernel 2
+        assert np.array_equal(a["ord_desc"], o["ord_desc"]), ctx
+        k = len(o["pkind"])
+        assert len(a["pkind"]) == k, ctx                              # kernel 3 / 3b: pairs bit-exact
+        assert np.array_equal(a["pkind"], o["pkind"]), ctx
+        assert np.array_equal(a["pbv"], o["pbv"]) and np.array_equal(a["pdv"], o["pdv"]), ctx
+        assert np.array_equal(a["pbirth"], o["pbirth"]) and np.array_equal(a["pdeath"], o["pdeath"]), ctx
+        assert np.array_equal(a["neg"], o["neg"]), ctx
+        assert np.array_equal(a["pos"], o["pos"]), ctx
+        assert rel_err(a["img"], o["img"]) < IMG_TOL, ctx             # kernel 4
+
+
+@pytest.mark.parametrize("tag", GRAPH_CASES)
+@pytest.mark.parametrize("ext", [0, 1])
+def test_golden_cases(tag, ext):
+    c = load_case(tag)
+    g = api.VicinityGraph(*c["csr"], device=0)
+    og = orc.OracleGraph(*c["csr"])
+    flags = L.F_NORM | (L.F_EXTENDED if ext else 0)
+    # batch call: images vs the REAL reference's pi_sg stored in the fixture, counts equal
+    pi, status, cnt = g.vicinity_pi(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=flags)
+    ref = c["pi_ext%d" % ext]
+    assert cnt == int(c["cnt_ext%d" % ext])
+    assert np.array_equal(ref.any(axis=1), pi.any(axis=1))
+    assert rel_err(pi, ref) < IMG_TOL
+    o = og.run_batch(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=flags)
+    assert np.array_equal(status, o["status"])
+    compare_detail(g, og, c["new_targets"], c["hop"], c["descriptor"], flags, flags)
+    g.close()
+
+
+@pytest.mark.parametrize("name,scale,hop,cont", [("cora", 1.0, 2, False), ("cora", 1.0, 3, False), ("pubmed", 0.3, 2, False),
+                                                 ("pubmed", 0.3, 2, True), ("computers", 0.05, 2, False),
+                                                 ("computers", 0.05, 2, True), ("ppi", 0.3, 1, False)])
+def test_random_targets(name, scale, hop, cont):
+    c = gg.make_config(name, scale=scale, continuous=cont)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    rng = np.random.default_rng(7)
+    tg = ne[rng.choice(len(ne), 48, replace=False)].astype(np.int32)
+    neg = rng.integers(0, len(labels), size=(16, 2)).astype(np.int32)
+    tg = np.concatenate([tg, neg, np.array([[-1, 3], [0, 0]], np.int32)])
+    flags = L.F_NORM | L.F_EXTENDED
+    compare_detail(g, og, tg, hop, "sum", flags, flags)
+    pi, status, cnt = g.vicinity_pi(tg, hop=hop, flags=flags)
+    o = og.run_batch(tg, hop=hop, flags=flags)
+    assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
+    assert rel_err(pi, o["pi"]) < IMG_TOL
+    g.close()
+
+
+def test_node_mode_kd_flags():
+    """PDGNN node-centred vicinities (Knowledge_Distillation/data_utils_NC.py:95-183 shape)."""
+    c = gg.make_config("ppi", scale=0.25)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    nodes = np.random.default_rng(3).choice(len(labels), 24, replace=False)
+    tg = np.stack([nodes, nodes], 1).astype(np.int32)
+    flags = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
+    compare_detail(g, og, tg, 2, "sum", flags, flags, mode=L.MODE_NODE)
+    g.close()
+
+
+def test_pimg_transform_golden():
+    import os
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "pimg_vectors.npz"))
+    img = api.pimg_transform(z["PD"]).reshape(-1)
+    assert np.max(np.abs(img - z["gt4"])) < 6e-5          # Knowledge_Distillation/pimg.py:450-505
+    assert rel_err(img, z["img"]) < IMG_TOL
+    for k in range(4):
+        assert rel_err(api.pimg_transform(z["rnd%d" % k]).reshape(-1), z["img%d" % k]) < IMG_TOL
+    assert rel_err(api.pimg_transform(z["rnd2"], 7).reshape(-1), z["img2_res7"]) < IMG_TOL
+
+
+def test_union_find_api():
+    """Union_find/Accelerate_PD entry point on a caller-supplied graph, order = tie-break."""
+    c = load_case("pubmed_s_hop2_cont")
+    og = orc.OracleGraph(*c["csr"])
+    for ti in range(6):
+        u, v = c["new_targets"][ti]
+        o = og.run_one(int(u), int(v), hop=2, flags=orc.F_NORM | orc.F_EXTENDED)
+        if o["status"] != 0:
+            continue
+        r = api.union_find(o["fval"], np.stack([o["elo"], o["ehi"]], 1), flags=L.F_EXTENDED)
+        assert np.array_equal(r["pkind"], o["pkind"])
+        assert np.array_equal(r["pbirth"], o["pbirth"]) and np.array_equal(r["pdeath"], o["pdeath"])
+        assert np.array_equal(r["pos"], o["pos"]) and np.array_equal(r["neg"], o["neg"])

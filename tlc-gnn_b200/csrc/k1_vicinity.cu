@@ -1,0 +1,295 @@
+// k1_vicinity.cu -- kernel 1: batched k-hop vicinity extraction on the CSR graph.
+//
+// Replaces riccidist2dgm.py:311-316 (two nx.bfs_edges balls, set intersection, G.subgraph) and
+// Knowledge_Distillation/data_utils_NC.py:97-100 (node-centred ball).
+//
+// One CTA per target at a time (persistent grid, targets handed out by an atomic counter).  The two
+// closed balls are bitmaps over the N graph nodes (shared memory when 2*ceil(N/32) words fit, else a
+// per-CTA slab in HBM); the vicinity is their AND.  Local vertex ids are ranks in the bitmap
+// (word-prefix popcounts), which yields the canonical ascending-id order for free; induced edges are
+// emitted lexicographically (lo,hi) by a count / scan / ballot-compacted fill over the CSR rows.
+//
+// Two entry points share the traversal: a counting pass (n, m per target -> the host sizes the chunk
+// arena) and the fill pass (vertex list, induced edges with weight kappa+1, local root ids).
+#include "tlc_common.cuh"
+
+namespace tlc {
+
+namespace {
+
+constexpr int K1_BLOCK = 256;
+
+struct K1Shared {
+  int32_t scan[K1_BLOCK + 1];
+  int32_t red[32];
+  int32_t qcnt[2];
+  int32_t target;
+  unsigned long long dacc;  // algorithmic-byte accounting: sum of expanded degrees (D_u + D_v + D_S)
+  unsigned long long xacc;  // ... and number of rowptr pairs read (X)
+};
+
+__device__ __forceinline__ bool test_bit(const uint32_t* bm, int32_t y) { return (bm[y >> 5] >> (y & 31)) & 1u; }
+__device__ __forceinline__ bool set_bit(uint32_t* bm, int32_t y) {  // returns true if newly set
+  const uint32_t bit = 1u << (y & 31);
+  if (bm[y >> 5] & bit) return false;
+  return (atomicOr(&bm[y >> 5], bit) & bit) == 0;
+}
+
+// closed ball of radius hop around root into bm (bm zeroed by the caller).
+// nodes_u = [root] + [x for _, x in nx.bfs_edges(G, root, depth_limit=hop)]   riccidist2dgm.py:311-312
+__device__ void ball(const GraphView& g, int32_t root, int hop, uint32_t* bm, int32_t* q0, int32_t* q1,
+                     K1Shared& sh) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  if (tid == 0) bm[root >> 5] |= 1u << (root & 31);
+  __syncthreads();
+  if (hop <= 0) return;
+  const int32_t r0 = g.rowptr[root], r1 = g.rowptr[root + 1];
+  if (tid == 0) { sh.dacc += (unsigned long long)(r1 - r0); sh.xacc += 1; }
+  // depth 1: the CSR row of the root, 128-bit loads where the row is aligned
+  for (int32_t e = r0 + tid; e < r1; e += nt) set_bit(bm, g.col[e]);
+  __syncthreads();
+  if (hop == 1) return;
+  // depth 2: one warp per depth-1 vertex, lanes stride its row (coalesced)
+  const bool push = hop > 2;
+  if (tid == 0) sh.qcnt[0] = 0;
+  __syncthreads();
+  for (int32_t i = r0 + wid; i < r1; i += nw) {
+    const int32_t x = g.col[i];
+    const int32_t a = g.rowptr[x], b = g.rowptr[x + 1];
+    if (lane == 0) { atomicAdd(&sh.dacc, (unsigned long long)(b - a)); atomicAdd(&sh.xacc, 1ull); }
+    for (int32_t e = a + lane; e < b; e += 32) {
+      const int32_t y = g.col[e];
+      if (set_bit(bm, y) && push) q0[atomicAdd(&sh.qcnt[0], 1)] = y;
+    }
+  }
+  __syncthreads();
+  // depth >= 3: explicit frontier queues (HBM slabs); newly set bits form the next frontier
+  int32_t* cur = q0;
+  int32_t* nxt = q1;
+  int ci = 0;
+  for (int d = 2; d < hop; d++) {
+    const int cnt = sh.qcnt[ci];
+    if (tid == 0) sh.qcnt[ci ^ 1] = 0;
+    __syncthreads();
+    if (cnt == 0) break;
+    const bool push2 = d + 1 < hop;
+    for (int i = wid; i < cnt; i += nw) {
+      const int32_t x = cur[i];
+      const int32_t a = g.rowptr[x], b = g.rowptr[x + 1];
+      if (lane == 0) { atomicAdd(&sh.dacc, (unsigned long long)(b - a)); atomicAdd(&sh.xacc, 1ull); }
+      for (int32_t e = a + lane; e < b; e += 32) {
+        const int32_t y = g.col[e];
+        if (set_bit(bm, y) && push2) nxt[atomicAdd(&sh.qcnt[ci ^ 1], 1)] = y;
+      }
+    }
+    __syncthreads();
+    int32_t* t = cur; cur = nxt; nxt = t;
+    ci ^= 1;
+  }
+  __syncthreads();
+}
+
+// ball(u) & ball(v) -> iw (in bm_u) ; word-prefix popcounts -> wbase (in bm_v) ; returns n
+__device__ int build_vicinity(const GraphView& g, const Params& p, int32_t u, int32_t v, int W, uint32_t* bm_u,
+                              uint32_t* bm_v, int32_t* q0, int32_t* q1, K1Shared& sh) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int w = tid; w < 2 * W; w += nt) bm_u[w] = 0;  // bm_v follows bm_u
+  __syncthreads();
+  ball(g, u, p.hop, bm_u, q0, q1, sh);
+  if (p.mode == TLC_MODE_EDGE) {
+    ball(g, v, p.hop, bm_v, q0, q1, sh);
+    for (int w = tid; w < W; w += nt) {  // nodes = set(nodes_u) & set(nodes_v)   :315
+      const uint32_t x = bm_u[w] & bm_v[w];
+      bm_u[w] = x;
+      bm_v[w] = __popc(x);
+    }
+  } else {
+    for (int w = tid; w < W; w += nt) bm_v[w] = __popc(bm_u[w]);
+  }
+  __syncthreads();
+  return block_exclusive_scan(reinterpret_cast<int32_t*>(bm_v), W, sh.scan);
+}
+
+__device__ __forceinline__ int32_t local_id(const uint32_t* iw, const uint32_t* wbase, int32_t y) {
+  return (int32_t)wbase[y >> 5] + __popc(iw[y >> 5] & ((1u << (y & 31)) - 1u));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(K1_BLOCK)
+vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int64_t E, int32_t* out_n, int32_t* out_m,
+                uint8_t* out_status, double* out_bytes, ChunkView c, VicinityScratch vs, int* work_counter, int W,
+                int bm_in_smem) {
+  extern __shared__ uint32_t dyn_smem[];
+  __shared__ K1Shared sh;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  uint32_t* bm_u = bm_in_smem ? dyn_smem : vs.bitmaps + (size_t)blockIdx.x * 2 * W;
+  uint32_t* bm_v = bm_u + W;
+  int32_t* q0 = vs.queue ? vs.queue + (size_t)blockIdx.x * 2 * g.N : nullptr;
+  int32_t* q1 = q0 ? q0 + g.N : nullptr;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sh.target = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int64_t t = sh.target;
+    if (t >= E) break;
+    const int64_t ti = FILL ? c.tidx[t] : t;
+    const int32_t u = targets[2 * ti], v = targets[2 * ti + 1];
+    const bool node_mode = p.mode == TLC_MODE_NODE;
+    // dict_node[u] KeyError (riccidist2dgm.py:353); the reference graph has no isolated nodes
+    bool bad = u < 0 || u >= g.N || (!node_mode && (v < 0 || v >= g.N));
+    if (!bad) bad = g.rowptr[u + 1] == g.rowptr[u] || (!node_mode && g.rowptr[v + 1] == g.rowptr[v]);
+    if (bad) {
+      if (tid == 0) {
+        if (!FILL) { out_n[t] = 0; out_m[t] = 0; out_status[t] = TLC_ST_UNKNOWN_NODE; }
+        else { c.tn[t] = 0; c.tm[t] = 0; c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tlu[t] = -1; c.tlv[t] = -1;
+               c.tstatus[t] = TLC_ST_UNKNOWN_NODE; }
+      }
+      continue;
+    }
+    if (tid == 0) { sh.dacc = 0; sh.xacc = 0; }
+    __syncthreads();
+    const int n = build_vicinity(g, p, u, v, W, bm_u, bm_v, q0, q1, sh);
+    const uint32_t* iw = bm_u;
+    const uint32_t* wbase = bm_v;
+
+    int64_t vo = 0, eo = 0;
+    int32_t* vcnt = nullptr;
+    if (FILL) { vo = c.voff[t]; eo = c.eoff[t]; vcnt = c.vs0 + vo; }
+
+    // pass A: per vicinity vertex, count induced neighbours with a larger id
+    int msum = 0;
+    for (int w = wid; w < W; w += nw) {
+      uint32_t bits = iw[w];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int32_t x = w * 32 + b;
+        const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
+        int cnt = 0;
+        for (int32_t e = ra + lane; e < rb; e += 32) {
+          const int32_t y = g.col[e];
+          cnt += (y > x && test_bit(iw, y)) ? 1 : 0;
+        }
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (!FILL && lane == 0) atomicAdd(&sh.dacc, (unsigned long long)(rb - ra));
+        if (FILL && lane == 0) {
+          const int32_t lx = local_id(iw, wbase, x);
+          vcnt[lx] = cnt;
+          c.vert[vo + lx] = x;
+        }
+        msum += (lane == 0) ? cnt : 0;
+      }
+    }
+    const int m = block_reduce_sum(msum, sh.red);
+
+    if (!FILL) {
+      if (tid == 0) {
+        out_n[t] = n;
+        out_m[t] = m;
+        uint8_t st = TLC_ST_OK;
+        if (n == 0) st = TLC_ST_EMPTY;                          // assert len(components) == 1 fails  :318
+        else if (node_mode && m == 0) st = TLC_ST_EMPTY;        // `return None, None` data_utils_NC.py:103-104
+        out_status[t] = st;
+        // compulsory bytes B_e: int32 neighbour reads of both expansions and of the induced
+        // scan, rowptr pairs, f64 weight per induced directed edge, fp32 image
+        if (out_bytes)
+          out_bytes[t] = 4.0 * (double)sh.dacc + 8.0 * (double)(sh.xacc + (unsigned long long)n) + 16.0 * (double)m +
+                         4.0 * p.resolution * p.resolution;
+      }
+      continue;
+    }
+
+    // pass B (fill): exclusive scan of the counts = start of every vertex's edge run
+    __syncthreads();
+    block_exclusive_scan(vcnt, n, sh.scan);
+    for (int w = wid; w < W; w += nw) {
+      uint32_t bits = iw[w];
+      int32_t lx = (int32_t)wbase[w];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int32_t x = w * 32 + b;
+        const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
+        int64_t out = eo + vcnt[lx];
+        for (int32_t e0 = ra; e0 < rb; e0 += 32) {
+          const int32_t e = e0 + lane;
+          int32_t y = -1;
+          bool keep = false;
+          if (e < rb) { y = g.col[e]; keep = y > x && test_bit(iw, y); }
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const int64_t o = out + __popc(bal & lanemask_lt());
+            c.elo[o] = lx;
+            c.ehi[o] = local_id(iw, wbase, y);
+            c.ew[o] = g.kappa[e] + 1.0;  // graph[a][b]['weight'] = kappa + 1   riccidist2dgm.py:225
+          }
+          out += __popc(bal);
+        }
+        lx++;
+      }
+    }
+    if (tid == 0) {
+      c.tn[t] = n;
+      c.tm[t] = m;
+      const bool u_in = test_bit(iw, u);
+      const bool v_in = node_mode ? u_in : test_bit(iw, v);
+      c.tlu[t] = u_in ? local_id(iw, wbase, u) : -1;
+      c.tlv[t] = node_mode ? c.tlu[t] : (v_in ? local_id(iw, wbase, v) : -1);
+      uint8_t st = (u_in && v_in) ? TLC_ST_OK : TLC_ST_TRIVIAL;
+      if (n == 0 || (node_mode && m == 0)) st = TLC_ST_EMPTY;  // :318 / data_utils_NC.py:103-104
+      c.tstatus[t] = st;
+      c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tncls[t] = 0;
+    }
+  }
+}
+
+}  // namespace
+
+int vicinity_grid(int device, const GraphView& g, const Params& p, size_t* bitmap_words, bool* use_smem) {
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const size_t W = ((size_t)g.N + 31) / 32;
+  *bitmap_words = W;
+  const size_t need = 2 * W * sizeof(uint32_t);
+  *use_smem = need <= 96 * 1024;
+  int per_sm = 4;
+  if (*use_smem && need > 0) {
+    const size_t fit = (size_t)(200 * 1024) / (need + 2048);
+    per_sm = (int)(fit < 1 ? 1 : (fit > 6 ? 6 : fit));
+  }
+  return prop.multiProcessorCount * per_sm;
+}
+
+static void set_smem(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
+                           int32_t* out_m, uint8_t* out_status, double* out_bytes, const VicinityScratch& vs,
+                           int* work_counter, cudaStream_t st) {
+  const int W = (g.N + 31) / 32;
+  const bool smem = vs.bitmaps == nullptr;
+  const size_t bytes = smem ? (size_t)2 * W * 4 : 0;
+  set_smem((const void*)vicinity_kernel<false>, bytes);
+  cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  ChunkView dummy{};
+  vicinity_kernel<false><<<vs.grid, K1_BLOCK, bytes, st>>>(g, p, targets, E, out_n, out_m, out_status, out_bytes, dummy, vs,
+                                                          work_counter, W, smem ? 1 : 0);
+  count_launch();
+}
+
+void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
+                          int* work_counter, cudaStream_t st) {
+  const int W = (g.N + 31) / 32;
+  const bool smem = vs.bitmaps == nullptr;
+  const size_t bytes = smem ? (size_t)2 * W * 4 : 0;
+  set_smem((const void*)vicinity_kernel<true>, bytes);
+  cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  const int grid = vs.grid < c.T ? vs.grid : c.T;
+  vicinity_kernel<true><<<grid, K1_BLOCK, bytes, st>>>(g, p, c.tgt, c.T, nullptr, nullptr, nullptr, nullptr, c, vs, work_counter,
+                                                      W, smem ? 1 : 0);
+  count_launch();
+}
+
+}  // namespace tlc

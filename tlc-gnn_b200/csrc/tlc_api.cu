@@ -1,0 +1,658 @@
+// tlc_api.cu -- host orchestration and the C-ABI of libtlc_b200.so (include/tlc_b200.h).
+//
+// A call processes its targets in CHUNKS.  The counting pass of kernel 1 gives every target's
+// vicinity size (n, m); the host sorts live targets by size (largest first: longest-processing-time
+// scheduling, and size-homogeneous chunks), packs as many as fit the HBM arena, and runs the stage
+// kernels over the chunk: 1 fill -> 1b filtration -> 2 sort -> 3 union-find -> [3b loops] -> 4 image.
+// Per-target segments of every array are addressed through exclusive offsets uploaded per chunk; the
+// image kernel scatters rows to their final position, so results keep the caller's target order.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "tlc_common.cuh"
+
+namespace tlc {
+static std::atomic_llong g_launches{0};
+int64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
+}  // namespace tlc
+
+using namespace tlc;
+
+static thread_local std::string g_err;
+static int fail(int rc, const std::string& msg) {
+  g_err = msg;
+  return rc;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(TLC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
+                                  std::to_string(__LINE__));                                       \
+  } while (0)
+
+static constexpr size_t ALIGN = 256;
+static size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+
+// bytes of arena per vertex / edge / pair slot (see carve())
+static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3;                   // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c
+static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1;           // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg
+static constexpr size_t BP = 1 + 4 * 2 + 8 * 2;                       // pkind | pbv pdv | pbirth pdeath
+static constexpr size_t BT = 8 * 3 + 4 * 8 + 1;                       // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls | tstatus
+
+struct tlc_graph {
+  int device = 0;
+  GraphView gv{};
+  cudaStream_t stream = nullptr;
+  char* arena = nullptr;
+  size_t arena_bytes = 0, arena_req = 0;
+  // vicinity scratch (depends on hop)
+  uint32_t* bitmaps = nullptr;
+  int32_t* queue = nullptr;
+  int vic_grid = 0, vic_hop = -1;
+  int* work_counter = nullptr;
+  // per-call device buffers
+  int32_t *d_n = nullptr, *d_m = nullptr;
+  uint8_t* d_st = nullptr;
+  double* d_bytes = nullptr;
+  int64_t call_cap = 0;
+  // host pinned staging
+  char* h_pin = nullptr;
+  size_t h_pin_bytes = 0;
+  // stats of the last call
+  double stage_ms[8] = {0};
+  int nchunks = 0;
+  double alg_bytes = 0, alg_bytes_bfs = 0, alg_bytes_uf = 0;
+  bool timing = false;
+  int sm_count = 0;
+};
+
+static int ensure_pinned(tlc_graph* g, size_t bytes) {
+  if (bytes <= g->h_pin_bytes) return TLC_OK;
+  if (g->h_pin) cudaFreeHost(g->h_pin);
+  g->h_pin = nullptr;
+  g->h_pin_bytes = 0;
+  CK(cudaMallocHost((void**)&g->h_pin, bytes));
+  g->h_pin_bytes = bytes;
+  return TLC_OK;
+}
+
+static int ensure_call_buffers(tlc_graph* g, int64_t E) {
+  if (E <= g->call_cap) return TLC_OK;
+  if (g->d_n) cudaFree(g->d_n);
+  if (g->d_m) cudaFree(g->d_m);
+  if (g->d_st) cudaFree(g->d_st);
+  if (g->d_bytes) cudaFree(g->d_bytes);
+  g->d_n = g->d_m = nullptr; g->d_st = nullptr; g->d_bytes = nullptr; g->call_cap = 0;
+  const int64_t cap = E + E / 8 + 1024;
+  CK(cudaMalloc((void**)&g->d_n, cap * 4));
+  CK(cudaMalloc((void**)&g->d_m, cap * 4));
+  CK(cudaMalloc((void**)&g->d_st, cap));
+  CK(cudaMalloc((void**)&g->d_bytes, cap * 8));
+  g->call_cap = cap;
+  return TLC_OK;
+}
+
+static int ensure_arena(tlc_graph* g, size_t need_min) {
+  if (g->arena && g->arena_bytes >= need_min) return TLC_OK;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  if (g->arena) { free_b += g->arena_bytes; cudaFree(g->arena); g->arena = nullptr; g->arena_bytes = 0; }
+  size_t want = g->arena_req;
+  if (want == 0) {
+    const char* env = getenv("TLC_ARENA_GB");
+    const double gb = env ? atof(env) : 24.0;
+    want = (size_t)(gb * (double)(1ull << 30));
+  }
+  want = std::max(want, need_min);
+  const size_t cap = (size_t)((double)free_b * 0.85);
+  if (want > cap) want = cap;
+  if (want < need_min)
+    return fail(TLC_E_NOMEM, "one vicinity needs " + std::to_string(need_min) + " arena bytes, only " +
+                                 std::to_string(cap) + " available");
+  CK(cudaMalloc((void**)&g->arena, want));
+  g->arena_bytes = want;
+  return TLC_OK;
+}
+
+static int ensure_vicinity_scratch(tlc_graph* g, const Params& p) {
+  if (g->vic_hop == p.hop && g->vic_grid > 0) return TLC_OK;
+  if (g->bitmaps) { cudaFree(g->bitmaps); g->bitmaps = nullptr; }
+  if (g->queue) { cudaFree(g->queue); g->queue = nullptr; }
+  size_t W = 0;
+  bool smem = false;
+  g->vic_grid = vicinity_grid(g->device, g->gv, p, &W, &smem);
+  if (!smem) CK(cudaMalloc((void**)&g->bitmaps, (size_t)g->vic_grid * 2 * W * sizeof(uint32_t)));
+  if (p.hop > 2) CK(cudaMalloc((void**)&g->queue, (size_t)g->vic_grid * 2 * (size_t)g->gv.N * sizeof(int32_t)));
+  g->vic_hop = p.hop;
+  return TLC_OK;
+}
+
+// carve the arena for a chunk with T targets, Nv vertices, Ne edges (pairs = Nv + Ne + T)
+static size_t chunk_bytes(int64_t T, int64_t Nv, int64_t Ne) {
+  const int64_t Np = Nv + Ne + T;
+  // every array individually aligned: 12 vertex arrays, 12 edge arrays, 5 pair arrays, 12 target arrays
+  return (size_t)(Nv * BV + Ne * BE + Np * BP + (T + 1) * BT) + ALIGN * 48;
+}
+
+template <typename T_>
+static T_* take(char*& cur, int64_t count) {
+  T_* p = reinterpret_cast<T_*>(cur);
+  cur += align_up((size_t)count * sizeof(T_));
+  return p;
+}
+
+static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, const int32_t* d_targets) {
+  ChunkView c{};
+  char* cur = arena;
+  const int64_t Np = Nv + Ne + T;
+  c.T = (int32_t)T;
+  c.tgt = d_targets;
+  c.tidx = take<int64_t>(cur, T);
+  c.voff = take<int64_t>(cur, T + 1);
+  c.eoff = take<int64_t>(cur, T + 1);
+  c.tn = take<int32_t>(cur, T); c.tm = take<int32_t>(cur, T); c.tlu = take<int32_t>(cur, T); c.tlv = take<int32_t>(cur, T);
+  c.tnp = take<int32_t>(cur, T); c.tnpos = take<int32_t>(cur, T); c.tnneg = take<int32_t>(cur, T); c.tncls = take<int32_t>(cur, T);
+  c.tstatus = take<uint8_t>(cur, T);
+  c.vert = take<int32_t>(cur, Nv); c.vcls = take<int32_t>(cur, Nv); c.vs0 = take<int32_t>(cur, Nv);
+  c.vs1 = take<int32_t>(cur, Nv); c.vs2 = take<int32_t>(cur, Nv); c.neg = take<int32_t>(cur, Nv);
+  c.fval = take<double>(cur, Nv); c.d1 = take<double>(cur, Nv); c.d2 = take<double>(cur, Nv);
+  c.v64a = take<unsigned long long>(cur, Nv); c.v64b = take<unsigned long long>(cur, Nv);
+  c.v64c = take<unsigned long long>(cur, Nv);
+  c.elo = take<int32_t>(cur, Ne); c.ehi = take<int32_t>(cur, Ne); c.pos = take<int32_t>(cur, Ne);
+  c.arank = take<int32_t>(cur, Ne);
+  c.ew = take<double>(cur, Ne);
+  c.ord_asc = take<uint32_t>(cur, Ne); c.ord_desc = take<uint32_t>(cur, Ne);
+  c.sp0 = take<uint32_t>(cur, Ne); c.sp1 = take<uint32_t>(cur, Ne);
+  c.sk0 = take<unsigned long long>(cur, Ne); c.sk1 = take<unsigned long long>(cur, Ne);
+  c.isneg = take<uint8_t>(cur, Ne);
+  c.pkind = take<uint8_t>(cur, Np);
+  c.pbv = take<int32_t>(cur, Np); c.pdv = take<int32_t>(cur, Np);
+  c.pbirth = take<double>(cur, Np); c.pdeath = take<double>(cur, Np);
+  return c;
+}
+
+static int block_for(int64_t m_max) {
+  if (m_max >= 32768) return 512;
+  if (m_max >= 4096) return 256;
+  if (m_max >= 512) return 128;
+  if (m_max >= 96) return 64;
+  return 32;
+}
+static int size_class(int64_t m) { return block_for(m); }
+
+struct StageTimer {
+  bool on;
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> stage;
+  explicit StageTimer(bool on_, cudaStream_t s) : on(on_), st(s) {}
+  void mark(int stage_id) {  // marks the START of stage_id (or the end marker with id -1)
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    stage.push_back(stage_id);
+  }
+  void collect(double* ms8) {
+    if (!on) return;
+    for (size_t i = 0; i + 1 < ev.size(); i++) {
+      if (stage[i] < 0) continue;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      ms8[stage[i]] += ms;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+    stage.clear();
+  }
+};
+
+// run the stage kernels over one carved chunk (offsets already uploaded)
+static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_t n_max, int64_t m_max, double* d_pi,
+                       float* d_pi32, uint8_t* d_status, bool want_lists, StageTimer& tm) {
+  cudaStream_t st = g->stream;
+  const int block = block_for(m_max);
+  VicinityScratch vs{g->bitmaps, g->queue, g->vic_grid};
+  tm.mark(1);
+  launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
+  tm.mark(2);
+  launch_filtration(p, c, block, st);
+  tm.mark(3);
+  launch_sort(p, c, block, st);
+  tm.mark(4);
+  const bool ext = (p.flags & TLC_F_EXTENDED) != 0;
+  const int64_t uf_ints = 2 * n_max * 4 <= 96 * 1024 ? 2 * n_max : 0;
+  launch_union_find(p, c, block, (int)uf_ints, (ext || want_lists) ? 1 : 0, st);
+  tm.mark(5);
+  if (ext) {
+    const int64_t lp_ints = 3 * n_max * 4 <= 200 * 1024 ? 3 * n_max : 0;
+    launch_loops(p, c, std::min(block, 128), (int)lp_ints, st);
+  }
+  tm.mark(6);
+  launch_pimg(p, c, d_pi, d_pi32, d_status, std::max(32, std::min(block, 256)), st);
+  tm.mark(-1);
+}
+
+static int check_params(const tlc_params* p) {
+  if (!p) return fail(TLC_E_INVALID, "params is NULL");
+  if (p->resolution < 1 || p->resolution > 16) return fail(TLC_E_INVALID, "resolution must be in 1..16");
+  if (p->hop < 0) return fail(TLC_E_INVALID, "hop must be >= 0");
+  if (p->mode != TLC_MODE_EDGE && p->mode != TLC_MODE_NODE) return fail(TLC_E_INVALID, "bad mode");
+  return TLC_OK;
+}
+
+// the whole path over device-resident targets.  detail != NULL: single chunk in input order, every
+// intermediate copied back to host.
+static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const tlc_params* up, double* d_pi,
+                        float* d_pi32, uint8_t* d_status, int64_t* cnt_compute, tlc_detail* detail) {
+  int rc = check_params(up);
+  if (rc) return rc;
+  if (E < 0) return fail(TLC_E_INVALID, "E < 0");
+  CK(cudaSetDevice(g->device));
+  Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
+  const int r2 = p.resolution * p.resolution;
+  cudaStream_t st = g->stream;
+  for (int i = 0; i < 8; i++) g->stage_ms[i] = 0;
+  g->nchunks = 0;
+  g->alg_bytes = g->alg_bytes_bfs = g->alg_bytes_uf = 0;
+  if (cnt_compute) *cnt_compute = 0;
+  if (E == 0) return TLC_OK;
+  const bool bad_desc = p.descriptor < 0 || p.descriptor > 2;
+
+  if ((rc = ensure_call_buffers(g, E))) return rc;
+  if ((rc = ensure_vicinity_scratch(g, p))) return rc;
+  const char* tenv = getenv("TLC_STAGE_TIMING");
+  g->timing = tenv && atoi(tenv) != 0;
+  StageTimer tm(g->timing, st);
+  cudaEvent_t ev_total0 = nullptr, ev_total1 = nullptr;
+  if (g->timing) { cudaEventCreate(&ev_total0); cudaEventCreate(&ev_total1); cudaEventRecord(ev_total0, st); }
+
+  // ---- kernel 1, counting pass ----
+  VicinityScratch vs{g->bitmaps, g->queue, g->vic_grid};
+  tm.mark(0);
+  launch_vicinity_sizes(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_st, g->d_bytes, vs, g->work_counter, st);
+  tm.mark(-1);
+  const size_t pin_need = align_up((size_t)E * 8) + (size_t)E * 9 + ALIGN;
+  if ((rc = ensure_pinned(g, align_up(pin_need) + (size_t)(E + 2) * 8 * 3 + ALIGN))) return rc;
+  int32_t* h_n = reinterpret_cast<int32_t*>(g->h_pin);
+  int32_t* h_m = h_n + E;
+  double* h_bytes = reinterpret_cast<double*>(g->h_pin + align_up((size_t)E * 8));
+  uint8_t* h_st = reinterpret_cast<uint8_t*>(h_bytes + E);
+  char* h_chunk = g->h_pin + align_up(pin_need);  // [tidx | voff | eoff] staging, (E+2)*8 each
+  CK(cudaMemcpyAsync(h_n, g->d_n, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_m, g->d_m, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_st, g->d_st, (size_t)E, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_bytes, g->d_bytes, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
+  // rows of targets that never reach the image kernel stay zero (riccidist2dgm.py:363)
+  CK(cudaMemsetAsync(d_pi, 0, (size_t)E * r2 * sizeof(double), st));
+  if (d_pi32) CK(cudaMemsetAsync(d_pi32, 0, (size_t)E * r2 * sizeof(float), st));
+  CK(cudaStreamSynchronize(st));
+  if (bad_desc) {  // KeyError in perturb_filter_function for every target that got that far (accelerated_PD.py:13)
+    for (int64_t i = 0; i < E; i++) if (h_st[i] == TLC_ST_OK) h_st[i] = TLC_ST_BAD_DESCRIPTOR;
+    if (d_status) CK(cudaMemcpyAsync(d_status, h_st, (size_t)E, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return TLC_OK;
+  }
+  if (d_status) CK(cudaMemcpyAsync(d_status, g->d_st, (size_t)E, cudaMemcpyDeviceToDevice, st));
+  for (int64_t i = 0; i < E; i++) g->alg_bytes += h_st[i] == TLC_ST_OK ? h_bytes[i] : 0.0;
+
+  // ---- plan chunks ----
+  std::vector<int64_t> order;
+  order.reserve(E);
+  if (detail) {
+    for (int64_t i = 0; i < E; i++) order.push_back(i);
+  } else {
+    for (int64_t i = 0; i < E; i++) if (h_st[i] == TLC_ST_OK) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      if (h_m[a] != h_m[b]) return h_m[a] > h_m[b];
+      return h_n[a] > h_n[b];
+    });
+  }
+  int64_t need_one = 0;
+  for (int64_t i : order) need_one = std::max<int64_t>(need_one, (int64_t)chunk_bytes(1, h_n[i], h_m[i]));
+  if (detail) {
+    int64_t Nv = 0, Ne = 0;
+    for (int64_t i : order) { Nv += h_n[i]; Ne += h_m[i]; }
+    need_one = (int64_t)chunk_bytes(E, Nv, Ne);
+    if (Nv > detail->cap_v || Ne > detail->cap_e || Nv + Ne + E > detail->cap_p)
+      return fail(TLC_E_CAPACITY, "detail capacity too small: need v=" + std::to_string(Nv) + " e=" +
+                                      std::to_string(Ne) + " p=" + std::to_string(Nv + Ne + E));
+  }
+  if ((rc = ensure_arena(g, (size_t)need_one))) return rc;
+
+  const int64_t max_T = 1 << 16;
+  size_t pos = 0;
+  int64_t* h_tidx = reinterpret_cast<int64_t*>(h_chunk);
+  int64_t* h_voff = h_tidx + (E + 2);
+  int64_t* h_eoff = h_voff + (E + 2);
+  while (pos < order.size()) {
+    // greedy pack: same size class, fits the arena
+    int64_t T = 0, Nv = 0, Ne = 0, n_max = 0, m_max = 0;
+    const int cls0 = size_class(h_m[order[pos]]);
+    size_t q = pos;
+    while (q < order.size() && T < max_T) {
+      const int64_t i = order[q];
+      if (!detail && size_class(h_m[i]) != cls0) break;
+      if (chunk_bytes(T + 1, Nv + h_n[i], Ne + h_m[i]) > g->arena_bytes) break;
+      // the staging buffers of a chunk are reused: wait for the previous chunk's upload (stream order suffices,
+      // the pinned region of this chunk is [pos, q) which no earlier chunk touches)
+      h_tidx[q] = i; h_voff[q] = Nv; h_eoff[q] = Ne;
+      Nv += h_n[i]; Ne += h_m[i];
+      n_max = std::max<int64_t>(n_max, h_n[i]); m_max = std::max<int64_t>(m_max, h_m[i]);
+      T++; q++;
+    }
+    if (T == 0) return fail(TLC_E_NOMEM, "a vicinity does not fit the arena");
+    ChunkView c = carve(g->arena, T, Nv, Ne, d_targets);
+    // offsets: [pos, pos+T) plus the terminating total.  voff/eoff need T+1 entries; the terminator is
+    // written into a separate tiny pinned slot so that the next chunk's slot `q` is not clobbered.
+    CK(cudaMemcpyAsync((void*)c.tidx, h_tidx + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)c.voff, h_voff + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)c.eoff, h_eoff + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)(c.voff + T), &Nv, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)(c.eoff + T), &Ne, 8, cudaMemcpyHostToDevice, st));
+    run_stages(g, p, c, n_max, m_max, d_pi, d_pi32, d_status, detail != nullptr, tm);
+    g->nchunks++;
+    if (detail) {
+      // copy every intermediate back (input order == chunk order here)
+      CK(cudaStreamSynchronize(st));
+#define D2H(dst, src, count, type) \
+  if (detail->dst) CK(cudaMemcpy(detail->dst, src, (size_t)(count) * sizeof(type), cudaMemcpyDeviceToHost))
+      D2H(n, c.tn, T, int32_t); D2H(m, c.tm, T, int32_t); D2H(lu, c.tlu, T, int32_t); D2H(lv, c.tlv, T, int32_t);
+      D2H(npairs, c.tnp, T, int32_t); D2H(npos, c.tnpos, T, int32_t); D2H(nneg, c.tnneg, T, int32_t);
+      D2H(vert, c.vert, Nv, int32_t); D2H(fval, c.fval, Nv, double); D2H(neg, c.neg, Nv, int32_t);
+      D2H(elo, c.elo, Ne, int32_t); D2H(ehi, c.ehi, Ne, int32_t); D2H(ew, c.ew, Ne, double);
+      D2H(ord_asc, c.ord_asc, Ne, int32_t); D2H(ord_desc, c.ord_desc, Ne, int32_t); D2H(pos, c.pos, Ne, int32_t);
+      D2H(pbv, c.pbv, Nv + Ne + T, int32_t); D2H(pdv, c.pdv, Nv + Ne + T, int32_t);
+      D2H(pbirth, c.pbirth, Nv + Ne + T, double); D2H(pdeath, c.pdeath, Nv + Ne + T, double);
+#undef D2H
+      if (detail->pkind) {
+        std::vector<uint8_t> k8((size_t)(Nv + Ne + T));
+        CK(cudaMemcpy(k8.data(), c.pkind, k8.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < k8.size(); i++) detail->pkind[i] = k8[i];
+      }
+      for (int64_t t = 0; t <= T; t++) {
+        const int64_t vo = t < T ? h_voff[pos + t] : Nv, eo = t < T ? h_eoff[pos + t] : Ne;
+        if (detail->voff) detail->voff[t] = vo;
+        if (detail->eoff) detail->eoff[t] = eo;
+        if (detail->poff) detail->poff[t] = vo + eo + t;
+      }
+    } else {
+      // Nv / Ne are stack variables read by the async copies above
+      CK(cudaStreamSynchronize(st));
+    }
+    pos = q;
+  }
+  if (g->timing) {
+    cudaEventRecord(ev_total1, st);
+    cudaStreamSynchronize(st);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_total0, ev_total1);
+    g->stage_ms[7] = ms;
+    tm.collect(g->stage_ms);
+    cudaEventDestroy(ev_total0);
+    cudaEventDestroy(ev_total1);
+  }
+  // cnt_compute: targets whose image row was really computed (riccidist2dgm.py:354)
+  if (cnt_compute || (detail && detail->status)) {
+    if (d_status) {
+      CK(cudaMemcpyAsync(h_st, d_status, (size_t)E, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      int64_t cnt = 0;
+      for (int64_t i = 0; i < E; i++) cnt += h_st[i] <= TLC_ST_TRIVIAL;
+      if (cnt_compute) *cnt_compute = cnt;
+      if (detail && detail->status) memcpy(detail->status, h_st, (size_t)E);
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  return TLC_OK;
+}
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+const char* tlc_last_error(void) { return g_err.c_str(); }
+const char* tlc_version(void) { return "tlc_b200 0.1 (sm_100a)"; }
+int64_t tlc_launch_count(void) { return launch_count(); }
+
+int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_t* col, const double* kappa, int device,
+                     uint64_t arena_bytes, tlc_graph** out) {
+  if (!out || !rowptr || (nnz > 0 && (!col || !kappa)) || N <= 0 || nnz < 0) return fail(TLC_E_INVALID, "bad graph arguments");
+  if (rowptr[0] != 0 || rowptr[N] != nnz) return fail(TLC_E_INVALID, "rowptr[0] != 0 or rowptr[N] != nnz");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(TLC_E_INVALID, "device index out of range");
+  CK(cudaSetDevice(device));
+  tlc_graph* g = new tlc_graph();
+  g->device = device;
+  g->arena_req = (size_t)arena_bytes;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  g->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  int32_t *d_rowptr = nullptr, *d_col = nullptr;
+  double* d_kappa = nullptr;
+  CK(cudaMalloc((void**)&d_rowptr, (size_t)(N + 1) * 4));
+  CK(cudaMalloc((void**)&d_col, std::max<size_t>((size_t)nnz * 4, 16)));
+  CK(cudaMalloc((void**)&d_kappa, std::max<size_t>((size_t)nnz * 8, 16)));
+  CK(cudaMemcpy(d_rowptr, rowptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice));
+  if (nnz) {
+    CK(cudaMemcpy(d_col, col, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_kappa, kappa, (size_t)nnz * 8, cudaMemcpyHostToDevice));
+  }
+  g->gv = GraphView{N, nnz, d_rowptr, d_col, d_kappa};
+  CK(cudaMalloc((void**)&g->work_counter, 64));
+  *out = g;
+  return TLC_OK;
+}
+
+int tlc_graph_destroy(tlc_graph* g) {
+  if (!g) return TLC_OK;
+  cudaSetDevice(g->device);
+  cudaFree((void*)g->gv.rowptr); cudaFree((void*)g->gv.col); cudaFree((void*)g->gv.kappa);
+  cudaFree(g->arena); cudaFree(g->bitmaps); cudaFree(g->queue); cudaFree(g->work_counter);
+  cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_st); cudaFree(g->d_bytes);
+  if (g->h_pin) cudaFreeHost(g->h_pin);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+  return TLC_OK;
+}
+
+int tlc_vicinity_pi_dev(tlc_graph* g, const int32_t* dev_targets, int64_t E, const tlc_params* p, double* dev_out_pi,
+                        float* dev_out_pi_f32, uint8_t* dev_out_status, int64_t* cnt_compute) {
+  if (!g || (E > 0 && (!dev_targets || !dev_out_pi))) return fail(TLC_E_INVALID, "NULL argument");
+  uint8_t* st = dev_out_status;
+  uint8_t* tmp = nullptr;
+  if (!st && cnt_compute && E > 0) { CK(cudaSetDevice(g->device)); CK(cudaMalloc((void**)&tmp, (size_t)E)); st = tmp; }
+  const int rc = run_pipeline(g, dev_targets, E, p, dev_out_pi, dev_out_pi_f32, st, cnt_compute, nullptr);
+  if (tmp) cudaFree(tmp);
+  return rc;
+}
+
+int tlc_vicinity_pi(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_params* p, double* out_pi,
+                    uint8_t* out_status, int64_t* cnt_compute) {
+  if (!g || (E > 0 && (!targets || !out_pi))) return fail(TLC_E_INVALID, "NULL argument");
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (cnt_compute) *cnt_compute = 0;
+  if (E == 0) return TLC_OK;
+  CK(cudaSetDevice(g->device));
+  const int r2 = p->resolution * p->resolution;
+  int32_t* d_t = nullptr;
+  double* d_pi = nullptr;
+  uint8_t* d_st = nullptr;
+  CK(cudaMalloc((void**)&d_t, (size_t)E * 8));
+  CK(cudaMalloc((void**)&d_pi, (size_t)E * r2 * 8));
+  CK(cudaMalloc((void**)&d_st, (size_t)E));
+  CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
+  rc = run_pipeline(g, d_t, E, p, d_pi, nullptr, d_st, cnt_compute, nullptr);
+  if (rc == TLC_OK) {
+    cudaError_t e1 = cudaMemcpyAsync(out_pi, d_pi, (size_t)E * r2 * 8, cudaMemcpyDeviceToHost, g->stream);
+    cudaError_t e2 = out_status ? cudaMemcpyAsync(out_status, d_st, (size_t)E, cudaMemcpyDeviceToHost, g->stream) : cudaSuccess;
+    cudaError_t e3 = cudaStreamSynchronize(g->stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail(TLC_E_CUDA, "copy back failed");
+  }
+  cudaFree(d_t); cudaFree(d_pi); cudaFree(d_st);
+  return rc;
+}
+
+int tlc_vicinity_sizes(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_params* up, int32_t* out_n,
+                       int32_t* out_m, uint8_t* out_status) {
+  if (!g || (E > 0 && !targets)) return fail(TLC_E_INVALID, "NULL argument");
+  int rc = check_params(up);
+  if (rc) return rc;
+  if (E == 0) return TLC_OK;
+  CK(cudaSetDevice(g->device));
+  Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
+  if ((rc = ensure_call_buffers(g, E))) return rc;
+  if ((rc = ensure_vicinity_scratch(g, p))) return rc;
+  int32_t* d_t = nullptr;
+  CK(cudaMalloc((void**)&d_t, (size_t)E * 8));
+  CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
+  VicinityScratch vs{g->bitmaps, g->queue, g->vic_grid};
+  launch_vicinity_sizes(g->gv, p, d_t, E, g->d_n, g->d_m, g->d_st, g->d_bytes, vs, g->work_counter, g->stream);
+  if (out_n) CK(cudaMemcpyAsync(out_n, g->d_n, (size_t)E * 4, cudaMemcpyDeviceToHost, g->stream));
+  if (out_m) CK(cudaMemcpyAsync(out_m, g->d_m, (size_t)E * 4, cudaMemcpyDeviceToHost, g->stream));
+  if (out_status) CK(cudaMemcpyAsync(out_status, g->d_st, (size_t)E, cudaMemcpyDeviceToHost, g->stream));
+  CK(cudaStreamSynchronize(g->stream));
+  cudaFree(d_t);
+  CK(cudaGetLastError());
+  return TLC_OK;
+}
+
+int tlc_vicinity_detail(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_params* p, tlc_detail* out) {
+  if (!g || !out || (E > 0 && !targets)) return fail(TLC_E_INVALID, "NULL argument");
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (E == 0) return TLC_OK;
+  CK(cudaSetDevice(g->device));
+  const int r2 = p->resolution * p->resolution;
+  int32_t* d_t = nullptr;
+  double* d_pi = nullptr;
+  uint8_t* d_st = nullptr;
+  CK(cudaMalloc((void**)&d_t, (size_t)E * 8));
+  CK(cudaMalloc((void**)&d_pi, (size_t)E * r2 * 8));
+  CK(cudaMalloc((void**)&d_st, (size_t)E));
+  CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
+  int64_t cnt = 0;
+  rc = run_pipeline(g, d_t, E, p, d_pi, nullptr, d_st, &cnt, out);
+  if (rc == TLC_OK && out->pi) {
+    if (cudaMemcpy(out->pi, d_pi, (size_t)E * r2 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(TLC_E_CUDA, "copy back failed");
+  }
+  cudaFree(d_t); cudaFree(d_pi); cudaFree(d_st);
+  return rc;
+}
+
+int tlc_union_find(int device, int32_t n, int32_t m, const double* fval, const int32_t* a, const int32_t* b, uint32_t flags,
+                   int32_t* npairs, int32_t* pkind, int32_t* pbv, int32_t* pdv, double* pbirth, double* pdeath,
+                   int32_t* npos, int32_t* pos, int32_t* nneg, int32_t* neg, uint8_t* status) {
+  if (n <= 0 || m < 0 || !fval || (m > 0 && (!a || !b))) return fail(TLC_E_INVALID, "bad arguments");
+  for (int32_t i = 0; i < m; i++)
+    if (a[i] < 0 || a[i] >= n || b[i] < 0 || b[i] >= n) return fail(TLC_E_INVALID, "edge endpoint out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
+  CK(cudaSetDevice(device));
+  char* arena = nullptr;
+  const size_t bytes = chunk_bytes(1, n, m);
+  CK(cudaMalloc((void**)&arena, bytes));
+  ChunkView c = carve(arena, 1, n, m, nullptr);
+  cudaStream_t st = nullptr;  // legacy default stream: the plain cudaMemcpy calls below order with it
+  const int64_t zero = 0, nv = n, ne = m;
+  const int32_t one_n = n, one_m = m, z32 = 0;
+  const uint8_t st_ok = TLC_ST_OK;
+  CK(cudaMemcpy((void*)c.tidx, &zero, 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy((void*)c.voff, &zero, 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy((void*)(c.voff + 1), &nv, 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy((void*)c.eoff, &zero, 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy((void*)(c.eoff + 1), &ne, 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c.tn, &one_n, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c.tm, &one_m, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c.tnp, &z32, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c.tnpos, &z32, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c.tnneg, &z32, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c.tstatus, &st_ok, 1, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c.fval, fval, (size_t)n * 8, cudaMemcpyHostToDevice));
+  if (m) {
+    CK(cudaMemcpy(c.elo, a, (size_t)m * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.ehi, b, (size_t)m * 4, cudaMemcpyHostToDevice));
+  }
+  Params p{0, TLC_MODE_NODE, TLC_DESC_SUM, 5, flags, 0};
+  const int block = block_for(m);
+  launch_sort(p, c, block, st);
+  const int64_t uf_ints = 2 * (int64_t)n * 4 <= 96 * 1024 ? 2 * (int64_t)n : 0;
+  launch_union_find(p, c, block, (int)uf_ints, 1, st);
+  if (flags & TLC_F_EXTENDED) {
+    const int64_t lp_ints = 3 * (int64_t)n * 4 <= 200 * 1024 ? 3 * (int64_t)n : 0;
+    launch_loops(p, c, std::min(block, 128), (int)lp_ints, st);
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  int32_t h_np = 0, h_npos = 0, h_nneg = 0;
+  uint8_t h_st = 0;
+  CK(cudaMemcpy(&h_np, c.tnp, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&h_npos, c.tnpos, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&h_nneg, c.tnneg, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&h_st, c.tstatus, 1, cudaMemcpyDeviceToHost));
+  if (npairs) *npairs = h_np;
+  if (npos) *npos = h_npos;
+  if (nneg) *nneg = h_nneg;
+  if (status) *status = h_st;
+  if (h_np > 0) {
+    if (pkind) {
+      std::vector<uint8_t> k8((size_t)h_np);
+      CK(cudaMemcpy(k8.data(), c.pkind, (size_t)h_np, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < h_np; i++) pkind[i] = k8[i];
+    }
+    if (pbv) CK(cudaMemcpy(pbv, c.pbv, (size_t)h_np * 4, cudaMemcpyDeviceToHost));
+    if (pdv) CK(cudaMemcpy(pdv, c.pdv, (size_t)h_np * 4, cudaMemcpyDeviceToHost));
+    if (pbirth) CK(cudaMemcpy(pbirth, c.pbirth, (size_t)h_np * 8, cudaMemcpyDeviceToHost));
+    if (pdeath) CK(cudaMemcpy(pdeath, c.pdeath, (size_t)h_np * 8, cudaMemcpyDeviceToHost));
+  }
+  if (pos && h_npos > 0) CK(cudaMemcpy(pos, c.pos, (size_t)h_npos * 4, cudaMemcpyDeviceToHost));
+  if (neg && h_nneg > 0) CK(cudaMemcpy(neg, c.neg, (size_t)h_nneg * 4, cudaMemcpyDeviceToHost));
+  cudaFree(arena);
+  return TLC_OK;
+}
+
+int tlc_pimg_transform(int device, const double* dgm, int64_t K, int32_t resolution, double* out) {
+  if (!out || (K > 0 && !dgm) || resolution < 1 || resolution > 16) return fail(TLC_E_INVALID, "bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
+  CK(cudaSetDevice(device));
+  double *d_dgm = nullptr, *d_out = nullptr;
+  CK(cudaMalloc((void**)&d_dgm, std::max<size_t>((size_t)K * 16, 16)));
+  CK(cudaMalloc((void**)&d_out, (size_t)resolution * resolution * 8));
+  if (K) CK(cudaMemcpy(d_dgm, dgm, (size_t)K * 16, cudaMemcpyHostToDevice));
+  launch_pimg_single(d_dgm, K, resolution, d_out, nullptr);
+  CK(cudaMemcpy(out, d_out, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost));
+  CK(cudaGetLastError());
+  cudaFree(d_dgm); cudaFree(d_out);
+  return TLC_OK;
+}
+
+int tlc_last_stage_ms(tlc_graph* g, double* out8) {
+  if (!g || !out8) return 0;
+  for (int i = 0; i < 8; i++) out8[i] = g->stage_ms[i];
+  return g->nchunks;
+}
+
+int tlc_last_algorithmic_bytes(tlc_graph* g, double* bytes_total, double* bytes_bfs, double* bytes_uf) {
+  if (!g) return TLC_E_INVALID;
+  if (bytes_total) *bytes_total = g->alg_bytes;
+  if (bytes_bfs) *bytes_bfs = g->alg_bytes_bfs;
+  if (bytes_uf) *bytes_uf = g->alg_bytes_uf;
+  return TLC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// tlc_common.cuh -- shared device-side definitions for the sm_100a kernels of the vicinity
+// persistence path.  One CTA ("team") works on one target at a time; every per-target array lives in
+// a chunk arena in HBM (SoA, addressed through per-target offsets), hot per-vertex state is staged in
+// shared memory when it fits.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tlc_b200.h"
+
+namespace tlc {
+
+struct GraphView {
+  int32_t N;
+  int64_t nnz;
+  const int32_t* rowptr;  // [N+1]
+  const int32_t* col;     // [nnz] ascending per row
+  const double* kappa;    // [nnz]
+};
+
+// All device pointers of one chunk of targets.  Vertex-indexed arrays are addressed at voff[t],
+// edge-indexed ones at eoff[t], pair arrays at poff(t) = voff[t] + eoff[t] + t (capacity n+m+1).
+struct ChunkView {
+  int32_t T;
+  const int32_t* tgt;   // [T][2] graph ids
+  const int64_t* tidx;  // [T] row in the caller's output
+  const int64_t* voff;  // [T+1]
+  const int64_t* eoff;  // [T+1]
+  int32_t *tn, *tm, *tlu, *tlv, *tnp, *tnpos, *tnneg, *tncls;
+  uint8_t* tstatus;
+  // vertex-indexed
+  int32_t *vert, *vcls, *vs0, *vs1, *vs2, *neg;
+  double *fval, *d1, *d2;
+  unsigned long long *v64a, *v64b, *v64c;
+  // edge-indexed
+  int32_t *elo, *ehi, *pos, *arank;
+  double* ew;
+  uint32_t *ord_asc, *ord_desc, *sp0, *sp1;
+  unsigned long long *sk0, *sk1;
+  uint8_t* isneg;
+  // pair-indexed
+  uint8_t* pkind;
+  int32_t *pbv, *pdv;
+  double *pbirth, *pdeath;
+  __host__ __device__ int64_t poff(int t) const { return voff[t] + eoff[t] + t; }
+};
+
+struct Params {
+  int32_t hop, mode, descriptor, resolution;
+  uint32_t flags, img_mask;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// order-preserving map double -> u64 (all finite values, -0 < +0 irrelevant here)
+__device__ __forceinline__ unsigned long long f64_to_ordered(double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// block-wide exclusive scan of `n` ints in (global or shared) memory, in place; returns the total.
+// Each thread owns a contiguous slice; `sh` needs blockDim.x + 1 ints.  All threads must call.
+__device__ inline int block_exclusive_scan(int32_t* data, int n, int32_t* sh) {
+  const int nt = blockDim.x, tid = threadIdx.x;
+  const int per = (n + nt - 1) / nt;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  int s = 0;
+  for (int i = lo; i < hi; i++) s += data[i];
+  sh[tid] = s;
+  __syncthreads();
+  // Hillis-Steele over nt entries (nt <= 1024)
+  for (int off = 1; off < nt; off <<= 1) {
+    int v = (tid >= off) ? sh[tid - off] : 0;
+    __syncthreads();
+    sh[tid] += v;
+    __syncthreads();
+  }
+  int total = sh[nt - 1];
+  int run = sh[tid] - s;  // exclusive prefix of this thread's slice
+  __syncthreads();
+  for (int i = lo; i < hi; i++) {
+    int v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  __syncthreads();
+  return total;
+}
+
+__device__ inline int block_reduce_sum(int v, int32_t* sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane_id() == 0) sh[w] = v;
+  __syncthreads();
+  int t = 0;
+  for (int i = 0; i < nw; i++) t += sh[i];
+  __syncthreads();
+  return t;
+}
+
+__device__ inline double block_reduce_max(double v, double* sh) {
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane_id() == 0) sh[w] = v;
+  __syncthreads();
+  double t = sh[0];
+  for (int i = 1; i < nw; i++) t = fmax(t, sh[i]);
+  __syncthreads();
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (defined in the k*.cu files), all asynchronous on `st`
+// ---------------------------------------------------------------------------------------------
+struct VicinityScratch {
+  uint32_t* bitmaps;  // global fallback: [grid][2*W] words when the bitmaps do not fit shared memory
+  int32_t* queue;     // [grid][2*N] frontier queues, only for hop > 2
+  int grid;
+};
+
+void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
+                           int32_t* out_m, uint8_t* out_status, double* out_bytes, const VicinityScratch& vs,
+                           int* work_counter, cudaStream_t st);
+void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
+                          int* work_counter, cudaStream_t st);
+void launch_filtration(const Params& p, const ChunkView& c, int block, cudaStream_t st);
+void launch_sort(const Params& p, const ChunkView& c, int block, cudaStream_t st);
+void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_ints, int build_lists, cudaStream_t st);
+void launch_loops(const Params& p, const ChunkView& c, int block, int smem_ints, cudaStream_t st);
+void launch_pimg(const Params& p, const ChunkView& c, double* out_pi, float* out_pi_f32, uint8_t* out_status,
+                 int block, cudaStream_t st);
+void launch_pimg_single(const double* dgm, int64_t K, int res, double* out, cudaStream_t st);
+
+int64_t launch_count();
+void count_launch();
+int vicinity_grid(int device, const GraphView& g, const Params& p, size_t* bitmap_words, bool* use_smem);
+
+}  // namespace tlc
