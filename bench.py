@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- vicinity PDs + persistence images per second (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (config.workload): Computers-shaped synthetic graph (13,752 nodes / 245,861 edges, seeded
+Chung-Lu, curvature on a 1/1024 grid), target = graph edges, 2-hop vicinity, descriptor 'sum',
+norm=True, 5x5 image -- BASELINE.json configs[2], the configuration the north_star target is quoted on.
+One step = one pass of the hot path over a batch of `--batch` targets PER GPU (weak scaling: every
+rank takes its own disjoint batch of a seeded permutation of the edge list; a new batch every step, so
+nothing is reused between steps and the per-step working set (GBs of per-vicinity arrays) >> L2).
+
+value : targets/s, inputs (target ids) resident in HBM, CUDA events on the library's stream around the
+        K timed steps, max over ranks.  N > 1 adds the NCCL all-gather of the fp32 image rows.
+e2e   : the same through the reference-facing call (sg2dgm.riccidist2dgm.graph2pi.get_pimg_for_all_edges:
+        host target list in, float64 pi_sg on the host out), host<->device copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tlc-gnn_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "vicinity_pd_pi_per_sec"
+UNIT = "targets/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("TLC_BENCH_BATCH", "1024")))
+    ap.add_argument("--workload", default=os.environ.get("TLC_BENCH_WORKLOAD", "computers"))
+    ap.add_argument("--hop", type=int, default=2)
+    ap.add_argument("--extended", type=int, default=int(os.environ.get("TLC_BENCH_EXTENDED", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def make_workload(name):
+    from tlc_b200 import graphgen as gg
+    c = gg.make_config(name)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    perm = np.random.default_rng(300 + gg.SHAPES[name][0]).permutation(len(ne))
+    return c, labels, ne, csr, perm
+
+
+def batch_targets(ne, perm, step, rank, world, batch):
+    """disjoint per (step, rank) slices of a seeded permutation of the edge list (wraps around)."""
+    start = ((step * world + rank) * batch) % len(perm)
+    idx = perm[np.arange(start, start + batch) % len(perm)]
+    return np.ascontiguousarray(ne[idx].astype(np.int32))
+
+
+def config_dict(args, world):
+    from tlc_b200 import graphgen as gg
+    _, N, M, _, _ = gg.SHAPES[args.workload]
+    return {"workload": "%s-shaped synthetic graph (%d nodes, %d edges), %d-hop edge vicinities, descriptor=sum, "
+                        "norm=True, 5x5 image, extended_flag=%s" % (args.workload, N, M, args.hop, bool(args.extended)),
+            "targets_per_gpu_per_step": args.batch, "global_targets_per_step": args.batch * world,
+            "kappa": "U(-0.9,0.9) on a 1/1024 grid", "extended_flag": bool(args.extended),
+            "l2": "new targets every step; per-step working set >> L2 (no flush needed)",
+            "parallelism": "targets sharded over %d GPU(s), CSR replicated, NCCL all-gather of fp32 images" % world}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_baseline(csr, ne, perm, args, seconds, nthreads=0, offset=0):
+    """the oracle port (oracle/tlc_oracle.c: the reference's algorithm restated in C, 2 shortest-path
+    runs per vicinity instead of 2n) on the host cores, bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    og = orc.OracleGraph(*csr)
+    cores = orc.max_threads() if nthreads <= 0 else nthreads
+    flags = orc.F_NORM | (orc.F_EXTENDED if args.extended else 0)
+    probe = batch_targets(ne, perm, 1000 + offset, 0, 1, max(2 * cores, 8))
+    t0 = time.perf_counter()
+    og.run_batch(probe, hop=args.hop, flags=flags, nthreads=cores)
+    dt = time.perf_counter() - t0
+    rate = len(probe) / dt
+    sample = int(min(max(rate * seconds, len(probe)), 200000))
+    tg = batch_targets(ne, perm, 2000 + offset, 0, 1, sample)
+    t0 = time.perf_counter()
+    r = og.run_batch(tg, hop=args.hop, flags=flags, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d targets of the same workload in %.1f s (C restatement of the reference algorithm, "
+                      "pthreads over targets; fast-oracle filtration: 2 SSSP per vicinity)" % (sample, dt),
+            "seconds": dt, "computed": int(r["cnt_compute"])}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    c, labels, ne, csr, perm = make_workload(args.workload)
+    per_step = max(4.0, min(30.0, 150.0 / max(args.steps + args.warmup, 1)))
+    res = []
+    for s in range(args.warmup + args.steps):
+        b = cpu_baseline(csr, ne, perm, args, per_step, offset=10 * s)
+        if s >= args.warmup:
+            res.append(b)
+    value = float(np.mean([b["value"] for b in res]))
+    secs = float(np.mean([b["seconds"] for b in res]))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": config_dict(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": res[-1]["cores"], "kind": "port",
+                             "sample": res[-1]["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from tlc_b200 import _lib as L
+    from tlc_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["TLC_STAGE_TIMING"] = "1"
+
+    c, labels, ne, csr, perm = make_workload(args.workload)
+    g = api.VicinityGraph(*csr, device=local)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)            # a real (non-default) stream: kernels, NCCL and the timing events share it
+    g.set_stream(stream.cuda_stream)
+    flags = L.F_NORM | (L.F_EXTENDED if args.extended else 0)
+    B, r2 = args.batch, 25
+
+    out_pi = torch.zeros((B, r2), dtype=torch.float64, device=dev)
+    out_f32 = torch.zeros((B, r2), dtype=torch.float32, device=dev)
+    out_st = torch.zeros((B,), dtype=torch.uint8, device=dev)
+    gathered = torch.zeros((world * B, r2), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(s):
+        tg = torch.from_numpy(batch_targets(ne, perm, s, rank, world, B)).to(dev)  # resident before timing
+        return tg
+
+    def run(tg):
+        g.vicinity_pi_dev(tg, out_pi, out_f32, out_st, hop=args.hop, flags=flags)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_f32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batches = [step(s) for s in range(args.warmup + args.steps)]
+    for s in range(args.warmup):
+        run(batches[s])
+    barrier()
+    stage_acc = {}
+    alg_bytes = 0.0
+    launches0 = api.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # library kernels, the all-gather and these events are all on torch's current stream
+    ev0.record()
+    t_wall0 = time.perf_counter()
+    for s in range(args.warmup, args.warmup + args.steps):
+        run(batches[s])
+        ms, _ = g.last_stage_ms()
+        for k, v in ms.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        alg_bytes += g.last_algorithmic_bytes()
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    launches = api.launch_count() - launches0
+    # device time of the K steps (CUDA events on the launching stream), max over ranks
+    dev_ms = float(ev0.elapsed_time(ev1))
+    elapsed = max(dev_ms / 1e3, 1e-9)
+    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_max = float(t.item())
+    value = world * B * args.steps / elapsed_max
+
+    # ---- e2e through the reference-facing API (host in, host out) ----
+    import networkx as nx  # noqa: F401  (the mirror accepts any graph object with nodes()/edges())
+    import sg2dgm.riccidist2dgm as mirror
+
+    g.set_stream(None)
+    gm = mirror.graph2pi.from_csr(*csr, device=local)
+    e2e_batches = [batch_targets(ne, perm, 500 + s, rank, world, B) for s in range(args.steps + 1)]
+    gm.get_pimg_for_all_edges(e2e_batches[0], cores=16, hop=args.hop, norm=True, extended_flag=bool(args.extended),
+                              resolution=5, descriptor="sum")
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        gm.get_pimg_for_all_edges(e2e_batches[1 + s], cores=16, hop=args.hop, norm=True,
+                                  extended_flag=bool(args.extended), resolution=5, descriptor="sum")
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, torch.from_numpy(gm.pi_sg.astype(np.float32)).to(dev))
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        # dominant kernel = the stage with the largest share of device time
+        stages = {k: v for k, v in stage_acc.items() if k != "total"}
+        dom = max(stages, key=stages.get) if stages else "n/a"
+        dom_ms = stages.get(dom, 0.0)
+        achieved = (alg_bytes / 1e9) / max(dom_ms / 1e3, 1e-12)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_target": alg_bytes / max(1, B * args.steps),
+                    "note": "achieved = compulsory bytes of the step's targets (SURVEY.md 8d B_e) / device time of the "
+                            "dominant stage kernel; CSR is L2-resident so this is an efficiency index vs the HBM roof",
+                    "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()},
+                    "whole_path_achieved": (alg_bytes / 1e9) / max(elapsed, 1e-12)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(csr, ne, perm, args, args.cpu_seconds)
+            cpu.pop("seconds", None)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(args, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 8),
+                        "d2h_bytes_per_step": int(B * (r2 * 8 + 1))},
+                "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_cuda(a)

@@ -137,6 +137,10 @@ int tlc_union_find(int device, int32_t n, int32_t m, const double *fval, const i
  * dgm[K][2] (birth, death) float64 -> out[res*res] float64, runs kernel 4 on `device`. */
 int tlc_pimg_transform(int device, const double *dgm, int64_t K, int32_t resolution, double *out);
 
+/* run this graph's kernels on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
+ * graph's own stream).  Lets a host framework order the work with its own (e.g. NCCL) operations. */
+int tlc_graph_set_stream(tlc_graph *g, void *stream);
+
 /* introspection */
 const char *tlc_last_error(void);
 const char *tlc_version(void);
@@ -148,6 +152,10 @@ int64_t tlc_launch_count(void);
 int tlc_last_stage_ms(tlc_graph *g, double *out8);
 /* algorithmic bytes (compulsory bytes B_e) summed over the targets of the last call */
 int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_bfs, double *bytes_uf);
+
+/* totals over the live targets of the last call: out[0] = live targets, out[1] = sum n, out[2] = sum m,
+ * out[3] = chunks */
+int tlc_last_counts(tlc_graph *g, int64_t *out4);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,76 @@
+"""The drop-in `sg2dgm` mirror against the REAL reference's stored outputs (golden fixtures) and against
+its error behaviour; reads like a test the reference could have had (it ships none)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import networkx as nx
+
+from helpers import GRAPH_CASES, load_case, rel_err, seg
+
+
+def build(c):
+    import sg2dgm.riccidist2dgm as r
+    g = nx.Graph()
+    g.add_edges_from([(int(a), int(b)) for a, b in c["edges"]])           # loaddatas.py:88-92
+    ricci = sorted([[int(a), int(b), float(k)] for (a, b), k in zip(c["edges"], c["kappa"])] +
+                   [[int(b), int(a), float(k)] for (a, b), k in zip(c["edges"], c["kappa"])])  # :117-121
+    return r.graph2pi(g, ricci_curv=ricci)
+
+
+@pytest.mark.parametrize("tag", GRAPH_CASES)
+def test_get_pimg_for_all_edges_matches_reference(tag):
+    c = load_case(tag)
+    pi = build(c)
+    for ext in (False, True):
+        pi.get_pimg_for_all_edges([list(map(int, t)) for t in c["targets"]], cores=16, hop=c["hop"], norm=True,
+                                  extended_flag=ext, resolution=5, descriptor=c["descriptor"])   # loaddatas.py:100
+        ref = c["pi_ext%d" % ext]
+        assert pi.pi_sg.shape == ref.shape and pi.pi_sg.dtype == np.float64
+        assert pi.cnt_compute == int(c["cnt_ext%d" % ext])
+        assert rel_err(pi.pi_sg, ref) < 1e-5
+
+
+def test_error_behaviour_toy():
+    c = load_case("toy7_hop2")
+    pi = build(c)
+    dn = pi.dict_node
+    with pytest.raises(AssertionError):
+        pi.sg2dgm_accelerate(dn[0], dn[5], 2, descriptor="sum", norm=True)      # empty vicinity  :318
+    with pytest.raises(KeyError):
+        pi.sg2dgm_accelerate(dn[1], dn[2], 2, norm=True)                        # default descriptor "seal"
+    with pytest.raises(ZeroDivisionError):
+        pi.sg2dgm_accelerate(dn[4], dn[5], 1, descriptor="sum", norm=True)      # vicinity == {u,v}
+    img = pi.sg2dgm_accelerate(dn[1], dn[2], 2, descriptor="sum", norm=True, extended_flag=True)
+    assert img.shape == (5, 5) and abs(img[0, 0] - 0.00780321722227386) < 1e-12
+    z = pi.get_pimg_for_one_edge(0, 99, hop=2, descriptor="sum")                # unknown label -> zeros, no raise
+    assert z.shape == (25,) and not z.any()
+
+
+def test_union_find_and_imager_mirrors():
+    import sg2dgm.accelerated_PD as apd
+    import sg2dgm.PersistenceImager as pimg
+    c = load_case("pubmed_s_hop2_dyadic")
+    for k in range(5):
+        if int(c["stage_ncomp"][k]) != 1:
+            continue
+        nodes = seg(c, "nodes", k)
+        fval = seg(c, "fval", k)
+        neg = seg(c, "neg", k).reshape(-1, 2)
+        pos = seg(c, "pos", k).reshape(-1, 2)
+        # rebuild the canonical vicinity graph the fixture was generated from
+        h = nx.Graph()
+        h.add_nodes_from(int(x) for x in nodes)
+        es = sorted([tuple(sorted(map(int, e))) for e in np.concatenate([neg, pos])])
+        h.add_edges_from(es)
+        for x, f in zip(nodes, fval):
+            h.nodes[int(x)]["sum"] = float(f)
+        sf = apd.perturb_filter_function(h, "sum")
+        PD, Pos, Neg = apd.Union_find(sf)
+        assert np.array_equal(np.array(PD), seg(c, "pd0", k).reshape(-1, 2))
+        assert Pos == pos.tolist() and Neg == neg.tolist()
+        PD1 = apd.Accelerate_PD(Pos, Neg, sf)
+        assert np.array_equal(np.array(PD1).reshape(-1, 2), seg(c, "pd1", k).reshape(-1, 2))
+        img = pimg.PersistenceImager(resolution=5).transform(np.array(PD + PD1))
+        assert img.shape == (5, 5)

@@ -50,7 +50,8 @@ static constexpr size_t BT = 8 * 3 + 4 * 8 + 1;                       // tidx vo
 struct tlc_graph {
   int device = 0;
   GraphView gv{};
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  int64_t last_live = 0, last_nv = 0, last_ne = 0;
   char* arena = nullptr;
   size_t arena_bytes = 0, arena_req = 0;
   // vicinity scratch (depends on hop)
@@ -264,6 +265,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   for (int i = 0; i < 8; i++) g->stage_ms[i] = 0;
   g->nchunks = 0;
   g->alg_bytes = g->alg_bytes_bfs = g->alg_bytes_uf = 0;
+  g->last_live = g->last_nv = g->last_ne = 0;
   if (cnt_compute) *cnt_compute = 0;
   if (E == 0) return TLC_OK;
   const bool bad_desc = p.descriptor < 0 || p.descriptor > 2;
@@ -303,7 +305,8 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     return TLC_OK;
   }
   if (d_status) CK(cudaMemcpyAsync(d_status, g->d_st, (size_t)E, cudaMemcpyDeviceToDevice, st));
-  for (int64_t i = 0; i < E; i++) g->alg_bytes += h_st[i] == TLC_ST_OK ? h_bytes[i] : 0.0;
+  for (int64_t i = 0; i < E; i++)
+    if (h_st[i] == TLC_ST_OK) { g->alg_bytes += h_bytes[i]; g->last_live++; g->last_nv += h_n[i]; g->last_ne += h_m[i]; }
 
   // ---- plan chunks ----
   std::vector<int64_t> order;
@@ -440,7 +443,8 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   g->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking));
+  g->stream = g->own_stream;
   int32_t *d_rowptr = nullptr, *d_col = nullptr;
   double* d_kappa = nullptr;
   CK(cudaMalloc((void**)&d_rowptr, (size_t)(N + 1) * 4));
@@ -464,7 +468,7 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaFree(g->arena); cudaFree(g->bitmaps); cudaFree(g->queue); cudaFree(g->work_counter);
   cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_st); cudaFree(g->d_bytes);
   if (g->h_pin) cudaFreeHost(g->h_pin);
-  if (g->stream) cudaStreamDestroy(g->stream);
+  if (g->own_stream) cudaStreamDestroy(g->own_stream);
   delete g;
   return TLC_OK;
 }
@@ -638,6 +642,18 @@ int tlc_pimg_transform(int device, const double* dgm, int64_t K, int32_t resolut
   CK(cudaMemcpy(out, d_out, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost));
   CK(cudaGetLastError());
   cudaFree(d_dgm); cudaFree(d_out);
+  return TLC_OK;
+}
+
+int tlc_graph_set_stream(tlc_graph* g, void* stream) {
+  if (!g) return fail(TLC_E_INVALID, "NULL graph");
+  g->stream = stream ? (cudaStream_t)stream : g->own_stream;
+  return TLC_OK;
+}
+
+int tlc_last_counts(tlc_graph* g, int64_t* out4) {
+  if (!g || !out4) return TLC_E_INVALID;
+  out4[0] = g->last_live; out4[1] = g->last_nv; out4[2] = g->last_ne; out4[3] = g->nchunks;
   return TLC_OK;
 }
 

@@ -19,7 +19,8 @@ ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NOD
 
 EXPORTS = ["tlc_graph_create", "tlc_graph_destroy", "tlc_vicinity_pi", "tlc_vicinity_pi_dev", "tlc_vicinity_sizes",
            "tlc_vicinity_detail", "tlc_union_find", "tlc_pimg_transform", "tlc_last_error", "tlc_version",
-           "tlc_launch_count", "tlc_last_stage_ms", "tlc_last_algorithmic_bytes"]
+           "tlc_launch_count", "tlc_last_stage_ms", "tlc_last_algorithmic_bytes", "tlc_graph_set_stream",
+           "tlc_last_counts"]
 
 
 class Params(C.Structure):
@@ -82,6 +83,10 @@ def lib():
     L.tlc_last_stage_ms.argtypes = [vp, vp]
     L.tlc_last_algorithmic_bytes.restype = C.c_int
     L.tlc_last_algorithmic_bytes.argtypes = [vp, vp, vp, vp]
+    L.tlc_graph_set_stream.restype = C.c_int
+    L.tlc_graph_set_stream.argtypes = [vp, vp]
+    L.tlc_last_counts.restype = C.c_int
+    L.tlc_last_counts.argtypes = [vp, vp]
     _lib = L
     return L
 

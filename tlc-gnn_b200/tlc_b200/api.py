@@ -139,6 +139,15 @@ class VicinityGraph:
         names = ["sizes", "fill", "filtration", "sort", "union_find", "loops", "image", "total"]
         return dict(zip(names, out.tolist())), int(nch)
 
+    def set_stream(self, cuda_stream_ptr):
+        """run on a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream (None: own stream)."""
+        L.check(L.lib().tlc_graph_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def last_counts(self):
+        out = np.zeros(4, np.int64)
+        L.lib().tlc_last_counts(self._h, out.ctypes.data)
+        return dict(live=int(out[0]), sum_n=int(out[1]), sum_m=int(out[2]), chunks=int(out[3]))
+
     def last_algorithmic_bytes(self):
         tot = C.c_double(0)
         L.lib().tlc_last_algorithmic_bytes(self._h, C.byref(tot), None, None)
