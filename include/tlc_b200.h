@@ -43,6 +43,9 @@ extern "C" {
 #define TLC_F_KEEP_ZERO 4u  /* KD copy: emit zero-persistence pairs      KD/accelerated_PD.py:68-69,108-109,169-170 */
 #define TLC_F_NORM_EPS 8u   /* KD: divide by (max + 1e-10)               KD/data_utils_NC.py:54 */
 #define TLC_F_SUM_PLAIN 16u /* path sums left-to-right (CPython <= 3.11); default Neumaier (CPython >= 3.12 sum()) */
+#define TLC_F_EDGE_SORTED 32u /* ascending sweep by the edge-sorted kernels 2+3 for every target (default: the
+                                 vertex-ordered kernels 2v+3v, which produce the identical pair sequence and hand
+                                 targets they cannot finish to kernels 2+3) -- a test/diagnostic switch */
 
 /* ---- pair kinds, in the reference's concatenation order    accelerated_PD.py:110, riccidist2dgm.py:328 ---- */
 #define TLC_K_UP 0      /* PD_up   : 0-dim ordinary                 accelerated_PD.py:65-66 */
@@ -147,15 +150,16 @@ const char *tlc_version(void);
 /* kernels launched by this library since load (the bench's gpu_launches counter) */
 int64_t tlc_launch_count(void);
 /* per-stage device time of the last tlc_vicinity_pi* call on this graph, ms, summed over chunks:
- * out[0..7] = sizes, fill, filtration, sort, union-find, loops, image, total; returns #chunks.
+ * out[0..9] = sizes, fill, filtration, vertex order (2v), vertex-ordered sweep (3v), edge sort (2),
+ * edge-sorted union-find (3), loops (3b), image (4), total; returns #chunks.
  * Only measured when the environment variable TLC_STAGE_TIMING=1 (adds event records). */
-int tlc_last_stage_ms(tlc_graph *g, double *out8);
+int tlc_last_stage_ms(tlc_graph *g, double *out10);
 /* algorithmic bytes (compulsory bytes B_e) summed over the targets of the last call */
 int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_bfs, double *bytes_uf);
 
 /* totals over the live targets of the last call: out[0] = live targets, out[1] = sum n, out[2] = sum m,
- * out[3] = chunks */
-int tlc_last_counts(tlc_graph *g, int64_t *out4);
+ * out[3] = chunks, out[4] = targets the vertex-ordered sweep handed back to the edge-sorted kernels */
+int tlc_last_counts(tlc_graph *g, int64_t *out5);
 
 #ifdef __cplusplus
 }

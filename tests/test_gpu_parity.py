@@ -41,29 +41,34 @@ def compare_detail(g, og, targets, hop, descriptor, flags, oflags, mode=L.MODE_E
         assert rel_err(a["img"], o["img"]) < IMG_TOL, ctx             # kernel 4
 
 
+# es = 1 forces the edge-sorted kernels 2+3 for the ascending sweep; es = 0 is the default vertex-ordered
+# kernels 2v+3v (with hand-back to 2+3).  Both must reproduce the oracle's pair sequence bit for bit.
 @pytest.mark.parametrize("tag", GRAPH_CASES)
 @pytest.mark.parametrize("ext", [0, 1])
-def test_golden_cases(tag, ext):
+@pytest.mark.parametrize("es", [0, 1])
+def test_golden_cases(tag, ext, es):
     c = load_case(tag)
     g = api.VicinityGraph(*c["csr"], device=0)
     og = orc.OracleGraph(*c["csr"])
-    flags = L.F_NORM | (L.F_EXTENDED if ext else 0)
+    oflags = orc.F_NORM | (orc.F_EXTENDED if ext else 0)
+    flags = L.F_NORM | (L.F_EXTENDED if ext else 0) | (L.F_EDGE_SORTED if es else 0)
     # batch call: images vs the REAL reference's pi_sg stored in the fixture, counts equal
     pi, status, cnt = g.vicinity_pi(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=flags)
     ref = c["pi_ext%d" % ext]
     assert cnt == int(c["cnt_ext%d" % ext])
     assert np.array_equal(ref.any(axis=1), pi.any(axis=1))
     assert rel_err(pi, ref) < IMG_TOL
-    o = og.run_batch(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=flags)
+    o = og.run_batch(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=oflags)
     assert np.array_equal(status, o["status"])
-    compare_detail(g, og, c["new_targets"], c["hop"], c["descriptor"], flags, flags)
+    compare_detail(g, og, c["new_targets"], c["hop"], c["descriptor"], flags, oflags)
     g.close()
 
 
+@pytest.mark.parametrize("es", [0, 1])
 @pytest.mark.parametrize("name,scale,hop,cont", [("cora", 1.0, 2, False), ("cora", 1.0, 3, False), ("pubmed", 0.3, 2, False),
                                                  ("pubmed", 0.3, 2, True), ("computers", 0.05, 2, False),
                                                  ("computers", 0.05, 2, True), ("ppi", 0.3, 1, False)])
-def test_random_targets(name, scale, hop, cont):
+def test_random_targets(name, scale, hop, cont, es):
     c = gg.make_config(name, scale=scale, continuous=cont)
     labels, ne = gg.relabel_first_appearance(c["edges"])
     csr = gg.build_csr(len(labels), ne, c["kappa"])
@@ -73,12 +78,16 @@ def test_random_targets(name, scale, hop, cont):
     tg = ne[rng.choice(len(ne), 48, replace=False)].astype(np.int32)
     neg = rng.integers(0, len(labels), size=(16, 2)).astype(np.int32)
     tg = np.concatenate([tg, neg, np.array([[-1, 3], [0, 0]], np.int32)])
-    flags = L.F_NORM | L.F_EXTENDED
-    compare_detail(g, og, tg, hop, "sum", flags, flags)
-    pi, status, cnt = g.vicinity_pi(tg, hop=hop, flags=flags)
-    o = og.run_batch(tg, hop=hop, flags=flags)
-    assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
-    assert rel_err(pi, o["pi"]) < IMG_TOL
+    oflags = orc.F_NORM | orc.F_EXTENDED
+    flags = L.F_NORM | L.F_EXTENDED | (L.F_EDGE_SORTED if es else 0)
+    compare_detail(g, og, tg, hop, "sum", flags, oflags)
+    for ext in (1, 0):  # the batch call without `extended` runs the ascending sweep only (image needs no PD_down)
+        fl = flags if ext else flags & ~L.F_EXTENDED
+        ofl = oflags if ext else oflags & ~orc.F_EXTENDED
+        pi, status, cnt = g.vicinity_pi(tg, hop=hop, flags=fl)
+        o = og.run_batch(tg, hop=hop, flags=ofl)
+        assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
+        assert rel_err(pi, o["pi"]) < IMG_TOL
     g.close()
 
 

@@ -36,13 +36,16 @@ struct UfShared {
   int32_t total, nmerge, npairs, nneg, minv, maxv;
 };
 
-__global__ void union_find_kernel(Params p, ChunkView c, int smem_ints, int build_lists) {
+__global__ void union_find_kernel(Params p, ChunkView c, int smem_ints, int build_lists, int sweep_mask, int fb_only) {
   extern __shared__ int32_t dyn[];
   __shared__ UfShared sh;
   const int t = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   const int n = c.tn[t], m = c.tm[t];
   if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
+  if (fb_only && !c.tfb[t]) sweep_mask &= ~1;  // kernel 3v already produced PD_up and [min,max] of this target
+  if (!sweep_mask) return;
+  const bool do_asc = (sweep_mask & 1) != 0, do_desc = (sweep_mask & 2) != 0;
   const int64_t vo = c.voff[t], eo = c.eoff[t], po = c.poff(t);
   const int32_t* __restrict__ elo = c.elo + eo;
   const int32_t* __restrict__ ehi = c.ehi + eo;
@@ -58,7 +61,7 @@ __global__ void union_find_kernel(Params p, ChunkView c, int smem_ints, int buil
   const int ncls = c.tncls[t];
 
   if (in_smem) for (int x = tid; x < n; x += nt) cls[x] = c.vcls[vo + x];
-  if (tid == 0) { sh.npairs = 0; sh.minv = n; sh.maxv = n; sh.nneg = 0; }
+  if (tid == 0) { sh.npairs = do_asc ? 0 : c.tnp[t]; sh.minv = n; sh.maxv = n; sh.nneg = 0; sh.nmerge = 0; }
   __syncthreads();
   // min_value / max_value: first vertex (ascending id) attaining them   accelerated_PD.py:35-38
   for (int x = tid; x < n; x += nt) {
@@ -68,6 +71,7 @@ __global__ void union_find_kernel(Params p, ChunkView c, int smem_ints, int buil
   }
 
   for (int sweep = 0; sweep < 2; sweep++) {
+    if (!((sweep_mask >> sweep) & 1)) continue;
     const uint32_t* __restrict__ ord = (sweep == 0 ? c.ord_asc : c.ord_desc) + eo;
     for (int x = tid; x < n; x += nt) parent[x] = x;
     if (sweep == 1) for (int k = tid; k < m; k += nt) isneg[k] = 0;
@@ -167,7 +171,8 @@ __global__ void union_find_kernel(Params p, ChunkView c, int smem_ints, int buil
 
   // Pos_edges in sweep order (accelerated_PD.py:109): ordered compaction of the non-tree flags
   const int nneg = sh.nneg;
-  if (build_lists) {
+  const int last_merges = sh.nmerge;
+  if (build_lists && do_desc) {
     const uint32_t* __restrict__ ord = c.ord_desc + eo;
     int32_t* pos = c.pos + eo;
     int cursor = 0;
@@ -193,19 +198,21 @@ __global__ void union_find_kernel(Params p, ChunkView c, int smem_ints, int buil
   }
   if (tid == 0) {
     c.tnp[t] = np;
-    c.tnneg[t] = nneg;
-    c.tnpos[t] = m - nneg;
-    if (nneg != n - 1) c.tstatus[t] = TLC_ST_DISCONNECTED;  // assert len(components) == 1   riccidist2dgm.py:318
+    if (do_desc) { c.tnneg[t] = nneg; c.tnpos[t] = m - nneg; }
+    else { c.tnneg[t] = 0; c.tnpos[t] = 0; }
+    // assert len(components) == 1 (riccidist2dgm.py:318): a spanning tree has n-1 merges in either sweep
+    if (last_merges != n - 1) c.tstatus[t] = TLC_ST_DISCONNECTED;
   }
 }
 
 }  // namespace
 
-void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_ints, int build_lists, cudaStream_t st) {
+void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_ints, int build_lists, int sweep_mask,
+                       int fb_only, cudaStream_t st) {
   const size_t bytes = (size_t)smem_ints * 4;
   if (bytes > 48 * 1024)
     cudaFuncSetAttribute((const void*)union_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  union_find_kernel<<<c.T, block, bytes, st>>>(p, c, smem_ints, build_lists);
+  union_find_kernel<<<c.T, block, bytes, st>>>(p, c, smem_ints, build_lists, sweep_mask, fb_only);
   count_launch();
 }
 

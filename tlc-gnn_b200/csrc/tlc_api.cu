@@ -42,16 +42,16 @@ static constexpr size_t ALIGN = 256;
 static size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
 // bytes of arena per vertex / edge / pair slot (see carve())
-static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3;                   // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c
-static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1;           // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg
+static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3 + 4 * 4;           // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c | vord vrank bfirst loff
+static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1 + 4;       // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg | ladj
 static constexpr size_t BP = 1 + 4 * 2 + 8 * 2;                       // pkind | pbv pdv | pbirth pdeath
-static constexpr size_t BT = 8 * 3 + 4 * 8 + 1;                       // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls | tstatus
+static constexpr size_t BT = 8 * 3 + 4 * 11 + 2 + 4 * 2;              // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls tnb tminv tmaxv | tstatus tfb | bfirst/loff terminators
 
 struct tlc_graph {
   int device = 0;
   GraphView gv{};
   cudaStream_t stream = nullptr, own_stream = nullptr;
-  int64_t last_live = 0, last_nv = 0, last_ne = 0;
+  int64_t last_live = 0, last_nv = 0, last_ne = 0, last_fb = 0;
   char* arena = nullptr;
   size_t arena_bytes = 0, arena_req = 0;
   // vicinity scratch (depends on hop)
@@ -68,7 +68,7 @@ struct tlc_graph {
   char* h_pin = nullptr;
   size_t h_pin_bytes = 0;
   // stats of the last call
-  double stage_ms[8] = {0};
+  double stage_ms[10] = {0};
   int nchunks = 0;
   double alg_bytes = 0, alg_bytes_bfs = 0, alg_bytes_uf = 0;
   bool timing = false;
@@ -139,8 +139,8 @@ static int ensure_vicinity_scratch(tlc_graph* g, const Params& p) {
 // carve the arena for a chunk with T targets, Nv vertices, Ne edges (pairs = Nv + Ne + T)
 static size_t chunk_bytes(int64_t T, int64_t Nv, int64_t Ne) {
   const int64_t Np = Nv + Ne + T;
-  // every array individually aligned: 12 vertex arrays, 12 edge arrays, 5 pair arrays, 12 target arrays
-  return (size_t)(Nv * BV + Ne * BE + Np * BP + (T + 1) * BT) + ALIGN * 48;
+  // every array individually aligned: 16 vertex arrays, 13 edge arrays, 5 pair arrays, 16 target arrays
+  return (size_t)(Nv * BV + Ne * BE + Np * BP + (T + 1) * BT) + ALIGN * 56;
 }
 
 template <typename T_>
@@ -161,7 +161,12 @@ static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, const int
   c.eoff = take<int64_t>(cur, T + 1);
   c.tn = take<int32_t>(cur, T); c.tm = take<int32_t>(cur, T); c.tlu = take<int32_t>(cur, T); c.tlv = take<int32_t>(cur, T);
   c.tnp = take<int32_t>(cur, T); c.tnpos = take<int32_t>(cur, T); c.tnneg = take<int32_t>(cur, T); c.tncls = take<int32_t>(cur, T);
+  c.tnb = take<int32_t>(cur, T); c.tminv = take<int32_t>(cur, T); c.tmaxv = take<int32_t>(cur, T);
   c.tstatus = take<uint8_t>(cur, T);
+  c.tfb = take<uint8_t>(cur, T);
+  c.vord = take<int32_t>(cur, Nv); c.vrank = take<int32_t>(cur, Nv);
+  c.bfirst = take<int32_t>(cur, Nv + T); c.loff = take<int32_t>(cur, Nv + T);
+  c.ladj = take<uint32_t>(cur, Ne);
   c.vert = take<int32_t>(cur, Nv); c.vcls = take<int32_t>(cur, Nv); c.vs0 = take<int32_t>(cur, Nv);
   c.vs1 = take<int32_t>(cur, Nv); c.vs2 = take<int32_t>(cur, Nv); c.neg = take<int32_t>(cur, Nv);
   c.fval = take<double>(cur, Nv); c.d1 = take<double>(cur, Nv); c.d2 = take<double>(cur, Nv);
@@ -203,7 +208,7 @@ struct StageTimer {
     ev.push_back(e);
     stage.push_back(stage_id);
   }
-  void collect(double* ms8) {
+  void collect(double* ms8) {  // ms8: per-stage accumulators (10 slots)
     if (!on) return;
     for (size_t i = 0; i + 1 < ev.size(); i++) {
       if (stage[i] < 0) continue;
@@ -227,18 +232,32 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
   launch_filtration(p, c, block, st);
-  tm.mark(3);
-  launch_sort(p, c, block, st);
-  tm.mark(4);
+  // ascending sweep: vertex-ordered kernels 2v + 3v; targets they hand back (tfb) and, when the descending
+  // sweep is wanted (diagram output, Pos/Neg lists for the loops), the edge-sorted kernels 2 + 3.  The image
+  // only needs PD_up and [min,max]: PD_down and [max,min] have death <= birth, i.e. weight 0.
   const bool ext = (p.flags & TLC_F_EXTENDED) != 0;
-  const int64_t uf_ints = 2 * n_max * 4 <= 96 * 1024 ? 2 * n_max : 0;
-  launch_union_find(p, c, block, (int)uf_ints, (ext || want_lists) ? 1 : 0, st);
+  const bool edge_sorted = (p.flags & TLC_F_EDGE_SORTED) != 0;
+  const bool want_desc = ext || want_lists;
+  tm.mark(3);
+  if (edge_sorted) {
+    cudaMemsetAsync(c.tfb, 1, (size_t)c.T, st);
+  } else {
+    launch_vorder(p, c, block, n_max, st);
+    tm.mark(4);
+    launch_sweep(p, c, n_max, st);
+  }
   tm.mark(5);
+  // kernel 3b ranks loop edges by their position in the ascending order, so `extended` needs ord_asc of every target
+  launch_sort(p, c, block, want_desc ? 3 : 1, want_desc ? 0 : 1, st);
+  tm.mark(6);
+  const int64_t uf_ints = 2 * n_max * 4 <= 96 * 1024 ? 2 * n_max : 0;
+  launch_union_find(p, c, block, (int)uf_ints, want_desc ? 1 : 0, want_desc ? 3 : 1, 1, st);
+  tm.mark(7);
   if (ext) {
     const int64_t lp_ints = 3 * n_max * 4 <= 200 * 1024 ? 3 * n_max : 0;
     launch_loops(p, c, std::min(block, 128), (int)lp_ints, st);
   }
-  tm.mark(6);
+  tm.mark(8);
   launch_pimg(p, c, d_pi, d_pi32, d_status, std::max(32, std::min(block, 256)), st);
   tm.mark(-1);
 }
@@ -262,10 +281,11 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
   const int r2 = p.resolution * p.resolution;
   cudaStream_t st = g->stream;
-  for (int i = 0; i < 8; i++) g->stage_ms[i] = 0;
+  for (int i = 0; i < 10; i++) g->stage_ms[i] = 0;
   g->nchunks = 0;
   g->alg_bytes = g->alg_bytes_bfs = g->alg_bytes_uf = 0;
-  g->last_live = g->last_nv = g->last_ne = 0;
+  g->last_live = g->last_nv = g->last_ne = g->last_fb = 0;
+  CK(cudaMemsetAsync(g->work_counter + 1, 0, sizeof(int), st));
   if (cnt_compute) *cnt_compute = 0;
   if (E == 0) return TLC_OK;
   const bool bad_desc = p.descriptor < 0 || p.descriptor > 2;
@@ -355,6 +375,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     }
     if (T == 0) return fail(TLC_E_NOMEM, "a vicinity does not fit the arena");
     ChunkView c = carve(g->arena, T, Nv, Ne, d_targets);
+    c.fb_counter = g->work_counter + 1;
     // offsets: [pos, pos+T) plus the terminating total.  voff/eoff need T+1 entries; the terminator is
     // written into a separate tiny pinned slot so that the next chunk's slot `q` is not clobbered.
     CK(cudaMemcpyAsync((void*)c.tidx, h_tidx + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
@@ -399,7 +420,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     cudaStreamSynchronize(st);
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_total0, ev_total1);
-    g->stage_ms[7] = ms;
+    g->stage_ms[9] = ms;
     tm.collect(g->stage_ms);
     cudaEventDestroy(ev_total0);
     cudaEventDestroy(ev_total1);
@@ -415,7 +436,12 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
       if (detail && detail->status) memcpy(detail->status, h_st, (size_t)E);
     }
   }
-  CK(cudaStreamSynchronize(st));
+  {
+    int fb = 0;
+    CK(cudaMemcpyAsync(&fb, g->work_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    g->last_fb = fb;
+  }
   CK(cudaGetLastError());
   return TLC_OK;
 }
@@ -593,9 +619,9 @@ int tlc_union_find(int device, int32_t n, int32_t m, const double* fval, const i
   }
   Params p{0, TLC_MODE_NODE, TLC_DESC_SUM, 5, flags, 0};
   const int block = block_for(m);
-  launch_sort(p, c, block, st);
+  launch_sort(p, c, block, 3, 0, st);
   const int64_t uf_ints = 2 * (int64_t)n * 4 <= 96 * 1024 ? 2 * (int64_t)n : 0;
-  launch_union_find(p, c, block, (int)uf_ints, 1, st);
+  launch_union_find(p, c, block, (int)uf_ints, 1, 3, 0, st);
   if (flags & TLC_F_EXTENDED) {
     const int64_t lp_ints = 3 * (int64_t)n * 4 <= 200 * 1024 ? 3 * (int64_t)n : 0;
     launch_loops(p, c, std::min(block, 128), (int)lp_ints, st);
@@ -651,15 +677,15 @@ int tlc_graph_set_stream(tlc_graph* g, void* stream) {
   return TLC_OK;
 }
 
-int tlc_last_counts(tlc_graph* g, int64_t* out4) {
-  if (!g || !out4) return TLC_E_INVALID;
-  out4[0] = g->last_live; out4[1] = g->last_nv; out4[2] = g->last_ne; out4[3] = g->nchunks;
+int tlc_last_counts(tlc_graph* g, int64_t* out5) {
+  if (!g || !out5) return TLC_E_INVALID;
+  out5[0] = g->last_live; out5[1] = g->last_nv; out5[2] = g->last_ne; out5[3] = g->nchunks; out5[4] = g->last_fb;
   return TLC_OK;
 }
 
-int tlc_last_stage_ms(tlc_graph* g, double* out8) {
-  if (!g || !out8) return 0;
-  for (int i = 0; i < 8; i++) out8[i] = g->stage_ms[i];
+int tlc_last_stage_ms(tlc_graph* g, double* out10) {
+  if (!g || !out10) return 0;
+  for (int i = 0; i < 10; i++) out10[i] = g->stage_ms[i];
   return g->nchunks;
 }
 

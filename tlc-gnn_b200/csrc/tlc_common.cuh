@@ -27,12 +27,20 @@ struct ChunkView {
   const int64_t* voff;  // [T+1]
   const int64_t* eoff;  // [T+1]
   int32_t *tn, *tm, *tlu, *tlv, *tnp, *tnpos, *tnneg, *tncls;
+  int32_t *tnb, *tminv, *tmaxv;  // kernel 2v: #blocks of the vertex order, local ids of the essential pair
   uint8_t* tstatus;
+  int* fb_counter;  // device counter: targets kernel 3v handed back
+  uint8_t* tfb;  // 1: the vertex-ordered sweep (kernel 3v) did not run / bailed out -> edge-sorted kernels 2 + 3 do the ascending sweep
   // vertex-indexed
   int32_t *vert, *vcls, *vs0, *vs1, *vs2, *neg;
   double *fval, *d1, *d2;
   unsigned long long *v64a, *v64b, *v64c;
+  int32_t *vord, *vrank;  // kernel 2v: rank -> local id, local id -> rank in the (value, id) vertex order
+  // (n+1)-per-target arrays, addressed at voff[t] + t
+  int32_t *bfirst;  // first rank of every block of the vertex order (bit 31: block holds distinct values), [nb] = n
+  int32_t *loff;    // start of every rank's lower adjacency in ladj (relative to eoff[t]), [n] = m
   // edge-indexed
+  uint32_t* ladj;   // rank-space lower adjacency: for owner rank r the ranks (< r) of its neighbours
   int32_t *elo, *ehi, *pos, *arank;
   double* ew;
   uint32_t *ord_asc, *ord_desc, *sp0, *sp1;
@@ -134,8 +142,12 @@ void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* t
 void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                           int* work_counter, cudaStream_t st);
 void launch_filtration(const Params& p, const ChunkView& c, int block, cudaStream_t st);
-void launch_sort(const Params& p, const ChunkView& c, int block, cudaStream_t st);
-void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_ints, int build_lists, cudaStream_t st);
+// sweep_mask: bit 0 ascending, bit 1 descending.  fb_only: the ascending sweep only for targets with tfb[t] != 0.
+void launch_sort(const Params& p, const ChunkView& c, int block, int sweep_mask, int fb_only, cudaStream_t st);
+void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_ints, int build_lists, int sweep_mask,
+                       int fb_only, cudaStream_t st);
+void launch_vorder(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st);
+void launch_sweep(const Params& p, const ChunkView& c, int64_t n_max, cudaStream_t st);
 void launch_loops(const Params& p, const ChunkView& c, int block, int smem_ints, cudaStream_t st);
 void launch_pimg(const Params& p, const ChunkView& c, double* out_pi, float* out_pi_f32, uint8_t* out_status,
                  int block, cudaStream_t st);

@@ -134,9 +134,9 @@ class VicinityGraph:
         return out
 
     def last_stage_ms(self):
-        out = np.zeros(8)
+        out = np.zeros(10)
         nch = L.lib().tlc_last_stage_ms(self._h, out.ctypes.data)
-        names = ["sizes", "fill", "filtration", "sort", "union_find", "loops", "image", "total"]
+        names = ["sizes", "fill", "filtration", "vorder", "sweep", "sort", "union_find", "loops", "image", "total"]
         return dict(zip(names, out.tolist())), int(nch)
 
     def set_stream(self, cuda_stream_ptr):
@@ -144,9 +144,9 @@ class VicinityGraph:
         L.check(L.lib().tlc_graph_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
     def last_counts(self):
-        out = np.zeros(4, np.int64)
+        out = np.zeros(5, np.int64)
         L.lib().tlc_last_counts(self._h, out.ctypes.data)
-        return dict(live=int(out[0]), sum_n=int(out[1]), sum_m=int(out[2]), chunks=int(out[3]))
+        return dict(live=int(out[0]), sum_n=int(out[1]), sum_m=int(out[2]), chunks=int(out[3]), handed_back=int(out[4]))
 
     def last_algorithmic_bytes(self):
         tot = C.c_double(0)
