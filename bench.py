@@ -221,6 +221,7 @@ def run_cuda(args):
     barrier()
     stage_acc = {}
     alg_bytes = 0.0
+    handed_back = 0
     launches0 = api.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -233,6 +234,7 @@ def run_cuda(args):
         for k, v in ms.items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
         alg_bytes += g.last_algorithmic_bytes()
+        handed_back += g.last_counts()["handed_back"]
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -257,10 +259,13 @@ def run_cuda(args):
     gm.get_pimg_for_all_edges(e2e_batches[0], cores=16, hop=args.hop, norm=True, extended_flag=bool(args.extended),
                               resolution=5, descriptor="sum")
     barrier()
+    e2e_stage = {}
     t0 = time.perf_counter()
     for s in range(args.steps):
         gm.get_pimg_for_all_edges(e2e_batches[1 + s], cores=16, hop=args.hop, norm=True,
                                   extended_flag=bool(args.extended), resolution=5, descriptor="sum")
+        for k, v in gm._graph.last_stage_ms()[0].items():
+            e2e_stage[k] = e2e_stage.get(k, 0.0) + v
         if world > 1:
             dist.all_gather_into_tensor(gathered, torch.from_numpy(gm.pi_sg.astype(np.float32)).to(dev))
     torch.cuda.synchronize()
@@ -298,7 +303,9 @@ def run_cuda(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(args, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 8),
-                        "d2h_bytes_per_step": int(B * (r2 * 8 + 1))},
+                        "d2h_bytes_per_step": int(B * (r2 * 8 + 1)),
+                        "stage_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()}},
+                "handed_back_per_step": handed_back / args.steps,
                 "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

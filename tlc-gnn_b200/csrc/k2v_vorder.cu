@@ -17,6 +17,7 @@
 //      (ties keep ascending local id)                    -> vord[rank] = local id, vrank[local id] = rank
 //   2. block starts (bit 31 of bfirst[b]: the block holds distinct values, i.e. a near-tie block)
 //   3. counting sort of the m edges by owner rank        -> loff[n+1], ladj[m] = rank of the other endpoint
+//      (bit 31: it lies in an earlier block), bend[b] = end of block b's edges | block flags
 //   4. local ids of the essential pair [min, max]        (accelerated_PD.py:35-38,110: first vertex in
 //      ascending id attaining the extreme value)
 #include "tlc_common.cuh"
@@ -39,6 +40,7 @@ __global__ void vorder_kernel(Params p, ChunkView c, int smem_ints) {
   int32_t* vrank = c.vrank + vo;
   int32_t* bfirst = c.bfirst + vo + t;
   int32_t* loff = c.loff + vo + t;
+  int32_t* bend = c.bend + vo + t;
 
   // ---- 1. vertex order ----
   unsigned long long* k0 = c.v64a + vo;
@@ -83,15 +85,23 @@ __global__ void vorder_kernel(Params p, ChunkView c, int smem_ints) {
   }
   __syncthreads();
   // ---- 3. rank-space lower adjacency ----
+  // srank[local id] = rank | block index << 16 (both < 65536 here)
+  if (n >= 65536) {  // 16-bit packing does not hold: leave this target to the edge-sorted kernels 2 + 3
+    if (tid == 0) c.tfb[t] = 1;
+    return;
+  }
   const bool in_smem = 2 * n <= smem_ints;
   int32_t* cnt = in_smem ? dyn : c.vs2 + vo;         // flag[] is dead from here on
-  int32_t* srank = in_smem ? dyn + n : vrank;
-  for (int i = tid; i < n; i += nt) { cnt[i] = 0; if (in_smem) srank[i] = vrank[i]; }
+  uint32_t* srank = in_smem ? reinterpret_cast<uint32_t*>(dyn + n) : reinterpret_cast<uint32_t*>(c.vcls + vo);
+  for (int i = tid; i < n; i += nt) {
+    cnt[i] = 0;
+    srank[ps[i]] = (uint32_t)i | ((uint32_t)(flag[i] - 1 + own[i]) << 16);
+  }
   __syncthreads();
   const int32_t* __restrict__ elo = c.elo + eo;
   const int32_t* __restrict__ ehi = c.ehi + eo;
   for (int e = tid; e < m; e += nt) {
-    const int ra = srank[elo[e]], rb = srank[ehi[e]];
+    const int ra = (int)(srank[elo[e]] & 0xffffu), rb = (int)(srank[ehi[e]] & 0xffffu);
     atomicAdd(&cnt[max(ra, rb)], 1);
   }
   __syncthreads();
@@ -99,11 +109,25 @@ __global__ void vorder_kernel(Params p, ChunkView c, int smem_ints) {
   for (int i = tid; i < n; i += nt) loff[i] = cnt[i];
   if (tid == 0) loff[n] = m;
   __syncthreads();
+  // ladj entry = rank of the earlier endpoint | bit 31 when it lies in an EARLIER block than the owner
   uint32_t* ladj = c.ladj + eo;
   for (int e = tid; e < m; e += nt) {
-    const int ra = srank[elo[e]], rb = srank[ehi[e]];
-    const int pos = atomicAdd(&cnt[max(ra, rb)], 1);
-    ladj[pos] = (uint32_t)min(ra, rb);
+    const uint32_t wa = srank[elo[e]], wb = srank[ehi[e]];
+    const uint32_t wo = (wa & 0xffffu) > (wb & 0xffffu) ? wa : wb, wy = wo == wa ? wb : wa;
+    const int pos = atomicAdd(&cnt[wo & 0xffffu], 1);
+    ladj[pos] = (wy & 0xffffu) | ((wy >> 16) != (wo >> 16) ? 0x80000000u : 0u);
+  }
+  __syncthreads();  // ladj of this vicinity complete (global writes of the block visible to the block)
+  // per block: end of its owned edges | bit 31 distinct values | bit 30 every vertex has an earlier-block neighbour
+  for (int b = tid; b < nb; b += nt) {
+    const int s0 = bfirst[b] & 0x7fffffff, s1 = bfirst[b + 1] & 0x7fffffff;
+    bool all_out = true;
+    for (int x = s0; x < s1 && all_out; x++) {
+      bool has = false;
+      for (int j = loff[x]; j < loff[x + 1] && !has; j++) has = (ladj[j] >> 31) != 0;
+      all_out = has;
+    }
+    bend[b] = loff[s1] | (bfirst[b] & (int32_t)0x80000000) | (all_out ? 0x40000000 : 0);
   }
 }
 

@@ -26,7 +26,7 @@ namespace tlc {
 namespace {
 
 constexpr int REP_CAP = 64;
-constexpr int SWEEP_WARPS = 4;
+constexpr int SWEEP_WARPS = 1;  // one warp per CTA: the shared-memory footprint (parents of ONE vicinity) sets the residency
 
 struct RepBuf {
   unsigned long long key[REP_CAP];
@@ -46,6 +46,52 @@ __device__ __forceinline__ int find_root(PT* p, int x) {  // path halving  accel
   }
 }
 
+// ---- the lower-adjacency stream: kernel 2v laid the owned edges out in sweep order, so the warp reads ladj
+// strictly front to back.  A per-warp shared-memory ring is kept RING-CHUNK entries ahead with cp.async.
+constexpr int RING = 512, CHUNK = 128;
+
+struct AdjStream {
+  const uint32_t* src;
+  uint32_t* ring;
+  int m, fetched, arrived;
+  __device__ __forceinline__ void issue(int lane) {
+#pragma unroll
+    for (int k = 0; k < CHUNK / 32; k++) {
+      const int idx = fetched + k * 32 + lane;
+      if (idx < m) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (idx & (RING - 1)));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + idx) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    fetched += CHUNK;
+  }
+  // make entries [j0, j1) readable (j1 - j0 <= 32); entries below j0 are dead.  Uniform over the warp.
+  __device__ __forceinline__ void ensure(int j0, int j1, int lane) {
+    if (j0 >= fetched + CHUNK) {  // the reader skipped ahead (blocks handled off-stream): drop the gap
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      fetched = j0 / CHUNK * CHUNK;
+      arrived = fetched;
+    }
+    if (fetched < m && fetched + CHUNK - j0 <= RING) {
+      __syncwarp();  // every lane is done reading the slots about to be overwritten
+      while (fetched < m && fetched + CHUNK - j0 <= RING) issue(lane);
+    }
+    if (j1 > arrived) {
+      const int need_end = (j1 + CHUNK - 1) / CHUNK * CHUNK;
+      const int later = (fetched - need_end) / CHUNK;  // groups issued after the one needed: may stay in flight
+      if (later >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      else if (later == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else if (later == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      arrived = fetched - (later >= 3 ? 3 : later) * CHUNK;
+    }
+  }
+  __device__ __forceinline__ uint32_t at(int j) const { return ring[j & (RING - 1)]; }
+};
+
 __device__ __forceinline__ bool rep_less(unsigned long long ka, int la, int ha, unsigned long long kb, int lb, int hb) {
   if (ka != kb) return ka < kb;
   if (la != lb) return la < lb;  // canonical edge index order == lexicographic (lo, hi)
@@ -56,6 +102,7 @@ template <typename PT>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, ChunkView c, int cap) {
   extern __shared__ unsigned char dyn_raw[];
   __shared__ RepBuf reps_all[SWEEP_WARPS];
+  __shared__ uint32_t ring_all[SWEEP_WARPS][RING];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int t = blockIdx.x * SWEEP_WARPS + wid;
   if (t >= c.T) return;
@@ -64,6 +111,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   const int64_t vo = c.voff[t], eo = c.eoff[t], po = c.poff(t);
   const int32_t* __restrict__ vord = c.vord + vo;
   const int32_t* __restrict__ bfirst = c.bfirst + vo + t;
+  const int32_t* __restrict__ bend = c.bend + vo + t;
   const int32_t* __restrict__ loff = c.loff + vo + t;
   const uint32_t* __restrict__ ladj = c.ladj + eo;
   const double* __restrict__ fval = c.fval + vo;
@@ -76,45 +124,43 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   for (int r = lane; r < n; r += 32) parent[r] = (PT)r;
   __syncwarp();
 
+  AdjStream adj{ladj, ring_all[wid], c.tm[t], 0, 0};
   int np = 0, nmerge = 0;
   bool bail = false;
-  int s = 0;
+  int s = 0, a0 = 0;
+  // block table, 32 blocks per coalesced load, the next group already in flight
+  int cur_first = 0, cur_end = 0, nxt_first = 0, nxt_end = 0;
+  {
+    const int i = lane;
+    if (i < nb) { nxt_first = bfirst[i + 1]; nxt_end = bend[i]; }
+  }
   for (int b = 0; b < nb && !bail; b++) {
-    const int wb = bfirst[b];
-    const int e = bfirst[b + 1] & 0x7fffffff;
-    const bool distinct = wb < 0;
-    const int a0 = loff[s], a1 = loff[e];
+    if ((b & 31) == 0) {
+      cur_first = nxt_first; cur_end = nxt_end;
+      const int i = b + 32 + lane;
+      if (i < nb) { nxt_first = bfirst[i + 1]; nxt_end = bend[i]; }
+    }
+    const int e = __shfl_sync(FULL, cur_first, b & 31) & 0x7fffffff;
+    const int we = __shfl_sync(FULL, cur_end, b & 31);
+    const bool distinct = we < 0;
+    const bool all_out = ((we >> 30) & 1) != 0;  // every vertex of the block has a neighbour in an earlier block
+    const int a1 = we & 0x3fffffff;
 
     // ---------------- trivial block test ----------------
     bool done = false;
-    if (!distinct && !keep0) {
+    if (!distinct && !keep0 && all_out) {
       int R = -1;
       bool ok = true;
-      if (e - s == 1) {  // singleton: every entry is an earlier-block neighbour
-        ok = a1 > a0;
-        for (int j0 = a0; j0 < a1 && ok; j0 += 32) {
-          const int j = j0 + lane;
-          const int rt = find_root(parent, (int)ladj[j < a1 ? j : a0]);
-          if (R < 0) R = __shfl_sync(FULL, rt, 0);
-          ok = __all_sync(FULL, rt == R);
-        }
-      } else {
-        for (int x = s; x < e && ok; x++) {
-          const int xa = loff[x], xb = loff[x + 1];
-          bool has = false;
-          for (int j0 = xa; j0 < xb && ok; j0 += 32) {
-            const int j = j0 + lane;
-            const int y = j < xb ? (int)ladj[j] : e;  // e: "inside the block", ignored
-            const bool out = y < s;
-            const int rt = out ? find_root(parent, y) : -1;
-            const unsigned bo = __ballot_sync(FULL, out);
-            if (bo) {
-              has = true;
-              if (R < 0) R = __shfl_sync(FULL, rt, __ffs(bo) - 1);
-              ok = __all_sync(FULL, !out || rt == R);
-            }
-          }
-          ok = ok && has;
+      for (int j0 = a0; j0 < a1 && ok; j0 += 32) {
+        const int j = j0 + lane;
+        adj.ensure(j0, min(j0 + 32, a1), lane);
+        const uint32_t w = j < a1 ? adj.at(j) : 0u;
+        const bool out = (w >> 31) != 0;  // entries inside the block are cycle edges once everything hangs off R
+        const int rt = out ? find_root(parent, (int)(w & 0x7fffffffu)) : -1;
+        const unsigned bo = __ballot_sync(FULL, out);
+        if (bo) {
+          if (R < 0) R = __shfl_sync(FULL, rt, __ffs(bo) - 1);
+          ok = __all_sync(FULL, !out || rt == R);
         }
       }
       if (ok) {
@@ -140,7 +186,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
           int y = 0, ly = 0, ry = -1, lo = 0, hi = 0;
           unsigned long long K = 0;
           if (valid) {
-            y = (int)ladj[j];
+            y = (int)(ladj[j] & 0x7fffffffu);
             ly = vord[y];
             ry = find_root(parent, y);  // no union has happened in this block yet: component at block start
             K = f64_to_ordered(key_asc(fx, fval[ly]));
@@ -216,7 +262,9 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
       }
     }
     s = e;
+    a0 = a1;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   if (lane == 0) {
     if (bail) {
@@ -240,7 +288,7 @@ void launch_sweep(const Params& p, const ChunkView& c, int64_t n_max, cudaStream
   // parents in shared memory when SWEEP_WARPS vicinities of the chunk's largest size fit
   const bool narrow = n_max < 65536;
   const size_t esz = narrow ? 2 : 4;
-  const size_t budget = 200 * 1024;
+  const size_t budget = 220 * 1024;
   int cap = (int)((n_max + 7) / 8 * 8);
   if ((size_t)cap * esz * SWEEP_WARPS > budget) cap = 0;
   const size_t bytes = (size_t)cap * esz * SWEEP_WARPS;

@@ -42,10 +42,10 @@ static constexpr size_t ALIGN = 256;
 static size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
 // bytes of arena per vertex / edge / pair slot (see carve())
-static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3 + 4 * 4;           // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c | vord vrank bfirst loff
+static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3 + 4 * 5;           // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c | vord vrank bfirst loff bend
 static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1 + 4;       // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg | ladj
 static constexpr size_t BP = 1 + 4 * 2 + 8 * 2;                       // pkind | pbv pdv | pbirth pdeath
-static constexpr size_t BT = 8 * 3 + 4 * 11 + 2 + 4 * 2;              // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls tnb tminv tmaxv | tstatus tfb | bfirst/loff terminators
+static constexpr size_t BT = 8 * 3 + 4 * 11 + 2 + 4 * 3;              // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls tnb tminv tmaxv | tstatus tfb | bfirst/loff/bend terminators
 
 struct tlc_graph {
   int device = 0;
@@ -64,6 +64,11 @@ struct tlc_graph {
   uint8_t* d_st = nullptr;
   double* d_bytes = nullptr;
   int64_t call_cap = 0;
+  // device staging of the host-buffer entry point (tlc_vicinity_pi): targets in, image rows + status out
+  int32_t* io_t = nullptr;
+  double* io_pi = nullptr;
+  uint8_t* io_st = nullptr;
+  int64_t io_cap_t = 0, io_cap_pi = 0;
   // host pinned staging
   char* h_pin = nullptr;
   size_t h_pin_bytes = 0;
@@ -98,6 +103,26 @@ static int ensure_call_buffers(tlc_graph* g, int64_t E) {
   CK(cudaMalloc((void**)&g->d_st, cap));
   CK(cudaMalloc((void**)&g->d_bytes, cap * 8));
   g->call_cap = cap;
+  return TLC_OK;
+}
+
+static int ensure_io_buffers(tlc_graph* g, int64_t E, int r2) {
+  if (E > g->io_cap_t) {
+    if (g->io_t) cudaFree(g->io_t);
+    if (g->io_st) cudaFree(g->io_st);
+    g->io_t = nullptr; g->io_st = nullptr; g->io_cap_t = 0;
+    const int64_t cap = E + E / 8 + 1024;
+    CK(cudaMalloc((void**)&g->io_t, (size_t)cap * 8));
+    CK(cudaMalloc((void**)&g->io_st, (size_t)cap));
+    g->io_cap_t = cap;
+  }
+  if (E * r2 > g->io_cap_pi) {
+    if (g->io_pi) cudaFree(g->io_pi);
+    g->io_pi = nullptr; g->io_cap_pi = 0;
+    const int64_t cap = (E + E / 8 + 1024) * r2;
+    CK(cudaMalloc((void**)&g->io_pi, (size_t)cap * 8));
+    g->io_cap_pi = cap;
+  }
   return TLC_OK;
 }
 
@@ -165,7 +190,7 @@ static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, const int
   c.tstatus = take<uint8_t>(cur, T);
   c.tfb = take<uint8_t>(cur, T);
   c.vord = take<int32_t>(cur, Nv); c.vrank = take<int32_t>(cur, Nv);
-  c.bfirst = take<int32_t>(cur, Nv + T); c.loff = take<int32_t>(cur, Nv + T);
+  c.bfirst = take<int32_t>(cur, Nv + T); c.loff = take<int32_t>(cur, Nv + T); c.bend = take<int32_t>(cur, Nv + T);
   c.ladj = take<uint32_t>(cur, Ne);
   c.vert = take<int32_t>(cur, Nv); c.vcls = take<int32_t>(cur, Nv); c.vs0 = take<int32_t>(cur, Nv);
   c.vs1 = take<int32_t>(cur, Nv); c.vs2 = take<int32_t>(cur, Nv); c.neg = take<int32_t>(cur, Nv);
@@ -493,6 +518,7 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaFree((void*)g->gv.rowptr); cudaFree((void*)g->gv.col); cudaFree((void*)g->gv.kappa);
   cudaFree(g->arena); cudaFree(g->bitmaps); cudaFree(g->queue); cudaFree(g->work_counter);
   cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_st); cudaFree(g->d_bytes);
+  cudaFree(g->io_t); cudaFree(g->io_pi); cudaFree(g->io_st);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   delete g;
@@ -519,12 +545,10 @@ int tlc_vicinity_pi(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_p
   if (E == 0) return TLC_OK;
   CK(cudaSetDevice(g->device));
   const int r2 = p->resolution * p->resolution;
-  int32_t* d_t = nullptr;
-  double* d_pi = nullptr;
-  uint8_t* d_st = nullptr;
-  CK(cudaMalloc((void**)&d_t, (size_t)E * 8));
-  CK(cudaMalloc((void**)&d_pi, (size_t)E * r2 * 8));
-  CK(cudaMalloc((void**)&d_st, (size_t)E));
+  if ((rc = ensure_io_buffers(g, E, r2))) return rc;  // grow-only device staging: no cudaMalloc/cudaFree per call
+  int32_t* d_t = g->io_t;
+  double* d_pi = g->io_pi;
+  uint8_t* d_st = g->io_st;
   CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
   rc = run_pipeline(g, d_t, E, p, d_pi, nullptr, d_st, cnt_compute, nullptr);
   if (rc == TLC_OK) {
@@ -533,7 +557,6 @@ int tlc_vicinity_pi(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_p
     cudaError_t e3 = cudaStreamSynchronize(g->stream);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail(TLC_E_CUDA, "copy back failed");
   }
-  cudaFree(d_t); cudaFree(d_pi); cudaFree(d_st);
   return rc;
 }
 

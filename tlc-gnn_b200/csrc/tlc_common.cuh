@@ -39,6 +39,7 @@ struct ChunkView {
   // (n+1)-per-target arrays, addressed at voff[t] + t
   int32_t *bfirst;  // first rank of every block of the vertex order (bit 31: block holds distinct values), [nb] = n
   int32_t *loff;    // start of every rank's lower adjacency in ladj (relative to eoff[t]), [n] = m
+  int32_t *bend;    // per block: end of the block's owned edges in ladj | bit 31 of bfirst
   // edge-indexed
   uint32_t* ladj;   // rank-space lower adjacency: for owner rank r the ranks (< r) of its neighbours
   int32_t *elo, *ehi, *pos, *arank;
