@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
 
   AdjStream adj{ladj, ring_all[wid], c.tm[t], 0, 0};
   int np = 0, nmerge = 0;
+  int ncomp = 0;  // components among the vertices of the blocks processed so far
   bool bail = false;
   int s = 0, a0 = 0;
   // block table, 32 blocks per coalesced load, the next group already in flight
@@ -151,16 +152,38 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
     if (!distinct && !keep0 && all_out) {
       int R = -1;
       bool ok = true;
-      for (int j0 = a0; j0 < a1 && ok; j0 += 32) {
-        const int j = j0 + lane;
-        adj.ensure(j0, min(j0 + 32, a1), lane);
-        const uint32_t w = j < a1 ? adj.at(j) : 0u;
-        const bool out = (w >> 31) != 0;  // entries inside the block are cycle edges once everything hangs off R
-        const int rt = out ? find_root(parent, (int)(w & 0x7fffffffu)) : -1;
-        const unsigned bo = __ballot_sync(FULL, out);
-        if (bo) {
-          if (R < 0) R = __shfl_sync(FULL, rt, __ffs(bo) - 1);
-          ok = __all_sync(FULL, !out || rt == R);
+      if (ncomp == 1) {
+        // the processed prefix is ONE component: every earlier-block neighbour is in it, no entry needs reading
+        R = find_root(parent, 0);
+        a0 = a1;
+      }
+      // UNROLL chunks of 32 entries per step: the finds of a step are independent chains (two dependent
+      // shared-memory loads each in the common case), issued together to overlap their latency
+      constexpr int UNROLL = 4;
+      for (int j0 = a0; j0 < a1 && ok; j0 += 32 * UNROLL) {
+        uint32_t w[UNROLL];
+        int p1[UNROLL], p2[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+          const int c0 = j0 + 32 * k;
+          if (c0 < a1) adj.ensure(c0, min(c0 + 32, a1), lane);  // uniform
+          const int j = c0 + lane;
+          w[k] = j < a1 ? adj.at(j) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) p1[k] = (w[k] >> 31) ? (int)parent[w[k] & 0x7fffffffu] : -1;
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) p2[k] = p1[k] >= 0 ? (int)parent[p1[k]] : -1;
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+          const bool out = (w[k] >> 31) != 0;  // entries inside the block are cycle edges once everything hangs off R
+          int rt = p2[k];
+          if (out && p2[k] != p1[k]) rt = find_root(parent, p2[k]);  // deeper than two levels: walk (and halve) the rest
+          const unsigned bo = __ballot_sync(FULL, out);
+          if (bo) {
+            if (R < 0) R = __shfl_sync(FULL, rt, __ffs(bo) - 1);
+            ok = ok && __all_sync(FULL, !out || rt == R);
+          }
         }
       }
       if (ok) {
@@ -168,12 +191,13 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
         for (int x = s + lane; x < e; x += 32) parent[x] = (PT)R;
         __syncwarp();
         nmerge += e - s;
-        done = true;
+        done = true;  // ncomp unchanged: the block's vertices joined an existing component
       }
     }
 
     // ---------------- general block ----------------
     if (!done) {
+      const int merges_before = nmerge;
       int nrep = 0;
       for (int x = s; x < e && !bail; x++) {
         const int xrep0 = nrep;
@@ -259,6 +283,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
         np = __shfl_sync(FULL, np, 0);
         nmerge = __shfl_sync(FULL, nmerge, 0);
         __syncwarp();
+        ncomp += (e - s) - (nmerge - merges_before);
       }
     }
     s = e;
