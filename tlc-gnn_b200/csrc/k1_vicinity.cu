@@ -24,6 +24,8 @@ struct K1Shared {
   int32_t red[32];
   int32_t qcnt[2];
   int32_t target;
+  int32_t next;   // fill: next vicinity vertex to hand to a warp
+  int32_t ecur;   // fill: adjacency entries reserved so far
   unsigned long long dacc;  // algorithmic-byte accounting: sum of expanded degrees (D_u + D_v + D_S)
   unsigned long long xacc;  // ... and number of rowptr pairs read (X)
 };
@@ -153,37 +155,27 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
     const uint32_t* iw = bm_u;
     const uint32_t* wbase = bm_v;
 
-    int64_t vo = 0, eo = 0;
-    int32_t* vcnt = nullptr;
-    if (FILL) { vo = c.voff[t]; eo = c.eoff[t]; vcnt = c.vs0 + vo; }
-
-    // pass A: per vicinity vertex, count induced neighbours with a larger id
-    int msum = 0;
-    for (int w = wid; w < W; w += nw) {
-      uint32_t bits = iw[w];
-      while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int32_t x = w * 32 + b;
-        const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
-        int cnt = 0;
-        for (int32_t e = ra + lane; e < rb; e += 32) {
-          const int32_t y = g.col[e];
-          cnt += (y > x && test_bit(iw, y)) ? 1 : 0;
-        }
-        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (!FILL && lane == 0) atomicAdd(&sh.dacc, (unsigned long long)(rb - ra));
-        if (FILL && lane == 0) {
-          const int32_t lx = local_id(iw, wbase, x);
-          vcnt[lx] = cnt;
-          c.vert[vo + lx] = x;
-        }
-        msum += (lane == 0) ? cnt : 0;
-      }
-    }
-    const int m = block_reduce_sum(msum, sh.red);
-
     if (!FILL) {
+      // counting pass: per vicinity vertex, induced neighbours with a larger id
+      int msum = 0;
+      for (int w = wid; w < W; w += nw) {
+        uint32_t bits = iw[w];
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int32_t x = w * 32 + b;
+          const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
+          int cnt = 0;
+          for (int32_t e = ra + lane; e < rb; e += 32) {
+            const int32_t y = g.col[e];
+            cnt += (y > x && test_bit(iw, y)) ? 1 : 0;
+          }
+          for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+          if (lane == 0) atomicAdd(&sh.dacc, (unsigned long long)(rb - ra));
+          msum += (lane == 0) ? cnt : 0;
+        }
+      }
+      const int m = block_reduce_sum(msum, sh.red);
       if (tid == 0) {
         out_n[t] = n;
         out_m[t] = m;
@@ -200,35 +192,96 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
       continue;
     }
 
-    // pass B (fill): exclusive scan of the counts = start of every vertex's edge run
-    __syncthreads();
-    block_exclusive_scan(vcnt, n, sh.scan);
-    for (int w = wid; w < W; w += nw) {
+    // ---- fill: vertex list, then the induced adjacency (both directions, rows ascending) ----
+    const int64_t vo = c.voff[t], ao = 2 * c.eoff[t];
+    for (int w = tid; w < W; w += nt) {
       uint32_t bits = iw[w];
       int32_t lx = (int32_t)wbase[w];
       while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
-        const int32_t x = w * 32 + b;
-        const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
-        int64_t out = eo + vcnt[lx];
-        for (int32_t e0 = ra; e0 < rb; e0 += 32) {
-          const int32_t e = e0 + lane;
-          int32_t y = -1;
-          bool keep = false;
-          if (e < rb) { y = g.col[e]; keep = y > x && test_bit(iw, y); }
-          const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            const int64_t o = out + __popc(bal & lanemask_lt());
-            c.elo[o] = lx;
-            c.ehi[o] = local_id(iw, wbase, y);
-            c.ew[o] = g.kappa[e] + 1.0;  // graph[a][b]['weight'] = kappa + 1   riccidist2dgm.py:225
-          }
-          out += __popc(bal);
-        }
-        lx++;
+        c.vert[vo + lx++] = w * 32 + b;
       }
     }
+    if (tid == 0) { sh.next = 0; sh.ecur = 0; }
+    __syncthreads();
+    // a warp takes the next vertex, reserves its row in the target's adjacency segment (rows land in
+    // hand-out order; astart/adeg address them) and writes local neighbour ids + weights kappa+1
+    constexpr int RCH = 4;  // rows up to 32*RCH entries are scanned once (kept in registers between count and write)
+    for (;;) {
+      int lx = 0;
+      if (lane == 0) lx = atomicAdd(&sh.next, 1);
+      lx = __shfl_sync(0xffffffffu, lx, 0);
+      if (lx >= n) break;
+      const int32_t x = c.vert[vo + lx];
+      const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
+      if (rb - ra <= 32 * RCH) {
+        int32_t y[RCH];
+        unsigned bal[RCH];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < RCH; k++) {
+          const int32_t e = ra + 32 * k + lane;
+          y[k] = e < rb ? g.col[e] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < RCH; k++) {
+          bal[k] = __ballot_sync(0xffffffffu, y[k] >= 0 && test_bit(iw, y[k]));
+          cnt += __popc(bal[k]);
+        }
+        int start = 0;
+        if (lane == 0) start = atomicAdd(&sh.ecur, cnt);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (lane == 0) { c.astart[vo + lx] = start; c.adeg[vo + lx] = cnt; }
+        int64_t out = ao + start;
+        double wmin = 1e300;
+#pragma unroll
+        for (int k = 0; k < RCH; k++) {
+          if ((bal[k] >> lane) & 1u) {
+            const int64_t o = out + __popc(bal[k] & lanemask_lt());
+            const double w = g.kappa[ra + 32 * k + lane] + 1.0;  // graph[a][b]['weight'] = kappa + 1   riccidist2dgm.py:225
+            c.anb[o] = (uint32_t)local_id(iw, wbase, y[k]);
+            c.aw[o] = w;
+            wmin = fmin(wmin, w);
+          }
+          out += __popc(bal[k]);
+        }
+        for (int o = 16; o; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        if (lane == 0) c.aminw[vo + lx] = __double2float_rd(wmin);  // smallest incident weight, rounded down
+      } else {
+        int cnt = 0;
+        for (int32_t e0 = ra; e0 < rb; e0 += 32) {
+          const int32_t e = e0 + lane;
+          const bool keep = e < rb && test_bit(iw, g.col[e]);
+          cnt += __popc(__ballot_sync(0xffffffffu, keep));
+        }
+        int start = 0;
+        if (lane == 0) start = atomicAdd(&sh.ecur, cnt);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (lane == 0) { c.astart[vo + lx] = start; c.adeg[vo + lx] = cnt; }
+        int64_t out = ao + start;
+        double wmin = 1e300;
+        for (int32_t e0 = ra; e0 < rb; e0 += 32) {
+          const int32_t e = e0 + lane;
+          int32_t yy = -1;
+          bool keep = false;
+          if (e < rb) { yy = g.col[e]; keep = test_bit(iw, yy); }
+          const unsigned bl = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const int64_t o = out + __popc(bl & lanemask_lt());
+            const double w = g.kappa[e] + 1.0;
+            c.anb[o] = (uint32_t)local_id(iw, wbase, yy);
+            c.aw[o] = w;
+            wmin = fmin(wmin, w);
+          }
+          out += __popc(bl);
+        }
+        for (int o = 16; o; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        if (lane == 0) c.aminw[vo + lx] = __double2float_rd(wmin);
+      }
+    }
+    __syncthreads();
+    const int m = sh.ecur / 2;
     if (tid == 0) {
       c.tn[t] = n;
       c.tm[t] = m;

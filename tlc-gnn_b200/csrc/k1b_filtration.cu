@@ -3,12 +3,18 @@
 // Replaces filtration.build_fv(weight_graph=True, norm) (riccidist2dgm.py:20-61) and the KD copy
 // (Knowledge_Distillation/data_utils_NC.py:34-55).  The reference runs one nx.dijkstra_path per
 // (vertex, root) and sums kappa+1 along the returned path with python's sum(); here each root gets ONE
-// shortest-path computation inside the vicinity:
-//   1. distances: edge-parallel Bellman-Ford relaxations with 64-bit atomicMin on the ordered bit
-//      pattern of the (non-negative) float64 distance -- the least fixpoint of d[x] = min fl(d[y]+w),
-//      i.e. exactly what Dijkstra computes; both roots relax in the same sweep over the edge list;
-//   2. shortest-path tree: parent[x] = smallest local id y with fl(d[y] + w(y,x)) == d[x]
-//      (packed (y, edge) 64-bit atomicMin) -- the same rule as the oracle's fast mode;
+// shortest-path computation inside the vicinity, one CTA per vicinity, distances in shared memory:
+//   1. distances: Dijkstra in parallel phases.  Each phase settles EVERY tentative vertex x with
+//      d[x] <= fl(d_min + minw[x]), d_min the smallest tentative distance and minw[x] the smallest weight
+//      incident to x (Crauser et al.'s IN criterion: whatever still reaches x comes from a vertex at
+//      distance >= d_min over an edge >= minw[x]); fl(+) is monotone, so the test is exact in IEEE
+//      arithmetic.  The settled vertices' rows are relaxed with a 64-bit atomicMin on the bit pattern of
+//      the (non-negative) float64 distance in shared memory; every row is read once per root.  A warp
+//      takes 32 settled vertices at a time and walks their concatenated rows (row found by a shuffle
+//      bisection of the degree prefix), so all loads of a batch are independent;
+//   2. shortest-path tree, in the same row read: parent[x] = smallest local id y with
+//      fl(d[y] + w(y,x)) == d[x] (rows are ascending: the smallest matching row position) -- the same rule
+//      as the oracle's fast mode.  All candidates y are final when x settles (d[y] <= d[x] - minw[x] <= d_min);
 //   3. the path sum is re-accumulated from x towards the root in python-sum order (Neumaier
 //      compensated as CPython >= 3.12 does, or plain with TLC_F_SUM_PLAIN)  -- SURVEY.md F5;
 //   4. min / max / sum descriptors, block max-reduce, true division by the normaliser (:50-56).
@@ -38,18 +44,45 @@ __device__ __forceinline__ double pysum_get(const PySum& p, bool plain) {
   return p.s;
 }
 
-__global__ void filtration_kernel(Params p, ChunkView c) {
-  __shared__ double shd[32];
-  __shared__ int sh_changed;
+constexpr int QCAP = 2048;  // vertices settled per phase at most
+struct FiltShared {
+  double redd[32];
+  unsigned long long redu[32];
+  int32_t scan[1025];
+  // the phase's settled vertices: id, first entry in the concatenated rows (exclusive degree prefix),
+  // row start in the adjacency, smallest adjacency position of a tree-parent candidate
+  int32_t qx[QCAP], qpre[QCAP + 1], qrs[QCAP], qbest[QCAP];
+  int qn;
+};
+
+__device__ inline unsigned long long block_reduce_min_u64(unsigned long long v, unsigned long long* sh) {
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane_id() == 0) sh[w] = v;
+  __syncthreads();
+  unsigned long long t = sh[0];
+  for (int i = 1; i < nw; i++) t = sh[i] < t ? sh[i] : t;
+  __syncthreads();
+  return t;
+}
+
+__global__ void filtration_kernel(Params p, ChunkView c, int cap) {
+  extern __shared__ unsigned long long dyn64[];
+  __shared__ FiltShared sh;
   const int t = blockIdx.x;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int n = c.tn[t], m = c.tm[t];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int n = c.tn[t];
   if (n == 0) return;
   if (c.tstatus[t] > TLC_ST_TRIVIAL) return;
-  const int64_t vo = c.voff[t], eo = c.eoff[t];
-  const int32_t* __restrict__ elo = c.elo + eo;
-  const int32_t* __restrict__ ehi = c.ehi + eo;
-  const double* __restrict__ ew = c.ew + eo;
+  const int64_t vo = c.voff[t], ao = 2 * c.eoff[t];
+  const int32_t* __restrict__ astart = c.astart + vo;
+  const int32_t* __restrict__ adeg = c.adeg + vo;
+  const uint32_t* __restrict__ anb = c.anb + ao;
+  const double* __restrict__ aw = c.aw + ao;
   double* d1 = c.d1 + vo;
   double* d2 = c.d2 + vo;
   double* fval = c.fval + vo;
@@ -63,66 +96,111 @@ __global__ void filtration_kernel(Params p, ChunkView c) {
     // nx.NodeNotFound for every vertex -> dist = 100   riccidist2dgm.py:31-32,36-37
     for (int x = tid; x < n; x += nt) { d1[x] = 100.0; d2[x] = 100.0; }
   } else {
-    unsigned long long* da = c.v64a + vo;  // ordered bits of dist to lu
-    unsigned long long* db = c.v64b + vo;  // ... to lv
-    for (int x = tid; x < n; x += nt) { da[x] = INF_BITS; db[x] = INF_BITS; }
-    __syncthreads();
-    if (tid == 0) { da[lu] = 0ull; db[lv] = 0ull; }
-    __syncthreads();
-    // 1. relaxations until a sweep changes nothing (<= n sweeps: guards kappa+1 <= 0 misuse)
-    for (int round = 0; round < n + 1; round++) {
-      if (tid == 0) sh_changed = 0;
-      __syncthreads();
-      int ch = 0;
-      for (int e = tid; e < m; e += nt) {
-        const int a = elo[e], b = ehi[e];
-        const double w = ew[e];
-        {
-          const double xa = __longlong_as_double((long long)da[a]), xb = __longlong_as_double((long long)da[b]);
-          const double ta = __dadd_rn(xa, w), tb = __dadd_rn(xb, w);
-          if (ta < xb) { atomicMin(&da[b], (unsigned long long)__double_as_longlong(ta)); ch = 1; }
-          else if (tb < xa) { atomicMin(&da[a], (unsigned long long)__double_as_longlong(tb)); ch = 1; }
-        }
-        if (two) {
-          const double xa = __longlong_as_double((long long)db[a]), xb = __longlong_as_double((long long)db[b]);
-          const double ta = __dadd_rn(xa, w), tb = __dadd_rn(xb, w);
-          if (ta < xb) { atomicMin(&db[b], (unsigned long long)__double_as_longlong(ta)); ch = 1; }
-          else if (tb < xa) { atomicMin(&db[a], (unsigned long long)__double_as_longlong(tb)); ch = 1; }
-        }
-      }
-      if (ch) sh_changed = 1;
-      __syncthreads();
-      const int any = sh_changed;
-      __syncthreads();
-      if (!any) break;
-    }
-    // 2.+3. per root: tree by packed (parent, edge) atomicMin, then python-order path sums
-    unsigned long long* key = c.v64c + vo;  // packed (parent, edge) of the shortest-path tree
+    const bool in_smem = n <= cap;
+    unsigned long long* dist = in_smem ? dyn64 : c.v64a + vo;
+    uint8_t* state = in_smem ? reinterpret_cast<uint8_t*>(dyn64 + cap) : reinterpret_cast<uint8_t*>(c.vs1 + vo);
+    int32_t* tpar = c.vs2 + vo;                            // shortest-path tree: parent and weight of the parent edge
+    double* tpw = reinterpret_cast<double*>(c.v64b + vo);
+    const float* __restrict__ aminw = c.aminw + vo;
+    constexpr uint8_t FAR = 0, TENT = 1, DONE = 2;
     for (int r = 0; r < (two ? 2 : 1); r++) {
-      unsigned long long* dist = r == 0 ? da : db;
       const int root = r == 0 ? lu : lv;
       double* out = r == 0 ? d1 : d2;
-      for (int x = tid; x < n; x += nt) key[x] = ~0ull;
+      for (int x = tid; x < n; x += nt) { dist[x] = INF_BITS; state[x] = FAR; tpar[x] = root; tpw[x] = 0.0; }
       __syncthreads();
-      for (int e = tid; e < m; e += nt) {
-        const int a = elo[e], b = ehi[e];
-        const double w = ew[e];
-        const double xa = __longlong_as_double((long long)dist[a]), xb = __longlong_as_double((long long)dist[b]);
-        if (__dadd_rn(xa, w) == xb) atomicMin(&key[b], ((unsigned long long)(uint32_t)a << 32) | (uint32_t)e);
-        if (__dadd_rn(xb, w) == xa) atomicMin(&key[a], ((unsigned long long)(uint32_t)b << 32) | (uint32_t)e);
+      if (tid == 0) { dist[root] = 0ull; state[root] = TENT; }
+      __syncthreads();
+      for (int phase = 0; phase < 2 * n + 2; phase++) {  // every phase settles at least one vertex
+        // ---- smallest tentative distance ----
+        unsigned long long lmin = INF_BITS;
+        for (int x = tid; x < n; x += nt)
+          if (state[x] == TENT) { const unsigned long long d = dist[x]; lmin = d < lmin ? d : lmin; }
+        const unsigned long long dminb = block_reduce_min_u64(lmin, sh.redu);
+        if (dminb == INF_BITS) break;  // nothing tentative left (the rest is unreachable)
+        const double dmin = __longlong_as_double((long long)dminb);
+        // ---- settle: d[x] <= fl(dmin + minw[x]); at most QCAP per phase (the others stay tentative) ----
+        if (tid == 0) sh.qn = 0;
+        __syncthreads();
+        for (int x0 = 0; x0 < n; x0 += nt) {
+          const int x = x0 + tid;
+          bool take = false;
+          if (x < n && state[x] == TENT) {
+            const double thr = __dadd_rn(dmin, (double)aminw[x]);
+            take = __longlong_as_double((long long)dist[x]) <= thr;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, take);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sh.qn, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int pos = base + __popc(bal & lanemask_lt());
+            if (take && pos < QCAP) {
+              state[x] = DONE;
+              sh.qx[pos] = x;
+              sh.qpre[pos] = adeg[x];
+              sh.qrs[pos] = astart[x];
+              sh.qbest[pos] = 0x7fffffff;
+            }
+          }
+        }
+        __syncthreads();
+        const int qn = min(sh.qn, QCAP);
+        const int total = block_exclusive_scan(sh.qpre, qn, sh.scan);  // qpre[i] = first entry of row i in the phase's concatenation
+        if (tid == 0) sh.qpre[qn] = total;
+        __syncthreads();
+        // ---- relax the settled rows, every warp an equal share of the concatenated entries (coalesced);
+        //      the same read picks the tree parent of each settled vertex ----
+        {
+          const int span = ((total + nw - 1) / nw + 31) & ~31;
+          const int e1 = min((wid + 1) * span, total);
+          int e = wid * span + lane;
+          if (e < e1) {
+            int lo = 0, hi = qn;  // row i: largest i with qpre[i] <= e
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.qpre[mid] <= e) lo = mid; else hi = mid; }
+            int i = lo, nxt = sh.qpre[i + 1];
+            while (e >= nxt) { i++; nxt = sh.qpre[i + 1]; }  // (rows of degree 0)
+            int off = sh.qrs[i] - sh.qpre[i];
+            unsigned long long dxb = dist[sh.qx[i]];
+            for (; e < e1; e += 32) {
+              if (e >= nxt) {
+                do { i++; nxt = sh.qpre[i + 1]; } while (e >= nxt);
+                off = sh.qrs[i] - sh.qpre[i];
+                dxb = dist[sh.qx[i]];
+              }
+              const int a = off + e;
+              const int y = (int)anb[a];
+              const double w = aw[a];
+              const unsigned long long dyb = dist[y];
+              const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dxb), w));
+              if (tb < dyb) {
+                atomicMin(&dist[y], tb);
+                if (state[y] == FAR) state[y] = TENT;
+              }
+              // y a parent of the row's vertex?  (d[y] is final whenever this can hold)
+              if (dyb != INF_BITS &&
+                  (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dxb)
+                atomicMin(&sh.qbest[i], a);
+            }
+          }
+        }
+        __syncthreads();
+        for (int i = tid; i < qn; i += nt) {
+          const int x = sh.qx[i], a = sh.qbest[i];
+          if (x != root && a != 0x7fffffff) { tpar[x] = (int)anb[a]; tpw[x] = aw[a]; }
+        }
       }
       __syncthreads();
+      // ---- 3. python-order path sums ----
       for (int x = tid; x < n; x += nt) {
         double res;
         if (x == root) res = 0.0;
-        else if (dist[x] == INF_BITS) res = 100.0;  // nx.NetworkXNoPath -> 100 (disconnected vicinity; status 3 later)
+        else if (state[x] != DONE) res = 100.0;  // nx.NetworkXNoPath -> 100 (disconnected vicinity; status 3 later)
         else {
           PySum ps{0.0, 0.0, 0};
           int y = x, guard = 0;
           while (y != root && guard++ <= n) {
-            const unsigned long long k = key[y];
-            pysum_add(ps, ew[(uint32_t)k], plain);  // ricci_curv[(path[y], path[y+1])] + 1   :30
-            y = (int)(k >> 32);
+            pysum_add(ps, tpw[y], plain);  // ricci_curv[(path[y], path[y+1])] + 1   :30
+            y = tpar[y];
           }
           res = pysum_get(ps, plain);
         }
@@ -144,8 +222,8 @@ __global__ void filtration_kernel(Params p, ChunkView c) {
     mx = fmax(mx, fmax(a, b));
     sm = fmax(sm, node_mode ? a : __dadd_rn(a, b));
   }
-  double smax = block_reduce_max(mx, shd);
-  double ssum = block_reduce_max(sm, shd);
+  double smax = block_reduce_max(mx, sh.redd);
+  double ssum = block_reduce_max(sm, sh.redd);
   const bool norm = (p.flags & TLC_F_NORM) != 0;
   if (norm) {
     if (p.flags & TLC_F_NORM_EPS) { smax = __dadd_rn(smax, 1e-10); ssum = __dadd_rn(ssum, 1e-10); }
@@ -167,8 +245,13 @@ __global__ void filtration_kernel(Params p, ChunkView c) {
 
 }  // namespace
 
-void launch_filtration(const Params& p, const ChunkView& c, int block, cudaStream_t st) {
-  filtration_kernel<<<c.T, block, 0, st>>>(p, c);
+void launch_filtration(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st) {
+  // dist (8) + state (1) bytes per vertex in shared memory when the chunk's largest vicinity fits
+  int cap = (int)((n_max + 7) / 8 * 8);
+  if ((size_t)cap * 9 > 180 * 1024) cap = 0;
+  const size_t bytes = (size_t)cap * 9;
+  cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  filtration_kernel<<<c.T, block, bytes, st>>>(p, c, cap);
   count_launch();
 }
 

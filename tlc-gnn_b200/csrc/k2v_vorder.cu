@@ -1,4 +1,4 @@
-// k2v_vorder.cu -- kernel 2v: the vertex order of every vicinity and its rank-space lower adjacency.
+// k2v_vorder.cu -- kernel 2v: the vertex order of every vicinity, cut into blocks.
 //
 // Replaces, together with kernel 3v, the ascending half of perturb_filter_function + Union_find
 // (accelerated_PD.py:6-23, :27-68) WITHOUT sorting the m edges.  The reference sorts all simplices by
@@ -15,10 +15,11 @@
 // One CTA per vicinity:
 //   1. stable LSD radix sort of the n vertices on the ordered image of their float64 value
 //      (ties keep ascending local id)                    -> vord[rank] = local id, vrank[local id] = rank
-//   2. block starts (bit 31 of bfirst[b]: the block holds distinct values, i.e. a near-tie block)
-//   3. counting sort of the m edges by owner rank        -> loff[n+1], ladj[m] = rank of the other endpoint
-//      (bit 31: it lies in an earlier block), bend[b] = end of block b's edges | block flags
-//   4. local ids of the essential pair [min, max]        (accelerated_PD.py:35-38,110: first vertex in
+//   2. block starts bfirst[b], with two flags kernel 3v decides on:
+//        bit 31: the block holds distinct values (a near-tie block: edge keys inside it interleave)
+//        bit 30: every vertex of the block has a neighbour in an EARLIER block (one early-exit scan of
+//                its adjacency row against the packed rank/block table in shared memory)
+//   3. local ids of the essential pair [min, max]        (accelerated_PD.py:35-38,110: first vertex in
 //      ascending id attaining the extreme value)
 #include "tlc_common.cuh"
 #include "tlc_sort.cuh"
@@ -31,16 +32,14 @@ __global__ void vorder_kernel(Params p, ChunkView c, int smem_ints) {
   __shared__ SortShared sh;
   const int t = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int n = c.tn[t], m = c.tm[t];
+  const int n = c.tn[t];
   if (tid == 0) c.tfb[t] = 0;
   if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
-  const int64_t vo = c.voff[t], eo = c.eoff[t];
+  const int64_t vo = c.voff[t], ao = 2 * c.eoff[t];
   const double* __restrict__ fval = c.fval + vo;
   int32_t* vord = c.vord + vo;
   int32_t* vrank = c.vrank + vo;
   int32_t* bfirst = c.bfirst + vo + t;
-  int32_t* loff = c.loff + vo + t;
-  int32_t* bend = c.bend + vo + t;
 
   // ---- 1. vertex order ----
   unsigned long long* k0 = c.v64a + vo;
@@ -75,70 +74,38 @@ __global__ void vorder_kernel(Params p, ChunkView c, int smem_ints) {
   for (int i = tid; i < n; i += nt) own[i] = flag[i];
   __syncthreads();
   const int nb = block_exclusive_scan(flag, n, sh.scan);  // flag[i] = #starts before i
-  for (int i = tid; i < n; i += nt) if (own[i]) bfirst[flag[i]] = i;
+  for (int i = tid; i < n; i += nt) if (own[i]) bfirst[flag[i]] = i | 0x40000000;  // bit 30 cleared below where it fails
   if (tid == 0) { bfirst[nb] = n; c.tnb[t] = nb; c.tminv[t] = (int32_t)ps[0]; }
   __syncthreads();
+  // block index of every LOCAL id, in shared memory when it fits (16-bit when nb < 65536)
+  const bool in_smem = n <= smem_ints;
+  int32_t* sblk = in_smem ? dyn : c.vcls + vo;
   for (int i = tid; i < n; i += nt) {
-    if (i > 0 && !own[i] && ks[i] != ks[i - 1]) atomicOr(&bfirst[flag[i] - 1 + own[i]], (int32_t)0x80000000);
+    const int bidx = flag[i] - 1 + own[i];
+    sblk[ps[i]] = bidx;
+    if (i > 0 && !own[i] && ks[i] != ks[i - 1]) atomicOr(&bfirst[bidx], (int32_t)0x80000000);
     // essential maximum: first rank attaining the largest value
     if (ks[i] == ks[n - 1] && (i == 0 || ks[i - 1] != ks[n - 1])) c.tmaxv[t] = (int32_t)ps[i];
   }
   __syncthreads();
-  // ---- 3. rank-space lower adjacency ----
-  // srank[local id] = rank | block index << 16 (both < 65536 here)
-  if (n >= 65536) {  // 16-bit packing does not hold: leave this target to the edge-sorted kernels 2 + 3
-    if (tid == 0) c.tfb[t] = 1;
-    return;
-  }
-  const bool in_smem = 2 * n <= smem_ints;
-  int32_t* cnt = in_smem ? dyn : c.vs2 + vo;         // flag[] is dead from here on
-  uint32_t* srank = in_smem ? reinterpret_cast<uint32_t*>(dyn + n) : reinterpret_cast<uint32_t*>(c.vcls + vo);
-  for (int i = tid; i < n; i += nt) {
-    cnt[i] = 0;
-    srank[ps[i]] = (uint32_t)i | ((uint32_t)(flag[i] - 1 + own[i]) << 16);
-  }
-  __syncthreads();
-  const int32_t* __restrict__ elo = c.elo + eo;
-  const int32_t* __restrict__ ehi = c.ehi + eo;
-  for (int e = tid; e < m; e += nt) {
-    const int ra = (int)(srank[elo[e]] & 0xffffu), rb = (int)(srank[ehi[e]] & 0xffffu);
-    atomicAdd(&cnt[max(ra, rb)], 1);
-  }
-  __syncthreads();
-  block_exclusive_scan(cnt, n, sh.scan);
-  for (int i = tid; i < n; i += nt) loff[i] = cnt[i];
-  if (tid == 0) loff[n] = m;
-  __syncthreads();
-  // ladj entry = rank of the earlier endpoint | bit 31 when it lies in an EARLIER block than the owner
-  uint32_t* ladj = c.ladj + eo;
-  for (int e = tid; e < m; e += nt) {
-    const uint32_t wa = srank[elo[e]], wb = srank[ehi[e]];
-    const uint32_t wo = (wa & 0xffffu) > (wb & 0xffffu) ? wa : wb, wy = wo == wa ? wb : wa;
-    const int pos = atomicAdd(&cnt[wo & 0xffffu], 1);
-    ladj[pos] = (wy & 0xffffu) | ((wy >> 16) != (wo >> 16) ? 0x80000000u : 0u);
-  }
-  __syncthreads();  // ladj of this vicinity complete (global writes of the block visible to the block)
-  // per block: end of its owned edges | bit 31 distinct values | bit 30 every vertex has an earlier-block neighbour
-  for (int b = tid; b < nb; b += nt) {
-    const int s0 = bfirst[b] & 0x7fffffff, s1 = bfirst[b + 1] & 0x7fffffff;
-    bool all_out = true;
-    for (int x = s0; x < s1 && all_out; x++) {
-      bool has = false;
-      for (int j = loff[x]; j < loff[x + 1] && !has; j++) has = (ladj[j] >> 31) != 0;
-      all_out = has;
-    }
-    bend[b] = loff[s1] | (bfirst[b] & (int32_t)0x80000000) | (all_out ? 0x40000000 : 0);
+  const int32_t* __restrict__ astart = c.astart + vo;
+  const int32_t* __restrict__ adeg = c.adeg + vo;
+  const uint32_t* __restrict__ anb = c.anb + ao;
+  for (int x = tid; x < n; x += nt) {  // x: local id
+    const int bx = sblk[x];
+    const int a = astart[x], dg = adeg[x];
+    bool has = false;
+    for (int j = 0; j < dg && !has; j++) has = sblk[anb[a + j]] < bx;
+    if (!has) atomicAnd(&bfirst[bx], (int32_t)~0x40000000);
   }
 }
 
 }  // namespace
 
 void launch_vorder(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st) {
-  const int64_t want = 2 * n_max;
-  const int smem_ints = want * 4 <= 160 * 1024 ? (int)want : 0;
+  const int smem_ints = n_max * 4 <= 160 * 1024 ? (int)n_max : 0;
   const size_t bytes = (size_t)smem_ints * 4;
-  if (bytes > 8 * 1024)
-    cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   vorder_kernel<<<c.T, block, bytes, st>>>(p, c, smem_ints);
   count_launch();
 }

@@ -46,52 +46,6 @@ __device__ __forceinline__ int find_root(PT* p, int x) {  // path halving  accel
   }
 }
 
-// ---- the lower-adjacency stream: kernel 2v laid the owned edges out in sweep order, so the warp reads ladj
-// strictly front to back.  A per-warp shared-memory ring is kept RING-CHUNK entries ahead with cp.async.
-constexpr int RING = 512, CHUNK = 128;
-
-struct AdjStream {
-  const uint32_t* src;
-  uint32_t* ring;
-  int m, fetched, arrived;
-  __device__ __forceinline__ void issue(int lane) {
-#pragma unroll
-    for (int k = 0; k < CHUNK / 32; k++) {
-      const int idx = fetched + k * 32 + lane;
-      if (idx < m) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (idx & (RING - 1)));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + idx) : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    fetched += CHUNK;
-  }
-  // make entries [j0, j1) readable (j1 - j0 <= 32); entries below j0 are dead.  Uniform over the warp.
-  __device__ __forceinline__ void ensure(int j0, int j1, int lane) {
-    if (j0 >= fetched + CHUNK) {  // the reader skipped ahead (blocks handled off-stream): drop the gap
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      fetched = j0 / CHUNK * CHUNK;
-      arrived = fetched;
-    }
-    if (fetched < m && fetched + CHUNK - j0 <= RING) {
-      __syncwarp();  // every lane is done reading the slots about to be overwritten
-      while (fetched < m && fetched + CHUNK - j0 <= RING) issue(lane);
-    }
-    if (j1 > arrived) {
-      const int need_end = (j1 + CHUNK - 1) / CHUNK * CHUNK;
-      const int later = (fetched - need_end) / CHUNK;  // groups issued after the one needed: may stay in flight
-      if (later >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
-      else if (later == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-      else if (later == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      arrived = fetched - (later >= 3 ? 3 : later) * CHUNK;
-    }
-  }
-  __device__ __forceinline__ uint32_t at(int j) const { return ring[j & (RING - 1)]; }
-};
-
 __device__ __forceinline__ bool rep_less(unsigned long long ka, int la, int ha, unsigned long long kb, int lb, int hb) {
   if (ka != kb) return ka < kb;
   if (la != lb) return la < lb;  // canonical edge index order == lexicographic (lo, hi)
@@ -102,7 +56,6 @@ template <typename PT>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, ChunkView c, int cap) {
   extern __shared__ unsigned char dyn_raw[];
   __shared__ RepBuf reps_all[SWEEP_WARPS];
-  __shared__ uint32_t ring_all[SWEEP_WARPS][RING];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int t = blockIdx.x * SWEEP_WARPS + wid;
   if (t >= c.T) return;
@@ -110,10 +63,11 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
   const int64_t vo = c.voff[t], eo = c.eoff[t], po = c.poff(t);
   const int32_t* __restrict__ vord = c.vord + vo;
+  const int32_t* __restrict__ vrank = c.vrank + vo;
   const int32_t* __restrict__ bfirst = c.bfirst + vo + t;
-  const int32_t* __restrict__ bend = c.bend + vo + t;
-  const int32_t* __restrict__ loff = c.loff + vo + t;
-  const uint32_t* __restrict__ ladj = c.ladj + eo;
+  const int32_t* __restrict__ astart = c.astart + vo;
+  const int32_t* __restrict__ adeg = c.adeg + vo;
+  const uint32_t* __restrict__ anb = c.anb + 2 * eo;
   const double* __restrict__ fval = c.fval + vo;
   PT* parent = n <= cap ? reinterpret_cast<PT*>(dyn_raw) + (size_t)wid * cap : reinterpret_cast<PT*>(c.vs2 + vo);
   RepBuf& rb = reps_all[wid];
@@ -124,28 +78,28 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   for (int r = lane; r < n; r += 32) parent[r] = (PT)r;
   __syncwarp();
 
-  AdjStream adj{ladj, ring_all[wid], c.tm[t], 0, 0};
   int np = 0, nmerge = 0;
   int ncomp = 0;  // components among the vertices of the blocks processed so far
   bool bail = false;
-  int s = 0, a0 = 0;
+  int s = 0;
   // block table, 32 blocks per coalesced load, the next group already in flight
-  int cur_first = 0, cur_end = 0, nxt_first = 0, nxt_end = 0;
-  {
-    const int i = lane;
-    if (i < nb) { nxt_first = bfirst[i + 1]; nxt_end = bend[i]; }
-  }
+  int cur_first = 0, nxt_first = 0;
+  if (lane <= nb) nxt_first = bfirst[lane];
+  int carry = 0;  // bfirst[b] of the current block (flags), handed over from the previous iteration
   for (int b = 0; b < nb && !bail; b++) {
     if ((b & 31) == 0) {
-      cur_first = nxt_first; cur_end = nxt_end;
+      cur_first = nxt_first;
       const int i = b + 32 + lane;
-      if (i < nb) { nxt_first = bfirst[i + 1]; nxt_end = bend[i]; }
+      if (i <= nb) nxt_first = bfirst[i];
+      carry = __shfl_sync(FULL, cur_first, 0);
     }
-    const int e = __shfl_sync(FULL, cur_first, b & 31) & 0x7fffffff;
-    const int we = __shfl_sync(FULL, cur_end, b & 31);
-    const bool distinct = we < 0;
-    const bool all_out = ((we >> 30) & 1) != 0;  // every vertex of the block has a neighbour in an earlier block
-    const int a1 = we & 0x3fffffff;
+    const int wb = carry;
+    // bfirst[b + 1]: lane (b+1)&31 of the current group, or lane 0 of the next one
+    const int wn = ((b + 1) & 31) ? __shfl_sync(FULL, cur_first, (b + 1) & 31) : __shfl_sync(FULL, nxt_first, 0);
+    carry = wn;
+    const int e = wn & 0x3fffffff;
+    const bool distinct = wb < 0;
+    const bool all_out = ((wb >> 30) & 1) != 0;  // every vertex of the block has a neighbour in an earlier block
 
     // ---------------- trivial block test ----------------
     bool done = false;
@@ -153,36 +107,23 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
       int R = -1;
       bool ok = true;
       if (ncomp == 1) {
-        // the processed prefix is ONE component: every earlier-block neighbour is in it, no entry needs reading
+        // the processed prefix is ONE component: every earlier-block neighbour is in it, no row needs reading
         R = find_root(parent, 0);
-        a0 = a1;
-      }
-      // UNROLL chunks of 32 entries per step: the finds of a step are independent chains (two dependent
-      // shared-memory loads each in the common case), issued together to overlap their latency
-      constexpr int UNROLL = 4;
-      for (int j0 = a0; j0 < a1 && ok; j0 += 32 * UNROLL) {
-        uint32_t w[UNROLL];
-        int p1[UNROLL], p2[UNROLL];
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) {
-          const int c0 = j0 + 32 * k;
-          if (c0 < a1) adj.ensure(c0, min(c0 + 32, a1), lane);  // uniform
-          const int j = c0 + lane;
-          w[k] = j < a1 ? adj.at(j) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) p1[k] = (w[k] >> 31) ? (int)parent[w[k] & 0x7fffffffu] : -1;
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) p2[k] = p1[k] >= 0 ? (int)parent[p1[k]] : -1;
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) {
-          const bool out = (w[k] >> 31) != 0;  // entries inside the block are cycle edges once everything hangs off R
-          int rt = p2[k];
-          if (out && p2[k] != p1[k]) rt = find_root(parent, p2[k]);  // deeper than two levels: walk (and halve) the rest
-          const unsigned bo = __ballot_sync(FULL, out);
-          if (bo) {
-            if (R < 0) R = __shfl_sync(FULL, rt, __ffs(bo) - 1);
-            ok = ok && __all_sync(FULL, !out || rt == R);
+      } else {
+        // several components below: all earlier-block neighbours of the block must share one root
+        for (int x = s; x < e && ok; x++) {
+          const int lx = vord[x];
+          const int a = astart[lx], dg = adeg[lx];
+          for (int j0 = 0; j0 < dg && ok; j0 += 32) {
+            const int j = j0 + lane;
+            const int ry = j < dg ? vrank[anb[a + j]] : e;  // e: "not in an earlier block", ignored
+            const bool out = ry < s;
+            const int rt = out ? find_root(parent, ry) : -1;
+            const unsigned bo = __ballot_sync(FULL, out);
+            if (bo) {
+              if (R < 0) R = __shfl_sync(FULL, rt, __ffs(bo) - 1);
+              ok = __all_sync(FULL, !out || rt == R);
+            }
           }
         }
       }
@@ -203,15 +144,18 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
         const int xrep0 = nrep;
         const int lx = vord[x];
         const double fx = fval[lx];
-        const int xa = loff[x], xb = loff[x + 1];
-        for (int j0 = xa; j0 < xb && !bail; j0 += 32) {
+        const int xa = astart[lx], xdg = adeg[lx];
+        for (int j0 = 0; j0 < xdg && !bail; j0 += 32) {
           const int j = j0 + lane;
-          const bool valid = j < xb;
           int y = 0, ly = 0, ry = -1, lo = 0, hi = 0;
           unsigned long long K = 0;
+          bool valid = false;
+          if (j < xdg) {
+            ly = (int)anb[xa + j];
+            y = vrank[ly];
+            valid = y < x;  // the edge is owned by its later endpoint
+          }
           if (valid) {
-            y = (int)(ladj[j] & 0x7fffffffu);
-            ly = vord[y];
             ry = find_root(parent, y);  // no union has happened in this block yet: component at block start
             K = f64_to_ordered(key_asc(fx, fval[ly]));
             lo = min(lx, ly); hi = max(lx, ly);
@@ -255,7 +199,6 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
         }
         __syncwarp();
         if (lane == 0) {
-          const int32_t* vrank = c.vrank + vo;
           for (int i = 0; i < nrep; i++) {
             const int q = rb.perm[i];
             const int a = rb.lo[q], bb = rb.hi[q];  // edge = [a, b], a < b (local ids)
@@ -287,9 +230,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
       }
     }
     s = e;
-    a0 = a1;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   if (lane == 0) {
     if (bail) {

@@ -42,10 +42,10 @@ static constexpr size_t ALIGN = 256;
 static size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
 // bytes of arena per vertex / edge / pair slot (see carve())
-static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3 + 4 * 5;           // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c | vord vrank bfirst loff bend
-static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1 + 4;       // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg | ladj
+static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3 + 4 * 6;           // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c | vord vrank bfirst astart adeg aminw
+static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1 + 2 * 12;  // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg | anb aw (2 per edge)
 static constexpr size_t BP = 1 + 4 * 2 + 8 * 2;                       // pkind | pbv pdv | pbirth pdeath
-static constexpr size_t BT = 8 * 3 + 4 * 11 + 2 + 4 * 3;              // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls tnb tminv tmaxv | tstatus tfb | bfirst/loff/bend terminators
+static constexpr size_t BT = 8 * 3 + 4 * 11 + 2 + 4;                  // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls tnb tminv tmaxv | tstatus tfb | bfirst terminator
 
 struct tlc_graph {
   int device = 0;
@@ -190,8 +190,9 @@ static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, const int
   c.tstatus = take<uint8_t>(cur, T);
   c.tfb = take<uint8_t>(cur, T);
   c.vord = take<int32_t>(cur, Nv); c.vrank = take<int32_t>(cur, Nv);
-  c.bfirst = take<int32_t>(cur, Nv + T); c.loff = take<int32_t>(cur, Nv + T); c.bend = take<int32_t>(cur, Nv + T);
-  c.ladj = take<uint32_t>(cur, Ne);
+  c.bfirst = take<int32_t>(cur, Nv + T);
+  c.astart = take<int32_t>(cur, Nv); c.adeg = take<int32_t>(cur, Nv); c.aminw = take<float>(cur, Nv);
+  c.anb = take<uint32_t>(cur, 2 * Ne); c.aw = take<double>(cur, 2 * Ne);
   c.vert = take<int32_t>(cur, Nv); c.vcls = take<int32_t>(cur, Nv); c.vs0 = take<int32_t>(cur, Nv);
   c.vs1 = take<int32_t>(cur, Nv); c.vs2 = take<int32_t>(cur, Nv); c.neg = take<int32_t>(cur, Nv);
   c.fval = take<double>(cur, Nv); c.d1 = take<double>(cur, Nv); c.d2 = take<double>(cur, Nv);
@@ -256,7 +257,7 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   tm.mark(1);
   launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
-  launch_filtration(p, c, block, st);
+  launch_filtration(p, c, block, n_max, st);
   // ascending sweep: vertex-ordered kernels 2v + 3v; targets they hand back (tfb) and, when the descending
   // sweep is wanted (diagram output, Pos/Neg lists for the loops), the edge-sorted kernels 2 + 3.  The image
   // only needs PD_up and [min,max]: PD_down and [max,min] have death <= birth, i.e. weight 0.
@@ -272,6 +273,8 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
     launch_sweep(p, c, n_max, st);
   }
   tm.mark(5);
+  // the edge-sorted kernels work on the canonical (lo, hi) edge list, derived from the adjacency where needed
+  launch_edgelist(p, c, block, want_desc ? 0 : 1, st);
   // kernel 3b ranks loop edges by their position in the ascending order, so `extended` needs ord_asc of every target
   launch_sort(p, c, block, want_desc ? 3 : 1, want_desc ? 0 : 1, st);
   tm.mark(6);
@@ -507,6 +510,7 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
     CK(cudaMemcpy(d_kappa, kappa, (size_t)nnz * 8, cudaMemcpyHostToDevice));
   }
   g->gv = GraphView{N, nnz, d_rowptr, d_col, d_kappa};
+
   CK(cudaMalloc((void**)&g->work_counter, 64));
   *out = g;
   return TLC_OK;

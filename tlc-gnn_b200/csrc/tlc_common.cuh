@@ -37,11 +37,14 @@ struct ChunkView {
   unsigned long long *v64a, *v64b, *v64c;
   int32_t *vord, *vrank;  // kernel 2v: rank -> local id, local id -> rank in the (value, id) vertex order
   // (n+1)-per-target arrays, addressed at voff[t] + t
-  int32_t *bfirst;  // first rank of every block of the vertex order (bit 31: block holds distinct values), [nb] = n
-  int32_t *loff;    // start of every rank's lower adjacency in ladj (relative to eoff[t]), [n] = m
-  int32_t *bend;    // per block: end of the block's owned edges in ladj | bit 31 of bfirst
-  // edge-indexed
-  uint32_t* ladj;   // rank-space lower adjacency: for owner rank r the ranks (< r) of its neighbours
+  int32_t *bfirst;  // first rank of every block of the vertex order | flags in bits 31, 30 (kernel 2v), [nb] = n
+  // induced adjacency (kernel 1), both directions: row of local vertex x = [astart[x], astart[x] + adeg[x])
+  // inside the target's segment, which starts at 2 * eoff[t]; rows ascending in local id
+  int32_t *astart, *adeg;  // vertex-indexed
+  float* aminw;            // vertex-indexed: smallest incident weight, rounded down (settling criterion of kernel 1b)
+  uint32_t* anb;           // [2 * sum m] neighbour local ids
+  double* aw;              // [2 * sum m] kappa + 1
+  // edge-indexed (canonical lexicographic (lo, hi) edge list: kernel 1c, only for the edge-sorted kernels)
   int32_t *elo, *ehi, *pos, *arank;
   double* ew;
   uint32_t *ord_asc, *ord_desc, *sp0, *sp1;
@@ -142,7 +145,9 @@ void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* t
                            int* work_counter, cudaStream_t st);
 void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                           int* work_counter, cudaStream_t st);
-void launch_filtration(const Params& p, const ChunkView& c, int block, cudaStream_t st);
+void launch_filtration(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st);
+// canonical edge list (elo, ehi, ew) from the adjacency; fb_only: only for targets with tfb[t] != 0
+void launch_edgelist(const Params& p, const ChunkView& c, int block, int fb_only, cudaStream_t st);
 // sweep_mask: bit 0 ascending, bit 1 descending.  fb_only: the ascending sweep only for targets with tfb[t] != 0.
 void launch_sort(const Params& p, const ChunkView& c, int block, int sweep_mask, int fb_only, cudaStream_t st);
 void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_ints, int build_lists, int sweep_mask,

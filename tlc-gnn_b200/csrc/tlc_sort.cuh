@@ -5,7 +5,7 @@
 
 namespace tlc {
 
-constexpr int SORT_MAX_WARPS = 32;
+constexpr int SORT_MAX_WARPS = 16;  // blocks of at most 512 threads
 constexpr int SORT_ITEMS = 4;
 
 struct SortShared {
