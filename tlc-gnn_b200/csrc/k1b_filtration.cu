@@ -44,7 +44,7 @@ __device__ __forceinline__ double pysum_get(const PySum& p, bool plain) {
   return p.s;
 }
 
-constexpr int QCAP = 2048;  // vertices settled per phase at most
+constexpr int QCAP = 1024;  // vertices settled per phase at most
 struct FiltShared {
   double redd[32];
   unsigned long long redu[32];
@@ -70,10 +70,10 @@ __device__ inline unsigned long long block_reduce_min_u64(unsigned long long v, 
   return t;
 }
 
-__global__ void filtration_kernel(Params p, ChunkView c, int cap) {
+__global__ void filtration_kernel(Params p, ChunkView c, int t0, int cap) {
   extern __shared__ unsigned long long dyn64[];
   __shared__ FiltShared sh;
-  const int t = blockIdx.x;
+  const int t = t0 + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   const int n = c.tn[t];
   if (n == 0) return;
@@ -161,25 +161,44 @@ __global__ void filtration_kernel(Params p, ChunkView c, int cap) {
             while (e >= nxt) { i++; nxt = sh.qpre[i + 1]; }  // (rows of degree 0)
             int off = sh.qrs[i] - sh.qpre[i];
             unsigned long long dxb = dist[sh.qx[i]];
-            for (; e < e1; e += 32) {
-              if (e >= nxt) {
-                do { i++; nxt = sh.qpre[i + 1]; } while (e >= nxt);
-                off = sh.qrs[i] - sh.qpre[i];
-                dxb = dist[sh.qx[i]];
+            // RU entries per lane and step: the row bookkeeping runs ahead in shared memory, then all loads of
+            // the step are issued before the first use
+            constexpr int RU = 4;
+            for (; e < e1; e += 32 * RU) {
+              int ai[RU], ri[RU];
+              unsigned long long dx[RU];
+#pragma unroll
+              for (int k = 0; k < RU; k++) {
+                const int ek = e + 32 * k;
+                if (ek < e1) {
+                  if (ek >= nxt) {
+                    do { i++; nxt = sh.qpre[i + 1]; } while (ek >= nxt);
+                    off = sh.qrs[i] - sh.qpre[i];
+                    dxb = dist[sh.qx[i]];
+                  }
+                  ai[k] = off + ek; ri[k] = i; dx[k] = dxb;
+                } else ai[k] = -1;
               }
-              const int a = off + e;
-              const int y = (int)anb[a];
-              const double w = aw[a];
-              const unsigned long long dyb = dist[y];
-              const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dxb), w));
-              if (tb < dyb) {
-                atomicMin(&dist[y], tb);
-                if (state[y] == FAR) state[y] = TENT;
+              int yy[RU];
+              double ww[RU];
+#pragma unroll
+              for (int k = 0; k < RU; k++) if (ai[k] >= 0) { yy[k] = (int)anb[ai[k]]; ww[k] = aw[ai[k]]; }
+#pragma unroll
+              for (int k = 0; k < RU; k++) {
+                if (ai[k] < 0) continue;
+                const int y = yy[k];
+                const double w = ww[k];
+                const unsigned long long dyb = dist[y];
+                const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dx[k]), w));
+                if (tb < dyb) {
+                  atomicMin(&dist[y], tb);
+                  if (state[y] == FAR) state[y] = TENT;
+                }
+                // y a parent of the row's vertex?  (d[y] is final whenever this can hold)
+                if (dyb != INF_BITS &&
+                    (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dx[k])
+                  atomicMin(&sh.qbest[ri[k]], ai[k]);
               }
-              // y a parent of the row's vertex?  (d[y] is final whenever this can hold)
-              if (dyb != INF_BITS &&
-                  (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dxb)
-                atomicMin(&sh.qbest[i], a);
             }
           }
         }
@@ -245,13 +264,13 @@ __global__ void filtration_kernel(Params p, ChunkView c, int cap) {
 
 }  // namespace
 
-void launch_filtration(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st) {
+void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
   // dist (8) + state (1) bytes per vertex in shared memory when the chunk's largest vicinity fits
   int cap = (int)((n_max + 7) / 8 * 8);
   if ((size_t)cap * 9 > 180 * 1024) cap = 0;
   const size_t bytes = (size_t)cap * 9;
   cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  filtration_kernel<<<c.T, block, bytes, st>>>(p, c, cap);
+  filtration_kernel<<<cnt, block, bytes, st>>>(p, c, t0, cap);
   count_launch();
 }
 

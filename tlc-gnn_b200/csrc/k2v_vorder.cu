@@ -27,10 +27,10 @@
 namespace tlc {
 namespace {
 
-__global__ void vorder_kernel(Params p, ChunkView c, int smem_ints) {
+__global__ void vorder_kernel(Params p, ChunkView c, int t0, int smem_ints) {
   extern __shared__ int32_t dyn[];
   __shared__ SortShared sh;
-  const int t = blockIdx.x;
+  const int t = t0 + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int n = c.tn[t];
   if (tid == 0) c.tfb[t] = 0;
@@ -102,11 +102,11 @@ __global__ void vorder_kernel(Params p, ChunkView c, int smem_ints) {
 
 }  // namespace
 
-void launch_vorder(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st) {
+void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
   const int smem_ints = n_max * 4 <= 160 * 1024 ? (int)n_max : 0;
   const size_t bytes = (size_t)smem_ints * 4;
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  vorder_kernel<<<c.T, block, bytes, st>>>(p, c, smem_ints);
+  vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints);
   count_launch();
 }
 

@@ -53,12 +53,12 @@ __device__ __forceinline__ bool rep_less(unsigned long long ka, int la, int ha, 
 }
 
 template <typename PT>
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, ChunkView c, int cap) {
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, ChunkView c, int t0, int tend, int cap) {
   extern __shared__ unsigned char dyn_raw[];
   __shared__ RepBuf reps_all[SWEEP_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int t = blockIdx.x * SWEEP_WARPS + wid;
-  if (t >= c.T) return;
+  const int t = t0 + blockIdx.x * SWEEP_WARPS + wid;
+  if (t >= tend) return;
   const int n = c.tn[t];
   if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
   const int64_t vo = c.voff[t], eo = c.eoff[t], po = c.poff(t);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
 
 }  // namespace
 
-void launch_sweep(const Params& p, const ChunkView& c, int64_t n_max, cudaStream_t st) {
+void launch_sweep(const Params& p, const ChunkView& c, int t0, int cnt, int64_t n_max, cudaStream_t st) {
   // parents in shared memory when SWEEP_WARPS vicinities of the chunk's largest size fit
   const bool narrow = n_max < 65536;
   const size_t esz = narrow ? 2 : 4;
@@ -258,13 +258,13 @@ void launch_sweep(const Params& p, const ChunkView& c, int64_t n_max, cudaStream
   int cap = (int)((n_max + 7) / 8 * 8);
   if ((size_t)cap * esz * SWEEP_WARPS > budget) cap = 0;
   const size_t bytes = (size_t)cap * esz * SWEEP_WARPS;
-  const int grid = (c.T + SWEEP_WARPS - 1) / SWEEP_WARPS;
+  const int grid = (cnt + SWEEP_WARPS - 1) / SWEEP_WARPS;
   if (narrow) {
     cudaFuncSetAttribute((const void*)sweep_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    sweep_kernel<uint16_t><<<grid, SWEEP_WARPS * 32, bytes, st>>>(p, c, cap);
+    sweep_kernel<uint16_t><<<grid, SWEEP_WARPS * 32, bytes, st>>>(p, c, t0, t0 + cnt, cap);
   } else {
     cudaFuncSetAttribute((const void*)sweep_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    sweep_kernel<int32_t><<<grid, SWEEP_WARPS * 32, bytes, st>>>(p, c, cap);
+    sweep_kernel<int32_t><<<grid, SWEEP_WARPS * 32, bytes, st>>>(p, c, t0, t0 + cnt, cap);
   }
   count_launch();
 }

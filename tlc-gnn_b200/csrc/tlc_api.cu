@@ -249,7 +249,13 @@ struct StageTimer {
 };
 
 // run the stage kernels over one carved chunk (offsets already uploaded)
-static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_t n_max, int64_t m_max, double* d_pi,
+// kernels whose shared-memory footprint follows the vicinity size are launched per SUB-RANGE of the chunk's
+// (size-sorted) targets, each with the capacity of its own largest vicinity: smaller vicinities get more
+// resident CTAs per SM
+struct SubRange { int t0, cnt; int64_t n_max; };
+
+static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_t n_max, int64_t m_max,
+                       const std::vector<SubRange>& subs, double* d_pi,
                        float* d_pi32, uint8_t* d_status, bool want_lists, StageTimer& tm) {
   cudaStream_t st = g->stream;
   const int block = block_for(m_max);
@@ -257,7 +263,7 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   tm.mark(1);
   launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
-  launch_filtration(p, c, block, n_max, st);
+  for (const SubRange& r : subs) launch_filtration(p, c, r.t0, r.cnt, block, r.n_max, st);
   // ascending sweep: vertex-ordered kernels 2v + 3v; targets they hand back (tfb) and, when the descending
   // sweep is wanted (diagram output, Pos/Neg lists for the loops), the edge-sorted kernels 2 + 3.  The image
   // only needs PD_up and [min,max]: PD_down and [max,min] have death <= birth, i.e. weight 0.
@@ -268,9 +274,9 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   if (edge_sorted) {
     cudaMemsetAsync(c.tfb, 1, (size_t)c.T, st);
   } else {
-    launch_vorder(p, c, block, n_max, st);
+    launch_vorder(p, c, 0, c.T, block, n_max, st);
     tm.mark(4);
-    launch_sweep(p, c, n_max, st);
+    launch_sweep(p, c, 0, c.T, n_max, st);
   }
   tm.mark(5);
   // the edge-sorted kernels work on the canonical (lo, hi) edge list, derived from the adjacency where needed
@@ -411,7 +417,17 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     CK(cudaMemcpyAsync((void*)c.eoff, h_eoff + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)(c.voff + T), &Nv, 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)(c.eoff + T), &Ne, 8, cudaMemcpyHostToDevice, st));
-    run_stages(g, p, c, n_max, m_max, d_pi, d_pi32, d_status, detail != nullptr, tm);
+    std::vector<SubRange> subs;
+    {
+      const int groups = T >= 4 * 2 * g->sm_count ? 4 : (T >= 2 * 2 * g->sm_count ? 2 : 1);
+      for (int gi = 0; gi < groups; gi++) {
+        const int64_t a = T * gi / groups, b = T * (gi + 1) / groups;
+        int64_t nm = 0;
+        for (int64_t k = a; k < b; k++) nm = std::max<int64_t>(nm, h_n[order[pos + k]]);
+        subs.push_back(SubRange{(int)a, (int)(b - a), nm});
+      }
+    }
+    run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
     g->nchunks++;
     if (detail) {
       // copy every intermediate back (input order == chunk order here)

@@ -145,15 +145,15 @@ void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* t
                            int* work_counter, cudaStream_t st);
 void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                           int* work_counter, cudaStream_t st);
-void launch_filtration(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st);
+void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
 // canonical edge list (elo, ehi, ew) from the adjacency; fb_only: only for targets with tfb[t] != 0
 void launch_edgelist(const Params& p, const ChunkView& c, int block, int fb_only, cudaStream_t st);
 // sweep_mask: bit 0 ascending, bit 1 descending.  fb_only: the ascending sweep only for targets with tfb[t] != 0.
 void launch_sort(const Params& p, const ChunkView& c, int block, int sweep_mask, int fb_only, cudaStream_t st);
 void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_ints, int build_lists, int sweep_mask,
                        int fb_only, cudaStream_t st);
-void launch_vorder(const Params& p, const ChunkView& c, int block, int64_t n_max, cudaStream_t st);
-void launch_sweep(const Params& p, const ChunkView& c, int64_t n_max, cudaStream_t st);
+void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
+void launch_sweep(const Params& p, const ChunkView& c, int t0, int cnt, int64_t n_max, cudaStream_t st);
 void launch_loops(const Params& p, const ChunkView& c, int block, int smem_ints, cudaStream_t st);
 void launch_pimg(const Params& p, const ChunkView& c, double* out_pi, float* out_pi_f32, uint8_t* out_status,
                  int block, cudaStream_t st);
