@@ -172,11 +172,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# algorithmic bytes per target of each stage kernel, from the vicinity's n, m and the
+# SURVEY.md 8d compulsory read volume B_e of the extraction
+def stage_alg_bytes(sum_n, sum_m, be_total, r2, live):
+    adj = 24.0 * sum_m                       # induced adjacency, both directions: (4 B id + 8 B weight) * 2m
+    return {"sizes": be_total - 16.0 * sum_m - 4.0 * r2 * live,      # expansion + induced-scan reads of the CSR
+            "fill": (be_total - 4.0 * r2 * live) + adj + 16.0 * sum_n,  # same reads + kappa of the induced edges + adjacency write
+            "filtration": 2.0 * adj + 40.0 * sum_n,                  # every row read once per root + d1, d2, fval, tree
+            "vorder": 48.0 * sum_n,                                  # sort keys/payload, rank tables, block table
+            "sweep": 12.0 * sum_n,                                   # block table + rank order (+ rows only off the fast path)
+            "image": 4.0 * r2 * live}
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
     from tlc_b200 import _lib as L
-    from tlc_b200 import api
+    from tlc_b200 import api, multi
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,16 +210,20 @@ def run_cuda(args):
     out_pi = torch.zeros((B, r2), dtype=torch.float64, device=dev)
     out_f32 = torch.zeros((B, r2), dtype=torch.float32, device=dev)
     out_st = torch.zeros((B,), dtype=torch.uint8, device=dev)
-    gathered = torch.zeros((world * B, r2), dtype=torch.float32, device=dev) if world > 1 else None
+    sv = multi.ShardedVicinity(csr[0], multi.cuda_local_fn(g, dev, hop=args.hop, flags=flags), dev) if world > 1 else None
 
-    def step(s):
-        tg = torch.from_numpy(batch_targets(ne, perm, s, rank, world, B)).to(dev)  # resident before timing
-        return tg
+    def global_targets(s):  # the step's targets of ALL ranks (weak scaling: world * B per step)
+        return np.concatenate([batch_targets(ne, perm, s, r, world, B) for r in range(world)])
 
-    def run(tg):
-        g.vicinity_pi_dev(tg, out_pi, out_f32, out_st, hop=args.hop, flags=flags)
+    def step(s):  # inputs resident in HBM before the timed region
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out_f32)
+            return sv.prepare(global_targets(s))
+        return torch.from_numpy(batch_targets(ne, perm, s, rank, world, B)).to(dev)
+
+    def run(x):
+        if world > 1:
+            return sv.run(x)   # this rank's shard through the C-ABI, NCCL all-gather of the fp32 rows, un-permute
+        g.vicinity_pi_dev(x, out_pi, out_f32, out_st, hop=args.hop, flags=flags)
 
     def barrier():
         torch.cuda.synchronize()
@@ -222,6 +238,7 @@ def run_cuda(args):
     stage_acc = {}
     alg_bytes = 0.0
     handed_back = 0
+    sum_n = sum_m = live = 0
     launches0 = api.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,7 +251,9 @@ def run_cuda(args):
         for k, v in ms.items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
         alg_bytes += g.last_algorithmic_bytes()
-        handed_back += g.last_counts()["handed_back"]
+        cnts = g.last_counts()
+        handed_back += cnts["handed_back"]
+        sum_n += cnts["sum_n"]; sum_m += cnts["sum_m"]; live += cnts["live"]
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -250,26 +269,37 @@ def run_cuda(args):
     value = world * B * args.steps / elapsed_max
 
     # ---- e2e through the reference-facing API (host in, host out) ----
-    import networkx as nx  # noqa: F401  (the mirror accepts any graph object with nodes()/edges())
     import sg2dgm.riccidist2dgm as mirror
 
     g.set_stream(None)
-    gm = mirror.graph2pi.from_csr(*csr, device=local)
-    e2e_batches = [batch_targets(ne, perm, 500 + s, rank, world, B) for s in range(args.steps + 1)]
-    gm.get_pimg_for_all_edges(e2e_batches[0], cores=16, hop=args.hop, norm=True, extended_flag=bool(args.extended),
-                              resolution=5, descriptor="sum")
-    barrier()
     e2e_stage = {}
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        gm.get_pimg_for_all_edges(e2e_batches[1 + s], cores=16, hop=args.hop, norm=True,
-                                  extended_flag=bool(args.extended), resolution=5, descriptor="sum")
-        for k, v in gm._graph.last_stage_ms()[0].items():
-            e2e_stage[k] = e2e_stage.get(k, 0.0) + v
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(gm.pi_sg.astype(np.float32)).to(dev))
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world == 1:
+        gm = mirror.graph2pi.from_csr(*csr, device=local)
+        e2e_batches = [batch_targets(ne, perm, 500 + s, rank, world, B) for s in range(args.steps + 1)]
+        gm.get_pimg_for_all_edges(e2e_batches[0], cores=16, hop=args.hop, norm=True, extended_flag=bool(args.extended),
+                                  resolution=5, descriptor="sum")
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            gm.get_pimg_for_all_edges(e2e_batches[1 + s], cores=16, hop=args.hop, norm=True,
+                                      extended_flag=bool(args.extended), resolution=5, descriptor="sum")
+            for k, v in gm._graph.last_stage_ms()[0].items():
+                e2e_stage[k] = e2e_stage.get(k, 0.0) + v
+        te_local = time.perf_counter() - t0
+        h2d, d2h = int(B * 8), int(B * (r2 * 8 + 1))
+    else:
+        # host target list in (every rank holds it, as the reference's caller would), full table back on the host
+        e2e_lists = [global_targets(500 + s) for s in range(args.steps + 1)]
+        sv.compute(e2e_lists[0])
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pi_all, st_all = sv.compute(e2e_lists[1 + s])
+            pi_host = pi_all.cpu()
+        torch.cuda.synchronize()
+        te_local = time.perf_counter() - t0
+        h2d, d2h = int(B * 8), int(world * B * r2 * 4)
+    te = torch.tensor([te_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
@@ -286,14 +316,27 @@ def run_cuda(args):
         stages = {k: v for k, v in stage_acc.items() if k != "total"}
         dom = max(stages, key=stages.get) if stages else "n/a"
         dom_ms = stages.get(dom, 0.0)
-        achieved = (alg_bytes / 1e9) / max(dom_ms / 1e3, 1e-12)
+        sab = stage_alg_bytes(float(sum_n), float(sum_m), alg_bytes, r2, float(live))
+        dom_bytes = sab.get(dom, alg_bytes)
+        achieved = (dom_bytes / 1e9) / max(dom_ms / 1e3, 1e-12)
+        traffic = None
+        try:  # DRAM bytes per target of that kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if dom in tj and args.workload == tj[dom].get("workload"):
+                traffic = tj[dom]["dram_bytes_per_target"] * live / max(1, args.steps)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_target": alg_bytes / max(1, B * args.steps),
-                    "note": "achieved = compulsory bytes of the step's targets (SURVEY.md 8d B_e) / device time of the "
-                            "dominant stage kernel; CSR is L2-resident so this is an efficiency index vs the HBM roof",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": dom_bytes / max(1, args.steps),
+                    "kernel_ms_per_step": dom_ms / max(1, args.steps),
+                    "note": "achieved = algorithmic bytes of the dominant stage kernel over the step's targets (DESIGN.md "
+                            "section 4) / its device time (CUDA events on the library's stream); traffic = ncu dram bytes "
+                            "of the same kernel scaled to the step's targets",
                     "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()},
-                    "whole_path_achieved": (alg_bytes / 1e9) / max(elapsed, 1e-12)}
+                    "stage_alg_gbytes_per_step": {k: v / 1e9 / args.steps for k, v in sab.items()},
+                    "whole_path": {"compulsory_bytes_per_target": alg_bytes / max(1, live),
+                                   "achieved_gbs": (alg_bytes / 1e9) / max(elapsed, 1e-12)}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(csr, ne, perm, args, args.cpu_seconds)
@@ -302,8 +345,7 @@ def run_cuda(args):
                 "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(args, world),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 8),
-                        "d2h_bytes_per_step": int(B * (r2 * 8 + 1)),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "stage_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()}},
                 "handed_back_per_step": handed_back / args.steps,
                 "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,

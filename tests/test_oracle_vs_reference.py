@@ -1,0 +1,63 @@
+"""The CPU restatement against the REAL reference imported in place from /root/reference (build container
+only; the tree does not exist on the GPU box -> skipped there).  Fresh random graphs each run seed, i.e.
+inputs that are NOT in the committed fixtures: as-is batch output (images, counts) and the canonical-order
+stage outputs (filtration values, PD0, Pos/Neg, PD1) must agree bit for bit / to 1e-11."""
+import numpy as np
+import pytest
+
+import oracle as orc
+import ref_harness as rh
+from helpers import rel_err
+from tlc_b200 import graphgen as gg
+
+pytestmark = [pytest.mark.reference, pytest.mark.skipif(not rh.available(), reason="reference tree not mounted")]
+
+
+def _case(name, scale, cont, seed, ntargets):
+    c = gg.make_config(name, scale=scale, continuous=cont)
+    rng = np.random.default_rng(seed)
+    e = c["edges"]
+    tg = e[rng.choice(len(e), ntargets, replace=False)]
+    far = rng.integers(0, c["N"], size=(4, 2))
+    return c, np.concatenate([tg, far])
+
+
+@pytest.mark.parametrize("name,scale,hop,cont,ext", [("cora", 0.25, 2, False, True), ("pubmed", 0.04, 2, True, True),
+                                                     ("pubmed", 0.04, 2, False, False), ("computers", 0.02, 1, True, True)])
+def test_batch_matches_reference(name, scale, hop, cont, ext):
+    c, tg = _case(name, scale, cont, 11, 24)
+    pi_ref, cnt_ref, _ = rh.run_batch(c["edges"], c["kappa"], tg, hop, ext)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    lut = {int(l): i for i, l in enumerate(labels)}
+    new_t = np.array([[lut.get(int(a), -1), lut.get(int(b), -1)] for a, b in tg], dtype=np.int32)
+    og = orc.OracleGraph(*gg.build_csr(len(labels), ne, c["kappa"]))
+    r = og.run_batch(new_t, hop=hop, flags=orc.F_NORM | (orc.F_EXTENDED if ext else 0))
+    assert r["cnt_compute"] == cnt_ref
+    assert np.array_equal(pi_ref.any(axis=1), r["pi"].any(axis=1))
+    assert rel_err(r["pi"], pi_ref) < 1e-11
+
+
+def test_stages_match_canonical_reference():
+    c, tg = _case("pubmed", 0.04, True, 5, 10)
+    _, _, pi = rh.run_batch(c["edges"], c["kappa"], tg[:1], 2, True)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    lut = {int(l): i for i, l in enumerate(labels)}
+    og = orc.OracleGraph(*gg.build_csr(len(labels), ne, c["kappa"]))
+    checked = 0
+    for a, b in tg[:10]:
+        if int(a) not in lut or int(b) not in lut:
+            continue
+        st = rh.run_one_stages(pi, int(a), int(b), 2)
+        if st["ncomp"] != 1 or st.get("PD1") is None:
+            continue
+        o = og.run_one(lut[int(a)], lut[int(b)], hop=2, flags=orc.F_NORM | orc.F_EXTENDED)
+        assert list(o["vert"]) == st["nodes"]
+        assert np.array_equal(o["fval"], np.array([st["fval"][x] for x in st["nodes"]]))
+        k = o["pkind"]
+        assert np.array_equal(np.stack([o["pbirth"], o["pdeath"]], 1)[k != orc.K_ONE], np.array(st["PD0"]).reshape(-1, 2))
+        assert np.array_equal(np.stack([o["pbirth"], o["pdeath"]], 1)[k == orc.K_ONE], np.array(st["PD1"]).reshape(-1, 2))
+        vert = o["vert"]
+        assert np.stack([vert[o["elo"]][o["pos"]], vert[o["ehi"]][o["pos"]]], 1).tolist() == [list(e) for e in st["Pos"]]
+        assert np.stack([vert[o["elo"]][o["neg"]], vert[o["ehi"]][o["neg"]]], 1).tolist() == [list(e) for e in st["Neg"]]
+        checked += 1
+    assert checked >= 3

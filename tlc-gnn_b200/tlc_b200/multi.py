@@ -1,0 +1,123 @@
+"""Multi-GPU driver of the path: targets are independent (riccidist2dgm.py:366-368 maps a pure function over
+edges), so the CSR graph is replicated on every GPU, the target list is sharded, and the per-target image
+rows are combined with ONE all-gather of float32[E/G, res^2] (+ uint8 status) over NCCL/NVLink -- there is no
+other exchange on this path.
+
+Sharding: targets are ordered by an a-priori cost estimate (deg(u) + deg(v), from the host CSR) and dealt
+round-robin, so that every rank gets the same mix of heavy and light vicinities; shards are padded to equal
+length for the fixed-size collective and the rows are scattered back to the caller's order afterwards.
+
+The collective runs through torch.distributed (backend nccl on GPUs; gloo in the CPU tests of this logic).
+"""
+import numpy as np
+
+
+def plan_shards(targets, rowptr, world):
+    """-> (order int64[E], shard_len): rank r owns order[r::world] (length <= shard_len = ceil(E / world))."""
+    t = np.asarray(targets).reshape(-1, 2)
+    E = t.shape[0]
+    rp = np.asarray(rowptr, dtype=np.int64)
+    N = rp.size - 1
+    deg = np.diff(rp)
+    ok = (t >= 0).all(axis=1) & (t < N).all(axis=1)
+    tc = np.clip(t, 0, max(N - 1, 0))
+    cost = np.where(ok, deg[tc[:, 0]] + deg[tc[:, 1]], 0)
+    order = np.argsort(-cost, kind="stable").astype(np.int64)
+    return order, (E + world - 1) // world
+
+
+def shard_of(order, rank, world):
+    return order[rank::world]
+
+
+def unshard(gathered, order, world, E):
+    """gathered: [world, shard_len, ...] rows in shard order -> [E, ...] in the caller's target order."""
+    out_shape = (E,) + tuple(gathered.shape[2:])
+    if hasattr(gathered, "new_zeros"):
+        import torch
+        out = gathered.new_zeros(out_shape)
+        for r in range(world):
+            idx = torch.as_tensor(order[r::world], device=gathered.device)
+            out[idx] = gathered[r, : idx.numel()]
+        return out
+    out = np.zeros(out_shape, dtype=gathered.dtype)
+    for r in range(world):
+        idx = order[r::world]
+        out[idx] = gathered[r, : len(idx)]
+    return out
+
+
+class ShardedVicinity:
+    """all ranks call compute() with the SAME target list; every rank gets the full [E, res^2] float32 table.
+
+    local_fn(targets_shard int32[k,2]) -> (pi float32 tensor [k, r2] on `device`, status uint8 tensor [k]);
+    the product passes the CUDA path (tlc_b200.api.VicinityGraph.vicinity_pi_dev), the CPU tests a stand-in."""
+
+    def __init__(self, rowptr, local_fn, device, resolution=5, group=None):
+        import torch.distributed as dist
+        self.rowptr = np.asarray(rowptr)
+        self.local_fn = local_fn
+        self.device = device
+        self.r2 = resolution * resolution
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def prepare(self, targets):
+        """plan the shards of a target list and make this rank's shard resident on the device."""
+        import torch
+        t = np.ascontiguousarray(targets, dtype=np.int32).reshape(-1, 2)
+        order, L = plan_shards(t, self.rowptr, self.world)
+        mine = shard_of(order, self.rank, self.world)
+        shard = torch.from_numpy(np.ascontiguousarray(t[mine])).to(self.device)
+        return dict(E=t.shape[0], order=order, L=L, k=len(mine), shard=shard)
+
+    def run(self, prep):
+        """compute this rank's shard (already resident), all-gather, un-permute."""
+        return self._finish(prep["E"], prep["order"], prep["L"], prep["k"], *self.local_fn(prep["shard"]))
+
+    def compute(self, targets):
+        t = np.ascontiguousarray(targets, dtype=np.int32).reshape(-1, 2)
+        order, L = plan_shards(t, self.rowptr, self.world)
+        mine = shard_of(order, self.rank, self.world)
+        pi_loc, st_loc = self.local_fn(t[mine])
+        return self._finish(t.shape[0], order, L, len(mine), pi_loc, st_loc)
+
+    def _finish(self, E, order, L, k, pi_loc, st_loc):
+        import torch
+        import torch.distributed as dist
+        mine = range(k)
+        pi_pad = torch.zeros((L, self.r2), dtype=torch.float32, device=self.device)
+        st_pad = torch.zeros((L,), dtype=torch.uint8, device=self.device)
+        pi_pad[: len(mine)] = pi_loc
+        st_pad[: len(mine)] = st_loc
+        if self.world == 1:
+            return unshard(pi_pad[None], order, 1, E), unshard(st_pad[None], order, 1, E)
+        g_pi = torch.empty((self.world * L, self.r2), dtype=torch.float32, device=self.device)
+        g_st = torch.empty((self.world * L,), dtype=torch.uint8, device=self.device)
+        if dist.get_backend(self.group) == "gloo":  # (gloo has no all_gather_into_tensor)
+            dist.all_gather(list(g_pi.view(self.world, L, self.r2).unbind(0)), pi_pad, group=self.group)
+            dist.all_gather(list(g_st.view(self.world, L).unbind(0)), st_pad, group=self.group)
+        else:
+            dist.all_gather_into_tensor(g_pi, pi_pad, group=self.group)
+            dist.all_gather_into_tensor(g_st, st_pad, group=self.group)
+        return (unshard(g_pi.view(self.world, L, self.r2), order, self.world, E),
+                unshard(g_st.view(self.world, L), order, self.world, E))
+
+
+def cuda_local_fn(graph, device, hop=2, descriptor="sum", resolution=5, flags=1, mode=0):
+    """the product's per-rank compute: one C-ABI call on this rank's shard, rows stay in HBM."""
+    import torch
+
+    def fn(tshard):
+        k = tshard.shape[0]
+        r2 = resolution * resolution
+        tg = tshard if torch.is_tensor(tshard) else torch.from_numpy(np.ascontiguousarray(tshard)).to(device)
+        pi64 = torch.empty((max(k, 1), r2), dtype=torch.float64, device=device)
+        pi32 = torch.empty((max(k, 1), r2), dtype=torch.float32, device=device)
+        st = torch.empty((max(k, 1),), dtype=torch.uint8, device=device)
+        if k:
+            graph.vicinity_pi_dev(tg, pi64, pi32, st, hop=hop, mode=mode, descriptor=descriptor,
+                                  resolution=resolution, flags=flags)
+        return pi32[:k], st[:k]
+    return fn
