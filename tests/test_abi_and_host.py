@@ -1,0 +1,75 @@
+"""CPU-side checks: the C-ABI library loads without a GPU and exports every symbol include/tlc_b200.h declares
+(no compute calls), constants of the Python binding equal the header's, argument errors are reported through the
+rc / tlc_last_error convention, and the host-side mirror logic (label mapping, CSR ingestion) behaves like the
+reference's graph2pi.__init__ (riccidist2dgm.py:216-226)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tlc_b200 import _lib as L
+from tlc_b200 import graphgen as gg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "tlc_b200.h")).read()
+
+
+def _declared_functions():
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(tlc_[a-z_0-9]+)\s*\(", HEADER, flags=re.M)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(L.SO_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = C.CDLL(L.SO_PATH)
+    decl = _declared_functions()
+    assert len(decl) >= 15
+    for name in decl:
+        assert hasattr(lib, name), name
+    assert sorted(decl) == sorted(L.EXPORTS)          # the binding lists exactly the header's entry points
+
+
+def test_binding_constants_match_header():
+    macros = dict(re.findall(r"#define\s+(TLC_[A-Z_0-9]+)\s+\(?(-?\d+)u?\)?", HEADER))
+    for k, v in [("TLC_F_NORM", L.F_NORM), ("TLC_F_EXTENDED", L.F_EXTENDED), ("TLC_F_KEEP_ZERO", L.F_KEEP_ZERO),
+                 ("TLC_F_NORM_EPS", L.F_NORM_EPS), ("TLC_F_SUM_PLAIN", L.F_SUM_PLAIN), ("TLC_F_EDGE_SORTED", L.F_EDGE_SORTED),
+                 ("TLC_MODE_EDGE", L.MODE_EDGE), ("TLC_MODE_NODE", L.MODE_NODE), ("TLC_K_UP", L.K_UP), ("TLC_K_ONE", L.K_ONE),
+                 ("TLC_ST_OK", L.ST_OK), ("TLC_ST_NO_TREE_EDGES", L.ST_NO_TREE_EDGES), ("TLC_DESC_SUM", L.DESC["sum"])]:
+        assert int(macros[k]) == v, k
+    assert C.sizeof(L.Params) == 24
+
+
+def test_call_level_errors_without_gpu():
+    lib = L.lib()
+    h = C.c_void_p()
+    rp = np.array([0, 1, 2], np.int32); col = np.array([1, 0], np.int32); kap = np.zeros(2)
+    # bad arguments are rejected before any CUDA call
+    assert lib.tlc_graph_create(0, 2, rp.ctypes.data, col.ctypes.data, kap.ctypes.data, 0, 0, C.byref(h)) == -1
+    assert b"bad graph" in lib.tlc_last_error()
+    bad = np.array([1, 1, 2], np.int32)
+    assert lib.tlc_graph_create(2, 2, bad.ctypes.data, col.ctypes.data, kap.ctypes.data, 0, 0, C.byref(h)) == -1
+    out = np.zeros(25)
+    assert lib.tlc_pimg_transform(0, None, 3, 5, out.ctypes.data) == -1
+    assert lib.tlc_pimg_transform(0, out.ctypes.data, 1, 99, out.ctypes.data) == -1
+    import torch
+    if not torch.cuda.is_available():   # no device: a well-formed call reports TLC_E_NODEVICE instead of crashing
+        assert lib.tlc_graph_create(2, 2, rp.ctypes.data, col.ctypes.data, kap.ctypes.data, 0, 0, C.byref(h)) == -4
+
+
+def test_csr_ingestion_matches_reference_numbering():
+    e = np.array([[7, 3], [3, 9], [9, 7], [2, 7]])
+    labels, ne = gg.relabel_first_appearance(e)
+    assert labels.tolist() == [7, 3, 9, 2]                      # first-appearance order, loaddatas.py:88-92
+    assert ne.tolist() == [[0, 1], [1, 2], [2, 0], [3, 0]]
+    rowptr, col, kap = gg.build_csr(4, ne, np.array([0.5, -0.25, 0.0, 0.125]))
+    assert rowptr.tolist() == [0, 3, 5, 7, 8] and col.tolist() == [1, 2, 3, 0, 2, 0, 1, 0]
+    assert kap.tolist() == [0.5, 0.0, 0.125, 0.5, -0.25, 0.0, -0.25, 0.125]   # kappa stored both directions :222-226
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "SO_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        L.lib()
