@@ -70,7 +70,7 @@ __device__ inline unsigned long long block_reduce_min_u64(unsigned long long v, 
   return t;
 }
 
-__global__ void filtration_kernel(Params p, ChunkView c, int t0, int cap) {
+__global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap) {
   extern __shared__ unsigned long long dyn64[];
   __shared__ FiltShared sh;
   const int t = t0 + blockIdx.x;
@@ -270,6 +270,9 @@ void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int
   if ((size_t)cap * 9 > 180 * 1024) cap = 0;
   const size_t bytes = (size_t)cap * 9;
   cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
+  if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
   filtration_kernel<<<cnt, block, bytes, st>>>(p, c, t0, cap);
   count_launch();
 }

@@ -27,7 +27,7 @@
 namespace tlc {
 namespace {
 
-__global__ void vorder_kernel(Params p, ChunkView c, int t0, int smem_ints) {
+__global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, int t0, int smem_ints) {
   extern __shared__ int32_t dyn[];
   __shared__ SortShared sh;
   const int t = t0 + blockIdx.x;
@@ -106,6 +106,7 @@ void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int blo
   const int smem_ints = n_max * 4 <= 160 * 1024 ? (int)n_max : 0;
   const size_t bytes = (size_t)smem_ints * 4;
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints);
   count_launch();
 }

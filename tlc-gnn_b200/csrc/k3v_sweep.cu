@@ -261,6 +261,7 @@ void launch_sweep(const Params& p, const ChunkView& c, int t0, int cnt, int64_t 
   const int grid = (cnt + SWEEP_WARPS - 1) / SWEEP_WARPS;
   if (narrow) {
     cudaFuncSetAttribute((const void*)sweep_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncSetAttribute((const void*)sweep_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     sweep_kernel<uint16_t><<<grid, SWEEP_WARPS * 32, bytes, st>>>(p, c, t0, t0 + cnt, cap);
   } else {
     cudaFuncSetAttribute((const void*)sweep_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
