@@ -11,6 +11,8 @@
 //
 // Two entry points share the traversal: a counting pass (n, m per target -> the host sizes the chunk
 // arena) and the fill pass (vertex list, induced edges with weight kappa+1, local root ids).
+#include <algorithm>
+
 #include "tlc_common.cuh"
 
 namespace tlc {
@@ -93,8 +95,24 @@ __device__ void ball(const GraphView& g, int32_t root, int hop, uint32_t* bm, in
 
 // ball(u) & ball(v) -> iw (in bm_u) ; word-prefix popcounts -> wbase (in bm_v) ; returns n
 __device__ int build_vicinity(const GraphView& g, const Params& p, int32_t u, int32_t v, int W, uint32_t* bm_u,
-                              uint32_t* bm_v, int32_t* q0, int32_t* q1, K1Shared& sh) {
+                              uint32_t* bm_v, int32_t* q0, int32_t* q1, K1Shared& sh, const VicinityScratch& vs) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (vs.ball_cache) {  // both balls are cached rows: nodes = set(nodes_u) & set(nodes_v)   :315
+    const uint32_t* __restrict__ bu = vs.ball_cache + (size_t)u * W;
+    const uint32_t* __restrict__ bv = vs.ball_cache + (size_t)v * W;
+    const bool edge = p.mode == TLC_MODE_EDGE;
+    for (int w = tid; w < W; w += nt) {
+      const uint32_t x = edge ? (bu[w] & bv[w]) : bu[w];
+      bm_u[w] = x;
+      bm_v[w] = __popc(x);
+    }
+    if (tid == 0) {
+      sh.dacc = vs.ball_acc[2 * (size_t)u] + (edge ? vs.ball_acc[2 * (size_t)v] : 0ull);
+      sh.xacc = vs.ball_acc[2 * (size_t)u + 1] + (edge ? vs.ball_acc[2 * (size_t)v + 1] : 0ull);
+    }
+    __syncthreads();
+    return block_exclusive_scan(reinterpret_cast<int32_t*>(bm_v), W, sh.scan);
+  }
   for (int w = tid; w < 2 * W; w += nt) bm_u[w] = 0;  // bm_v follows bm_u
   __syncthreads();
   ball(g, u, p.hop, bm_u, q0, q1, sh);
@@ -114,6 +132,44 @@ __device__ int build_vicinity(const GraphView& g, const Params& p, int32_t u, in
 
 __device__ __forceinline__ int32_t local_id(const uint32_t* iw, const uint32_t* wbase, int32_t y) {
   return (int32_t)wbase[y >> 5] + __popc(iw[y >> 5] & ((1u << (y & 31)) - 1u));
+}
+
+// ---- ball cache ----
+__global__ void ball_mark_kernel(const int32_t* __restrict__ targets, int64_t E, int node_mode, GraphView g,
+                                 VicinityScratch vs) {
+  const int64_t total = 2 * E;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (node_mode && (i & 1)) continue;
+    const int32_t x = targets[i];
+    if (x < 0 || x >= g.N || g.rowptr[x + 1] == g.rowptr[x]) continue;
+    if (vs.ball_state[x] == 0 && atomicCAS(&vs.ball_state[x], 0, 1) == 0) vs.ball_list[atomicAdd(vs.ball_count, 1)] = x;
+  }
+}
+
+__global__ void __launch_bounds__(K1_BLOCK)
+ball_build_kernel(GraphView g, Params p, VicinityScratch vs, int W, int bm_in_smem) {
+  extern __shared__ uint32_t dyn_smem[];
+  __shared__ K1Shared sh;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  uint32_t* bm = bm_in_smem ? dyn_smem : vs.bitmaps + (size_t)blockIdx.x * 2 * W;
+  int32_t* q0 = vs.queue ? vs.queue + (size_t)blockIdx.x * 2 * g.N : nullptr;
+  int32_t* q1 = q0 ? q0 + g.N : nullptr;
+  const int cnt = *vs.ball_count;
+  for (int idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
+    const int32_t root = vs.ball_list[idx];
+    __syncthreads();
+    for (int w = tid; w < W; w += nt) bm[w] = 0;
+    if (tid == 0) { sh.dacc = 0; sh.xacc = 0; }
+    __syncthreads();
+    ball(g, root, p.hop, bm, q0, q1, sh);
+    uint32_t* row = vs.ball_cache + (size_t)root * W;
+    for (int w = tid; w < W; w += nt) row[w] = bm[w];
+    if (tid == 0) {
+      vs.ball_acc[2 * (size_t)root] = sh.dacc;
+      vs.ball_acc[2 * (size_t)root + 1] = sh.xacc;
+      vs.ball_state[root] = 2;
+    }
+  }
 }
 
 template <bool FILL>
@@ -151,7 +207,7 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
     }
     if (tid == 0) { sh.dacc = 0; sh.xacc = 0; }
     __syncthreads();
-    const int n = build_vicinity(g, p, u, v, W, bm_u, bm_v, q0, q1, sh);
+    const int n = build_vicinity(g, p, u, v, W, bm_u, bm_v, q0, q1, sh, vs);
     const uint32_t* iw = bm_u;
     const uint32_t* wbase = bm_v;
 
@@ -316,6 +372,21 @@ int vicinity_grid(int device, const GraphView& g, const Params& p, size_t* bitma
 
 static void set_smem(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+void launch_ball_cache(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
+                       cudaStream_t st) {
+  if (!vs.ball_cache || E <= 0) return;
+  const int W = (g.N + 31) / 32;
+  const bool smem = vs.bitmaps == nullptr;
+  const size_t bytes = smem ? (size_t)2 * W * 4 : 0;
+  cudaMemsetAsync(vs.ball_count, 0, sizeof(int), st);
+  const int mgrid = (int)std::min<int64_t>((2 * E + 255) / 256, 4096);
+  ball_mark_kernel<<<mgrid, 256, 0, st>>>(targets, E, p.mode == TLC_MODE_NODE ? 1 : 0, g, vs);
+  count_launch();
+  set_smem((const void*)ball_build_kernel, bytes);
+  ball_build_kernel<<<vs.grid, K1_BLOCK, bytes, st>>>(g, p, vs, W, smem ? 1 : 0);
+  count_launch();
 }
 
 void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,

@@ -57,6 +57,10 @@ struct tlc_graph {
   // vicinity scratch (depends on hop)
   uint32_t* bitmaps = nullptr;
   int32_t* queue = nullptr;
+  // ball cache (valid for vic_hop)
+  uint32_t* ball_cache = nullptr;
+  unsigned long long* ball_acc = nullptr;
+  int32_t *ball_state = nullptr, *ball_list = nullptr;
   int vic_grid = 0, vic_hop = -1;
   int* work_counter = nullptr;
   // per-call device buffers
@@ -148,10 +152,35 @@ static int ensure_arena(tlc_graph* g, size_t need_min) {
   return TLC_OK;
 }
 
+static VicinityScratch make_vs(const tlc_graph* g) {
+  return VicinityScratch{g->bitmaps, g->queue, g->vic_grid, g->ball_cache, g->ball_acc, g->ball_state, g->ball_list,
+                         g->work_counter + 2};
+}
+
 static int ensure_vicinity_scratch(tlc_graph* g, const Params& p) {
   if (g->vic_hop == p.hop && g->vic_grid > 0) return TLC_OK;
   if (g->bitmaps) { cudaFree(g->bitmaps); g->bitmaps = nullptr; }
   if (g->queue) { cudaFree(g->queue); g->queue = nullptr; }
+  if (g->ball_cache) { cudaFree(g->ball_cache); g->ball_cache = nullptr; }
+  if (g->ball_acc) { cudaFree(g->ball_acc); g->ball_acc = nullptr; }
+  if (g->ball_state) { cudaFree(g->ball_state); g->ball_state = nullptr; }
+  if (g->ball_list) { cudaFree(g->ball_list); g->ball_list = nullptr; }
+  {
+    // one bitmap row per node, if that is affordable (TLC_BALL_CACHE_GB, default 16; 0 disables)
+    const char* env = getenv("TLC_BALL_CACHE_GB");
+    const double gb = env ? atof(env) : 16.0;
+    const size_t Wc = ((size_t)g->gv.N + 31) / 32;
+    const size_t need = (size_t)g->gv.N * Wc * sizeof(uint32_t);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (gb > 0 && (double)need <= gb * (double)(1ull << 30) && need <= free_b / 4) {
+      CK(cudaMalloc((void**)&g->ball_cache, std::max<size_t>(need, 16)));
+      CK(cudaMalloc((void**)&g->ball_acc, (size_t)g->gv.N * 2 * sizeof(unsigned long long)));
+      CK(cudaMalloc((void**)&g->ball_state, (size_t)g->gv.N * sizeof(int32_t)));
+      CK(cudaMalloc((void**)&g->ball_list, (size_t)g->gv.N * sizeof(int32_t)));
+      CK(cudaMemset(g->ball_state, 0, (size_t)g->gv.N * sizeof(int32_t)));
+    }
+  }
   size_t W = 0;
   bool smem = false;
   g->vic_grid = vicinity_grid(g->device, g->gv, p, &W, &smem);
@@ -259,7 +288,7 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
                        float* d_pi32, uint8_t* d_status, bool want_lists, StageTimer& tm) {
   cudaStream_t st = g->stream;
   const int block = block_for(m_max);
-  VicinityScratch vs{g->bitmaps, g->queue, g->vic_grid};
+  VicinityScratch vs = make_vs(g);
   tm.mark(1);
   launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
@@ -333,8 +362,9 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   if (g->timing) { cudaEventCreate(&ev_total0); cudaEventCreate(&ev_total1); cudaEventRecord(ev_total0, st); }
 
   // ---- kernel 1, counting pass ----
-  VicinityScratch vs{g->bitmaps, g->queue, g->vic_grid};
+  VicinityScratch vs = make_vs(g);
   tm.mark(0);
+  launch_ball_cache(g->gv, p, d_targets, E, vs, st);
   launch_vicinity_sizes(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_st, g->d_bytes, vs, g->work_counter, st);
   tm.mark(-1);
   const size_t pin_need = align_up((size_t)E * 8) + (size_t)E * 9 + ALIGN;
@@ -537,6 +567,7 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaSetDevice(g->device);
   cudaFree((void*)g->gv.rowptr); cudaFree((void*)g->gv.col); cudaFree((void*)g->gv.kappa);
   cudaFree(g->arena); cudaFree(g->bitmaps); cudaFree(g->queue); cudaFree(g->work_counter);
+  cudaFree(g->ball_cache); cudaFree(g->ball_acc); cudaFree(g->ball_state); cudaFree(g->ball_list);
   cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_st); cudaFree(g->d_bytes);
   cudaFree(g->io_t); cudaFree(g->io_pi); cudaFree(g->io_st);
   if (g->h_pin) cudaFreeHost(g->h_pin);
@@ -593,7 +624,8 @@ int tlc_vicinity_sizes(tlc_graph* g, const int32_t* targets, int64_t E, const tl
   int32_t* d_t = nullptr;
   CK(cudaMalloc((void**)&d_t, (size_t)E * 8));
   CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
-  VicinityScratch vs{g->bitmaps, g->queue, g->vic_grid};
+  VicinityScratch vs = make_vs(g);
+  launch_ball_cache(g->gv, p, d_t, E, vs, g->stream);
   launch_vicinity_sizes(g->gv, p, d_t, E, g->d_n, g->d_m, g->d_st, g->d_bytes, vs, g->work_counter, g->stream);
   if (out_n) CK(cudaMemcpyAsync(out_n, g->d_n, (size_t)E * 4, cudaMemcpyDeviceToHost, g->stream));
   if (out_m) CK(cudaMemcpyAsync(out_m, g->d_m, (size_t)E * 4, cudaMemcpyDeviceToHost, g->stream));

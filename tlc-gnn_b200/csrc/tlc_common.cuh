@@ -138,6 +138,13 @@ struct VicinityScratch {
   uint32_t* bitmaps;  // global fallback: [grid][2*W] words when the bitmaps do not fit shared memory
   int32_t* queue;     // [grid][2*N] frontier queues, only for hop > 2
   int grid;
+  // ball cache (per graph and hop): the closed k-hop ball of a node is shared by every target incident to it, so
+  // it is expanded once and kept as a bitmap row; a vicinity is then the AND of two rows.  nullptr: expand per target.
+  uint32_t* ball_cache;            // [N][W]
+  unsigned long long* ball_acc;    // [N][2]: expanded degree sum, rowptr pairs read (algorithmic-byte accounting)
+  int32_t* ball_state;             // [N]: 0 not cached, 1 claimed for this call, 2 cached
+  int32_t* ball_list;              // [N] nodes to expand in this call
+  int* ball_count;
 };
 
 void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
@@ -162,5 +169,8 @@ void launch_pimg_single(const double* dgm, int64_t K, int res, double* out, cuda
 int64_t launch_count();
 void count_launch();
 int vicinity_grid(int device, const GraphView& g, const Params& p, size_t* bitmap_words, bool* use_smem);
+// expand (once) the balls of the targets' endpoints that are not cached yet
+void launch_ball_cache(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
+                       cudaStream_t st);
 
 }  // namespace tlc
