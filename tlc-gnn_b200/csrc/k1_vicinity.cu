@@ -26,8 +26,10 @@ struct K1Shared {
   int32_t red[32];
   int32_t qcnt[2];
   int32_t target;
-  int32_t next;   // fill: next vicinity vertex to hand to a warp
+  int32_t next;   // next bitmap word (a batch of <= 32 vicinity vertices) to hand to a warp
   int32_t ecur;   // fill: adjacency entries reserved so far
+  int32_t bcnt[K1_BLOCK / 32][32];  // fill, per warp: kept entries / running write cursor of the batch's 32 rows
+  int32_t bmin[K1_BLOCK / 32][32];  // fill, per warp: smallest kept weight of each row (float bits, rounded down)
   unsigned long long dacc;  // algorithmic-byte accounting: sum of expanded degrees (D_u + D_v + D_S)
   unsigned long long xacc;  // ... and number of rowptr pairs read (X)
 };
@@ -134,6 +136,19 @@ __device__ __forceinline__ int32_t local_id(const uint32_t* iw, const uint32_t* 
   return (int32_t)wbase[y >> 5] + __popc(iw[y >> 5] & ((1u << (y & 31)) - 1u));
 }
 
+// A batch = the vicinity vertices of one bitmap word: lane k holds the CSR row (start ra, degree dg) of vertex
+// 32*w + k (dg = 0 if the bit is clear).  The rows are walked as ONE concatenated sequence, 32 consecutive entries
+// per step, so every load of a step is independent of the previous step; `inc` is the inclusive degree prefix.
+__device__ __forceinline__ int batch_row_of(int inc, int e) {  // smallest lane r with inc[r] > e   (warp-wide)
+  int r = 0;
+#pragma unroll
+  for (int s = 16; s; s >>= 1) {
+    const int v = __shfl_sync(0xffffffffu, inc, (r + s - 1) & 31);
+    if (v <= e) r += s;
+  }
+  return r;
+}
+
 // ---- ball cache ----
 __global__ void ball_mark_kernel(const int32_t* __restrict__ targets, int64_t E, int node_mode, GraphView g,
                                  VicinityScratch vs) {
@@ -212,26 +227,42 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
     const uint32_t* wbase = bm_v;
 
     if (!FILL) {
-      // counting pass: per vicinity vertex, induced neighbours with a larger id
+      // counting pass: every induced edge is seen from both ends -> m = (sum over vicinity rows of kept entries) / 2
+      if (tid == 0) sh.next = 0;
+      __syncthreads();
       int msum = 0;
-      for (int w = wid; w < W; w += nw) {
-        uint32_t bits = iw[w];
-        while (bits) {
-          const int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const int32_t x = w * 32 + b;
-          const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
-          int cnt = 0;
-          for (int32_t e = ra + lane; e < rb; e += 32) {
-            const int32_t y = g.col[e];
-            cnt += (y > x && test_bit(iw, y)) ? 1 : 0;
+      for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&sh.next, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= W) break;
+        const uint32_t bits = iw[w];
+        if (!bits) continue;
+        const bool has = (bits >> lane) & 1u;
+        const int32_t x = w * 32 + lane;
+        const int32_t ra = has ? g.rowptr[x] : 0;
+        const int dg = has ? g.rowptr[x + 1] - ra : 0;
+        int inc = dg;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) atomicAdd(&sh.dacc, (unsigned long long)total);
+        constexpr int CU = 4;
+        for (int e0 = 0; e0 < total; e0 += 32 * CU) {
+          int32_t yy[CU];
+#pragma unroll
+          for (int k = 0; k < CU; k++) {
+            const int ek = e0 + 32 * k + lane;
+            const bool act = ek < total;
+            const int e = act ? ek : total - 1;
+            const int rr = batch_row_of(inc, e);
+            const int a = __shfl_sync(0xffffffffu, ra, rr) + e - (__shfl_sync(0xffffffffu, inc, rr) - __shfl_sync(0xffffffffu, dg, rr));
+            yy[k] = (act && e0 + 32 * k < total) ? g.col[a] : -1;
           }
-          for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-          if (lane == 0) atomicAdd(&sh.dacc, (unsigned long long)(rb - ra));
-          msum += (lane == 0) ? cnt : 0;
+#pragma unroll
+          for (int k = 0; k < CU; k++) msum += (yy[k] >= 0 && test_bit(iw, yy[k])) ? 1 : 0;
         }
       }
-      const int m = block_reduce_sum(msum, sh.red);
+      const int m = block_reduce_sum(msum, sh.red) / 2;
       if (tid == 0) {
         out_n[t] = n;
         out_m[t] = m;
@@ -261,80 +292,101 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
     }
     if (tid == 0) { sh.next = 0; sh.ecur = 0; }
     __syncthreads();
-    // a warp takes the next vertex, reserves its row in the target's adjacency segment (rows land in
-    // hand-out order; astart/adeg address them) and writes local neighbour ids + weights kappa+1
-    constexpr int RCH = 4;  // rows up to 32*RCH entries are scanned once (kept in registers between count and write)
+    // a warp takes the next bitmap word (batch of <= 32 vertices), counts the kept entries of its rows (walk 1),
+    // reserves the batch's rows in the target's adjacency segment with one atomic, and writes local neighbour
+    // ids + weights kappa+1 in row order (walk 2; the col entries of walk 1 are still in L1)
+    int32_t* bcnt = sh.bcnt[wid];
+    int32_t* bmin = sh.bmin[wid];
     for (;;) {
-      int lx = 0;
-      if (lane == 0) lx = atomicAdd(&sh.next, 1);
-      lx = __shfl_sync(0xffffffffu, lx, 0);
-      if (lx >= n) break;
-      const int32_t x = c.vert[vo + lx];
-      const int32_t ra = g.rowptr[x], rb = g.rowptr[x + 1];
-      if (rb - ra <= 32 * RCH) {
-        int32_t y[RCH];
-        unsigned bal[RCH];
-        int cnt = 0;
+      int w = 0;
+      if (lane == 0) w = atomicAdd(&sh.next, 1);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= W) break;
+      const uint32_t bits = iw[w];
+      if (!bits) continue;
+      const bool has = (bits >> lane) & 1u;
+      const int32_t x = w * 32 + lane;
+      const int lx = (int)wbase[w] + __popc(bits & lanemask_lt());
+      const int32_t ra = has ? g.rowptr[x] : 0;
+      const int dg = has ? g.rowptr[x + 1] - ra : 0;
+      int inc = dg;
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      const int total = __shfl_sync(0xffffffffu, inc, 31);
+      bcnt[lane] = 0;
+      bmin[lane] = 0x7f7fffff;  // FLT_MAX
+      __syncwarp();
+      constexpr int CU = 4;
+      // ---- walk 1: kept entries per row ----
+      for (int e0 = 0; e0 < total; e0 += 32 * CU) {
+        int32_t yy[CU];
+        int rw[CU];
 #pragma unroll
-        for (int k = 0; k < RCH; k++) {
-          const int32_t e = ra + 32 * k + lane;
-          y[k] = e < rb ? g.col[e] : -1;
+        for (int k = 0; k < CU; k++) {
+          const int ek = e0 + 32 * k + lane;
+          const bool act = ek < total;
+          const int e = act ? ek : total - 1;
+          const int rr = batch_row_of(inc, e);
+          const int a = __shfl_sync(0xffffffffu, ra, rr) + e - (__shfl_sync(0xffffffffu, inc, rr) - __shfl_sync(0xffffffffu, dg, rr));
+          rw[k] = rr;
+          yy[k] = act ? g.col[a] : -1;
         }
 #pragma unroll
-        for (int k = 0; k < RCH; k++) {
-          bal[k] = __ballot_sync(0xffffffffu, y[k] >= 0 && test_bit(iw, y[k]));
-          cnt += __popc(bal[k]);
-        }
-        int start = 0;
-        if (lane == 0) start = atomicAdd(&sh.ecur, cnt);
-        start = __shfl_sync(0xffffffffu, start, 0);
-        if (lane == 0) { c.astart[vo + lx] = start; c.adeg[vo + lx] = cnt; }
-        int64_t out = ao + start;
-        double wmin = 1e300;
-#pragma unroll
-        for (int k = 0; k < RCH; k++) {
-          if ((bal[k] >> lane) & 1u) {
-            const int64_t o = out + __popc(bal[k] & lanemask_lt());
-            const double w = g.kappa[ra + 32 * k + lane] + 1.0;  // graph[a][b]['weight'] = kappa + 1   riccidist2dgm.py:225
-            c.anb[o] = (uint32_t)local_id(iw, wbase, y[k]);
-            c.aw[o] = w;
-            wmin = fmin(wmin, w);
-          }
-          out += __popc(bal[k]);
-        }
-        for (int o = 16; o; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
-        if (lane == 0) c.aminw[vo + lx] = __double2float_rd(wmin);  // smallest incident weight, rounded down
-      } else {
-        int cnt = 0;
-        for (int32_t e0 = ra; e0 < rb; e0 += 32) {
-          const int32_t e = e0 + lane;
-          const bool keep = e < rb && test_bit(iw, g.col[e]);
-          cnt += __popc(__ballot_sync(0xffffffffu, keep));
-        }
-        int start = 0;
-        if (lane == 0) start = atomicAdd(&sh.ecur, cnt);
-        start = __shfl_sync(0xffffffffu, start, 0);
-        if (lane == 0) { c.astart[vo + lx] = start; c.adeg[vo + lx] = cnt; }
-        int64_t out = ao + start;
-        double wmin = 1e300;
-        for (int32_t e0 = ra; e0 < rb; e0 += 32) {
-          const int32_t e = e0 + lane;
-          int32_t yy = -1;
-          bool keep = false;
-          if (e < rb) { yy = g.col[e]; keep = test_bit(iw, yy); }
-          const unsigned bl = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            const int64_t o = out + __popc(bl & lanemask_lt());
-            const double w = g.kappa[e] + 1.0;
-            c.anb[o] = (uint32_t)local_id(iw, wbase, yy);
-            c.aw[o] = w;
-            wmin = fmin(wmin, w);
-          }
-          out += __popc(bl);
-        }
-        for (int o = 16; o; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
-        if (lane == 0) c.aminw[vo + lx] = __double2float_rd(wmin);
+        for (int k = 0; k < CU; k++) if (yy[k] >= 0 && test_bit(iw, yy[k])) atomicAdd(&bcnt[rw[k]], 1);
       }
+      __syncwarp();
+      const int cntl = bcnt[lane];
+      int cinc = cntl;
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, cinc, o); if (lane >= o) cinc += v; }
+      int start = 0;
+      if (lane == 31) start = atomicAdd(&sh.ecur, cinc);
+      start = __shfl_sync(0xffffffffu, start, 31);
+      const int rbase = start + cinc - cntl;
+      if (has) { c.astart[vo + lx] = rbase; c.adeg[vo + lx] = cntl; }
+      __syncwarp();
+      bcnt[lane] = rbase;  // from here on: the running write cursor of every row
+      __syncwarp();
+      // ---- walk 2: write, rows stay ascending (steps in order, lanes of a step ranked inside their row) ----
+      for (int e0 = 0; e0 < total; e0 += 32 * CU) {
+        int32_t yy[CU];
+        int rw[CU], aa[CU];
+#pragma unroll
+        for (int k = 0; k < CU; k++) {
+          const int ek = e0 + 32 * k + lane;
+          const bool act = ek < total;
+          const int e = act ? ek : total - 1;
+          const int rr = batch_row_of(inc, e);
+          aa[k] = __shfl_sync(0xffffffffu, ra, rr) + e - (__shfl_sync(0xffffffffu, inc, rr) - __shfl_sync(0xffffffffu, dg, rr));
+          rw[k] = act ? rr : 32 + lane;  // idle lanes: a row of their own
+          yy[k] = act ? g.col[aa[k]] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < CU; k++) {
+          if (e0 + 32 * k >= total) break;  // uniform
+          const bool keep = yy[k] >= 0 && test_bit(iw, yy[k]);
+          const unsigned km = __ballot_sync(0xffffffffu, keep);
+          // lanes of one row are contiguous: segment = [first lane of my row, first lane of the next row)
+          const int up = __shfl_up_sync(0xffffffffu, rw[k], 1);
+          const unsigned chg = __ballot_sync(0xffffffffu, lane == 0 || up != rw[k]);
+          const int s0 = 31 - __clz(chg & (lanemask_lt() | (1u << lane)));
+          const unsigned above = chg & ~((2u << lane) - 1u);  // segment starts above my lane
+          const int s1 = above ? __ffs(above) - 1 : 32;
+          const unsigned seg = (s1 == 32 ? 0xffffffffu : ((1u << s1) - 1u)) & ~((1u << s0) - 1u);
+          const int cur = rw[k] < 32 ? bcnt[rw[k]] : 0;
+          __syncwarp();
+          if (keep) {
+            const int64_t o = ao + cur + __popc(km & seg & lanemask_lt());
+            const double wgt = g.kappa[aa[k]] + 1.0;  // graph[a][b]['weight'] = kappa + 1   riccidist2dgm.py:225
+            c.anb[o] = (uint32_t)local_id(iw, wbase, yy[k]);
+            c.aw[o] = wgt;
+            atomicMin(&bmin[rw[k]], __float_as_int(__double2float_rd(wgt)));  // positive floats order like ints
+          }
+          if (lane == s1 - 1 && rw[k] < 32) bcnt[rw[k]] = cur + __popc(km & seg);
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+      if (has) c.aminw[vo + lx] = __int_as_float(bmin[lane]);  // smallest incident weight, rounded down
+      __syncwarp();
     }
     __syncthreads();
     const int m = sh.ecur / 2;
