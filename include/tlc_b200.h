@@ -158,8 +158,9 @@ int tlc_last_stage_ms(tlc_graph *g, double *out10);
 int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_bfs, double *bytes_uf);
 
 /* totals over the live targets of the last call: out[0] = live targets, out[1] = sum n, out[2] = sum m,
- * out[3] = chunks, out[4] = targets the vertex-ordered sweep handed back to the edge-sorted kernels */
-int tlc_last_counts(tlc_graph *g, int64_t *out5);
+ * out[3] = chunks, out[4] = targets the vertex-ordered sweep handed back to the edge-sorted kernels,
+ * out[5..7] = blocks of the vertex order through the general path / the row check / in total (kernel 3v) */
+int tlc_last_counts(tlc_graph *g, int64_t *out8);
 
 #ifdef __cplusplus
 }

@@ -18,3 +18,4 @@ for s in range(4):
     dt = time.perf_counter() - t0
     ms, nch = g.last_stage_ms()
     print("call %d: wall %.1f ms  chunks %d  stages %s" % (s, dt * 1e3, nch, {k: round(v, 2) for k, v in ms.items()}), flush=True)
+print(g.last_counts())

@@ -17,8 +17,10 @@ def flush():
     agg = {}
 for r in rows:
     if not r: continue
-    if r[0] == "Kernel Name": flush(); kname = r[1]; continue
-    if r[0] == "File Name": fname = r[1].split("/")[-1]; continue
+    if r[0] in ("Kernel Name", "Function Name"):
+        if r[1] != kname: flush()
+        kname = r[1]; continue
+    if r[0] in ("File Name", "File Path"): fname = r[1].split("/")[-1]; continue
     if r[0] == "Line No": hdr = r; isamp = hdr.index("# Samples"); iex = hdr.index("Instructions Executed"); stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]; continue
     if hdr is None or len(r) < len(hdr) - 2: continue
     if r[0] != "": cur = (fname, r[0], r[1]); continue   # a CUDA source line; its SASS rows follow

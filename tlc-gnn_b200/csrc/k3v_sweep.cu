@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
 
   int np = 0, nmerge = 0;
   int ncomp = 0;  // components among the vertices of the blocks processed so far
+  int ngeneral = 0, nrowcheck = 0;  // statistics: blocks through the general path / through the row check
   bool bail = false;
   int s = 0;
   // block table, 32 blocks per coalesced load, the next group already in flight
@@ -92,6 +93,22 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
       const int i = b + 32 + lane;
       if (i <= nb) nxt_first = bfirst[i];
       carry = __shfl_sync(FULL, cur_first, 0);
+      // a whole group of trivial blocks above a connected prefix: every vertex of the group joins the one root
+      if (ncomp == 1 && !keep0) {
+        const int nbk = min(32, nb - b);
+        const bool triv = lane >= nbk || ((cur_first >> 30) & 3) == 1;  // bit 30 set, bit 31 clear
+        if (__all_sync(FULL, triv)) {
+          const int ge = (nbk < 32 ? __shfl_sync(FULL, cur_first, nbk) : __shfl_sync(FULL, nxt_first, 0)) & 0x3fffffff;
+          const int R = find_root(parent, 0);
+          __syncwarp();
+          for (int x = s + lane; x < ge; x += 32) parent[x] = (PT)R;
+          __syncwarp();
+          nmerge += ge - s;
+          s = ge;
+          b += nbk - 1;
+          continue;
+        }
+      }
     }
     const int wb = carry;
     // bfirst[b + 1]: lane (b+1)&31 of the current group, or lane 0 of the next one
@@ -110,6 +127,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
         // the processed prefix is ONE component: every earlier-block neighbour is in it, no row needs reading
         R = find_root(parent, 0);
       } else {
+        nrowcheck++;
         // several components below: all earlier-block neighbours of the block must share one root
         for (int x = s; x < e && ok; x++) {
           const int lx = vord[x];
@@ -138,6 +156,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
 
     // ---------------- general block ----------------
     if (!done) {
+      ngeneral++;
       const int merges_before = nmerge;
       int nrep = 0;
       for (int x = s; x < e && !bail; x++) {
@@ -232,6 +251,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
     s = e;
   }
 
+  if (lane == 0 && c.fb_counter) { atomicAdd(c.fb_counter + 1, ngeneral); atomicAdd(c.fb_counter + 2, nrowcheck); atomicAdd(c.fb_counter + 3, nb); }
   if (lane == 0) {
     if (bail) {
       c.tfb[t] = 1;

@@ -51,7 +51,7 @@ struct tlc_graph {
   int device = 0;
   GraphView gv{};
   cudaStream_t stream = nullptr, own_stream = nullptr;
-  int64_t last_live = 0, last_nv = 0, last_ne = 0, last_fb = 0;
+  int64_t last_live = 0, last_nv = 0, last_ne = 0, last_fb = 0, last_general = 0, last_rowcheck = 0, last_blocks = 0;
   char* arena = nullptr;
   size_t arena_bytes = 0, arena_req = 0;
   // vicinity scratch (depends on hop)
@@ -348,7 +348,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   g->nchunks = 0;
   g->alg_bytes = g->alg_bytes_bfs = g->alg_bytes_uf = 0;
   g->last_live = g->last_nv = g->last_ne = g->last_fb = 0;
-  CK(cudaMemsetAsync(g->work_counter + 1, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(g->work_counter + 4, 0, 4 * sizeof(int), st));
   if (cnt_compute) *cnt_compute = 0;
   if (E == 0) return TLC_OK;
   const bool bad_desc = p.descriptor < 0 || p.descriptor > 2;
@@ -439,7 +439,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     }
     if (T == 0) return fail(TLC_E_NOMEM, "a vicinity does not fit the arena");
     ChunkView c = carve(g->arena, T, Nv, Ne, d_targets);
-    c.fb_counter = g->work_counter + 1;
+    c.fb_counter = g->work_counter + 4;
     // offsets: [pos, pos+T) plus the terminating total.  voff/eoff need T+1 entries; the terminator is
     // written into a separate tiny pinned slot so that the next chunk's slot `q` is not clobbered.
     CK(cudaMemcpyAsync((void*)c.tidx, h_tidx + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
@@ -511,10 +511,10 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     }
   }
   {
-    int fb = 0;
-    CK(cudaMemcpyAsync(&fb, g->work_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int fb[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(fb, g->work_counter + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    g->last_fb = fb;
+    g->last_fb = fb[0]; g->last_general = fb[1]; g->last_rowcheck = fb[2]; g->last_blocks = fb[3];
   }
   CK(cudaGetLastError());
   return TLC_OK;
@@ -752,9 +752,10 @@ int tlc_graph_set_stream(tlc_graph* g, void* stream) {
   return TLC_OK;
 }
 
-int tlc_last_counts(tlc_graph* g, int64_t* out5) {
+int tlc_last_counts(tlc_graph* g, int64_t* out5) {  // out5: 8 slots
   if (!g || !out5) return TLC_E_INVALID;
   out5[0] = g->last_live; out5[1] = g->last_nv; out5[2] = g->last_ne; out5[3] = g->nchunks; out5[4] = g->last_fb;
+  out5[5] = g->last_general; out5[6] = g->last_rowcheck; out5[7] = g->last_blocks;
   return TLC_OK;
 }
 

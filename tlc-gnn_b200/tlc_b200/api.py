@@ -144,9 +144,10 @@ class VicinityGraph:
         L.check(L.lib().tlc_graph_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
     def last_counts(self):
-        out = np.zeros(5, np.int64)
+        out = np.zeros(8, np.int64)
         L.lib().tlc_last_counts(self._h, out.ctypes.data)
-        return dict(live=int(out[0]), sum_n=int(out[1]), sum_m=int(out[2]), chunks=int(out[3]), handed_back=int(out[4]))
+        return dict(live=int(out[0]), sum_n=int(out[1]), sum_m=int(out[2]), chunks=int(out[3]), handed_back=int(out[4]),
+                    blocks_general=int(out[5]), blocks_rowcheck=int(out[6]), blocks=int(out[7]))
 
     def last_algorithmic_bytes(self):
         tot = C.c_double(0)
