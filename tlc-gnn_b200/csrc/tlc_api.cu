@@ -424,11 +424,19 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   while (pos < order.size()) {
     // greedy pack: same size class, fits the arena
     int64_t T = 0, Nv = 0, Ne = 0, n_max = 0, m_max = 0;
-    const int cls0 = size_class(h_m[order[pos]]);
+    int cls0 = size_class(h_m[order[pos]]);
     size_t q = pos;
     while (q < order.size() && T < max_T) {
       const int64_t i = order[q];
-      if (!detail && size_class(h_m[i]) != cls0) break;
+      if (!detail && size_class(h_m[i]) != cls0) {
+        // a new size class starts its own chunk (own CTA width) only if it can fill the GPU about twice;
+        // a handful of smaller targets ride along in the current chunk instead of paying a tail of their own
+        const int cls1 = size_class(h_m[i]);
+        size_t q2 = q;
+        while (q2 < order.size() && q2 - q < (size_t)(2 * g->sm_count) && size_class(h_m[order[q2]]) == cls1) q2++;
+        if (q2 - q >= (size_t)(2 * g->sm_count)) break;
+        cls0 = cls1;
+      }
       if (chunk_bytes(T + 1, Nv + h_n[i], Ne + h_m[i]) > g->arena_bytes) break;
       // the staging buffers of a chunk are reused: wait for the previous chunk's upload (stream order suffices,
       // the pinned region of this chunk is [pos, q) which no earlier chunk touches)
