@@ -19,6 +19,8 @@
 //      compensated as CPython >= 3.12 does, or plain with TLC_F_SUM_PLAIN)  -- SURVEY.md F5;
 //   4. min / max / sum descriptors, block max-reduce, true division by the normaliser (:50-56).
 // Precondition (as for networkx's Dijkstra): kappa + 1 > 0.
+#include <cuda_fp16.h>
+
 #include "tlc_common.cuh"
 
 namespace tlc {
@@ -47,27 +49,37 @@ __device__ __forceinline__ double pysum_get(const PySum& p, bool plain) {
 constexpr int QCAP = 1024;  // vertices settled per phase at most
 struct FiltShared {
   double redd[32];
-  unsigned long long redu[32];
-  int32_t scan[1025];
   // the phase's settled vertices: id, first entry in the concatenated rows (exclusive degree prefix),
   // row start in the adjacency, smallest adjacency position of a tree-parent candidate
   int32_t qx[QCAP], qpre[QCAP + 1], qrs[QCAP], qbest[QCAP];
-  int qn;
+  int32_t wsum[33];
+  // double-buffered by phase parity: vertices settled in the phase / smallest tentative distance for the next one
+  int qn[2];
+  unsigned long long nmin[2];
 };
 
-__device__ inline unsigned long long block_reduce_min_u64(unsigned long long v, unsigned long long* sh) {
-  for (int o = 16; o; o >>= 1) {
-    const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = w < v ? w : v;
+// exclusive scan of data[0..cnt) in shared memory, two barriers; returns the total.  All threads call.
+__device__ inline int block_scan_shfl(int32_t* data, int cnt, int32_t* wsum) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
+  const int per = (cnt + nt - 1) / nt;
+  const int lo = min(tid * per, cnt), hi = min(lo + per, cnt);
+  int s = 0;
+  for (int i = lo; i < hi; i++) s += data[i];
+  int inc = s;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const int wv = lane < nw ? wsum[lane] : 0;
+    int winc = wv;
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += v; }
+    if (lane < nw) wsum[lane] = winc - wv;
+    if (lane == 31) wsum[32] = winc;
   }
-  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   __syncthreads();
-  if (lane_id() == 0) sh[w] = v;
-  __syncthreads();
-  unsigned long long t = sh[0];
-  for (int i = 1; i < nw; i++) t = sh[i] < t ? sh[i] : t;
-  __syncthreads();
-  return t;
+  int run = wsum[wid] + inc - s;
+  for (int i = lo; i < hi; i++) { const int v = data[i]; data[i] = run; run += v; }
+  return wsum[32];
 }
 
 __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap) {
@@ -98,7 +110,8 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   } else {
     const bool in_smem = n <= cap;
     unsigned long long* dist = in_smem ? dyn64 : c.v64a + vo;
-    uint8_t* state = in_smem ? reinterpret_cast<uint8_t*>(dyn64 + cap) : reinterpret_cast<uint8_t*>(c.vs1 + vo);
+    __half* smw = reinterpret_cast<__half*>(dyn64 + cap);  // (shared-memory route only) smallest incident weight, rounded down
+    uint8_t* state = in_smem ? reinterpret_cast<uint8_t*>(smw + cap) : reinterpret_cast<uint8_t*>(c.vs1 + vo);
     int32_t* tpar = c.vs2 + vo;                            // shortest-path tree: parent and weight of the parent edge
     double* tpw = reinterpret_cast<double*>(c.v64b + vo);
     const float* __restrict__ aminw = c.aminw + vo;
@@ -106,32 +119,36 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
     for (int r = 0; r < (two ? 2 : 1); r++) {
       const int root = r == 0 ? lu : lv;
       double* out = r == 0 ? d1 : d2;
-      for (int x = tid; x < n; x += nt) { dist[x] = INF_BITS; state[x] = FAR; tpar[x] = root; tpw[x] = 0.0; }
+      for (int x = tid; x < n; x += nt) {
+        dist[x] = INF_BITS; state[x] = FAR; tpar[x] = root; tpw[x] = 0.0;
+        if (in_smem && r == 0) smw[x] = __float2half_rd(fminf(aminw[x], 60000.f));  // rounded DOWN: the criterion stays valid
+      }
+      if (tid == 0) { sh.nmin[0] = 0ull; sh.nmin[1] = INF_BITS; sh.qn[0] = 0; sh.qn[1] = 0; }
       __syncthreads();
       if (tid == 0) { dist[root] = 0ull; state[root] = TENT; }
       __syncthreads();
       for (int phase = 0; phase < 2 * n + 2; phase++) {  // every phase settles at least one vertex
-        // ---- smallest tentative distance ----
-        unsigned long long lmin = INF_BITS;
-        for (int x = tid; x < n; x += nt)
-          if (state[x] == TENT) { const unsigned long long d = dist[x]; lmin = d < lmin ? d : lmin; }
-        const unsigned long long dminb = block_reduce_min_u64(lmin, sh.redu);
+        const int cur = phase & 1;
+        // smallest tentative distance: gathered by the previous phase (survivors of its settle scan, and every
+        // value its relaxation wrote)
+        const unsigned long long dminb = sh.nmin[cur];
         if (dminb == INF_BITS) break;  // nothing tentative left (the rest is unreachable)
         const double dmin = __longlong_as_double((long long)dminb);
         // ---- settle: d[x] <= fl(dmin + minw[x]); at most QCAP per phase (the others stay tentative) ----
-        if (tid == 0) sh.qn = 0;
-        __syncthreads();
+        unsigned long long lmin = INF_BITS;
         for (int x0 = 0; x0 < n; x0 += nt) {
           const int x = x0 + tid;
           bool take = false;
+          unsigned long long d = INF_BITS;
           if (x < n && state[x] == TENT) {
-            const double thr = __dadd_rn(dmin, (double)aminw[x]);
-            take = __longlong_as_double((long long)dist[x]) <= thr;
+            d = dist[x];
+            const double mw = in_smem ? (double)__half2float(smw[x]) : (double)aminw[x];
+            take = __longlong_as_double((long long)d) <= __dadd_rn(dmin, mw);
           }
           const unsigned bal = __ballot_sync(0xffffffffu, take);
           if (bal) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(&sh.qn, __popc(bal));
+            if (lane == 0) base = atomicAdd(&sh.qn[cur], __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
             const int pos = base + __popc(bal & lanemask_lt());
             if (take && pos < QCAP) {
@@ -140,14 +157,20 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
               sh.qpre[pos] = adeg[x];
               sh.qrs[pos] = astart[x];
               sh.qbest[pos] = 0x7fffffff;
+              d = INF_BITS;
             }
           }
+          lmin = d < lmin ? d : lmin;  // still tentative after this phase
         }
+        for (int o = 16; o; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, lmin, o); lmin = v < lmin ? v : lmin; }
+        if (lane == 0 && lmin != INF_BITS) atomicMin(&sh.nmin[cur ^ 1], lmin);
         __syncthreads();
-        const int qn = min(sh.qn, QCAP);
-        const int total = block_exclusive_scan(sh.qpre, qn, sh.scan);  // qpre[i] = first entry of row i in the phase's concatenation
+        const int qn = min(sh.qn[cur], QCAP);
+        if (tid == 0) { sh.nmin[cur] = INF_BITS; sh.qn[cur ^ 1] = 0; }  // (read by everyone before the barrier above)
+        const int total = block_scan_shfl(sh.qpre, qn, sh.wsum);  // qpre[i] = first entry of row i in the phase's concatenation
         if (tid == 0) sh.qpre[qn] = total;
         __syncthreads();
+        unsigned long long umin = INF_BITS;  // smallest distance this thread writes
         // ---- relax the settled rows, every warp an equal share of the concatenated entries (coalesced);
         //      the same read picks the tree parent of each settled vertex ----
         {
@@ -193,6 +216,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
                 if (tb < dyb) {
                   atomicMin(&dist[y], tb);
                   if (state[y] == FAR) state[y] = TENT;
+                  umin = tb < umin ? tb : umin;
                 }
                 // y a parent of the row's vertex?  (d[y] is final whenever this can hold)
                 if (dyb != INF_BITS &&
@@ -202,11 +226,14 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
             }
           }
         }
+        for (int o = 16; o; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, umin, o); umin = v < umin ? v : umin; }
+        if (lane == 0 && umin != INF_BITS) atomicMin(&sh.nmin[cur ^ 1], umin);
         __syncthreads();
         for (int i = tid; i < qn; i += nt) {
           const int x = sh.qx[i], a = sh.qbest[i];
           if (x != root && a != 0x7fffffff) { tpar[x] = (int)anb[a]; tpw[x] = aw[a]; }
         }
+        __syncthreads();  // the next phase overwrites the queue
       }
       __syncthreads();
       // ---- 3. python-order path sums ----
@@ -265,10 +292,10 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
 }  // namespace
 
 void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
-  // dist (8) + state (1) bytes per vertex in shared memory when the chunk's largest vicinity fits
+  // dist (8) + minw (2) + state (1) bytes per vertex in shared memory when the chunk's largest vicinity fits
   int cap = (int)((n_max + 7) / 8 * 8);
-  if ((size_t)cap * 9 > 180 * 1024) cap = 0;
-  const size_t bytes = (size_t)cap * 9;
+  if ((size_t)cap * 11 > 190 * 1024) cap = 0;
+  const size_t bytes = (size_t)cap * 11;
   cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
