@@ -28,8 +28,8 @@ struct K1Shared {
   int32_t target;
   int32_t next;   // next bitmap word (a batch of <= 32 vicinity vertices) to hand to a warp
   int32_t ecur;   // fill: adjacency entries reserved so far
-  int32_t bcnt[K1_BLOCK / 32][32];  // fill, per warp: kept entries / running write cursor of the batch's 32 rows
-  int32_t bmin[K1_BLOCK / 32][32];  // fill, per warp: smallest kept weight of each row (float bits, rounded down)
+  // per warp, for the batch of 32 rows in flight: degree prefix, write cursors, row starts, smallest weights
+  int32_t bcnt[K1_BLOCK / 32][32], bmin[K1_BLOCK / 32][32], bra[K1_BLOCK / 32][32], bmw[K1_BLOCK / 32][32];
   unsigned long long dacc;  // algorithmic-byte accounting: sum of expanded degrees (D_u + D_v + D_S)
   unsigned long long xacc;  // ... and number of rowptr pairs read (X)
 };
@@ -190,8 +190,8 @@ ball_build_kernel(GraphView g, Params p, VicinityScratch vs, int W, int bm_in_sm
 template <bool FILL>
 __global__ void __launch_bounds__(K1_BLOCK)
 vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int64_t E, int32_t* out_n, int32_t* out_m,
-                uint8_t* out_status, double* out_bytes, ChunkView c, VicinityScratch vs, int* work_counter, int W,
-                int bm_in_smem) {
+                int32_t* out_ds, uint8_t* out_status, double* out_bytes, ChunkView c, VicinityScratch vs, int* work_counter,
+                int W, int bm_in_smem) {
   extern __shared__ uint32_t dyn_smem[];
   __shared__ K1Shared sh;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
@@ -214,7 +214,7 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
     if (!bad) bad = g.rowptr[u + 1] == g.rowptr[u] || (!node_mode && g.rowptr[v + 1] == g.rowptr[v]);
     if (bad) {
       if (tid == 0) {
-        if (!FILL) { out_n[t] = 0; out_m[t] = 0; out_status[t] = TLC_ST_UNKNOWN_NODE; }
+        if (!FILL) { out_n[t] = 0; out_m[t] = 0; out_ds[t] = 0; out_status[t] = TLC_ST_UNKNOWN_NODE; }
         else { c.tn[t] = 0; c.tm[t] = 0; c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tlu[t] = -1; c.tlv[t] = -1;
                c.tstatus[t] = TLC_ST_UNKNOWN_NODE; }
       }
@@ -228,9 +228,11 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
 
     if (!FILL) {
       // counting pass: every induced edge is seen from both ends -> m = (sum over vicinity rows of kept entries) / 2
-      if (tid == 0) sh.next = 0;
+      if (tid == 0) { sh.next = 0; sh.ecur = 0; }
       __syncthreads();
       int msum = 0;
+      int32_t* binc = sh.bcnt[wid];  // per warp: inclusive degree prefix / row starts of the batch
+      int32_t* bra = sh.bmin[wid];
       for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(&sh.next, 1);
@@ -245,27 +247,35 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
         int inc = dg;
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
         const int total = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) atomicAdd(&sh.dacc, (unsigned long long)total);
+        __syncwarp();
+        binc[lane] = inc;
+        bra[lane] = ra - (inc - dg);  // entry e of row r sits at col[bra[r] + e]
+        __syncwarp();
+        if (lane == 0) atomicAdd(&sh.ecur, total);
+        // every lane walks the concatenated rows with its own monotone row pointer (no shuffles in the loop)
+        int r = 0, nxt = binc[0];
         constexpr int CU = 4;
-        for (int e0 = 0; e0 < total; e0 += 32 * CU) {
+        for (int e0 = lane; e0 < total; e0 += 32 * CU) {
           int32_t yy[CU];
 #pragma unroll
           for (int k = 0; k < CU; k++) {
-            const int ek = e0 + 32 * k + lane;
-            const bool act = ek < total;
-            const int e = act ? ek : total - 1;
-            const int rr = batch_row_of(inc, e);
-            const int a = __shfl_sync(0xffffffffu, ra, rr) + e - (__shfl_sync(0xffffffffu, inc, rr) - __shfl_sync(0xffffffffu, dg, rr));
-            yy[k] = (act && e0 + 32 * k < total) ? g.col[a] : -1;
+            const int e = e0 + 32 * k;
+            if (e < total) {
+              while (e >= nxt) nxt = binc[++r];
+              yy[k] = g.col[bra[r] + e];
+            } else yy[k] = -1;
           }
 #pragma unroll
           for (int k = 0; k < CU; k++) msum += (yy[k] >= 0 && test_bit(iw, yy[k])) ? 1 : 0;
         }
+        __syncwarp();
       }
       const int m = block_reduce_sum(msum, sh.red) / 2;
       if (tid == 0) {
+        sh.dacc += (unsigned long long)sh.ecur;
         out_n[t] = n;
         out_m[t] = m;
+        out_ds[t] = sh.ecur;  // D_S: sum of the vicinity vertices' degrees = capacity of the adjacency segment
         uint8_t st = TLC_ST_OK;
         if (n == 0) st = TLC_ST_EMPTY;                          // assert len(components) == 1 fails  :318
         else if (node_mode && m == 0) st = TLC_ST_EMPTY;        // `return None, None` data_utils_NC.py:103-104
@@ -280,7 +290,7 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
     }
 
     // ---- fill: vertex list, then the induced adjacency (both directions, rows ascending) ----
-    const int64_t vo = c.voff[t], ao = 2 * c.eoff[t];
+    const int64_t vo = c.voff[t], ao = c.aoff[t];
     for (int w = tid; w < W; w += nt) {
       uint32_t bits = iw[w];
       int32_t lx = (int32_t)wbase[w];
@@ -292,11 +302,14 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
     }
     if (tid == 0) { sh.next = 0; sh.ecur = 0; }
     __syncthreads();
-    // a warp takes the next bitmap word (batch of <= 32 vertices), counts the kept entries of its rows (walk 1),
-    // reserves the batch's rows in the target's adjacency segment with one atomic, and writes local neighbour
-    // ids + weights kappa+1 in row order (walk 2; the col entries of walk 1 are still in L1)
-    int32_t* bcnt = sh.bcnt[wid];
-    int32_t* bmin = sh.bmin[wid];
+    // a warp takes the next bitmap word (batch of <= 32 vertices), reserves the batch's rows (capacity = graph
+    // degree) in the target's adjacency segment with one atomic, and writes local neighbour ids + weights kappa+1
+    // compacted at each row's start, in row order: ONE walk over the concatenated rows
+    int32_t* binc = sh.bcnt[wid];   // inclusive degree prefix of the batch
+    int32_t* bcur = sh.bmin[wid];   // running write cursor of every row
+    int32_t* bra = sh.bra[wid];
+    int32_t* bmw = sh.bmw[wid];     // smallest kept weight of each row (float bits, rounded down)
+    int kept_total = 0;
     for (;;) {
       int w = 0;
       if (lane == 0) w = atomicAdd(&sh.next, 1);
@@ -312,52 +325,30 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
       int inc = dg;
       for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
       const int total = __shfl_sync(0xffffffffu, inc, 31);
-      bcnt[lane] = 0;
-      bmin[lane] = 0x7f7fffff;  // FLT_MAX
-      __syncwarp();
-      constexpr int CU = 4;
-      // ---- walk 1: kept entries per row ----
-      for (int e0 = 0; e0 < total; e0 += 32 * CU) {
-        int32_t yy[CU];
-        int rw[CU];
-#pragma unroll
-        for (int k = 0; k < CU; k++) {
-          const int ek = e0 + 32 * k + lane;
-          const bool act = ek < total;
-          const int e = act ? ek : total - 1;
-          const int rr = batch_row_of(inc, e);
-          const int a = __shfl_sync(0xffffffffu, ra, rr) + e - (__shfl_sync(0xffffffffu, inc, rr) - __shfl_sync(0xffffffffu, dg, rr));
-          rw[k] = rr;
-          yy[k] = act ? g.col[a] : -1;
-        }
-#pragma unroll
-        for (int k = 0; k < CU; k++) if (yy[k] >= 0 && test_bit(iw, yy[k])) atomicAdd(&bcnt[rw[k]], 1);
-      }
-      __syncwarp();
-      const int cntl = bcnt[lane];
-      int cinc = cntl;
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, cinc, o); if (lane >= o) cinc += v; }
       int start = 0;
-      if (lane == 31) start = atomicAdd(&sh.ecur, cinc);
-      start = __shfl_sync(0xffffffffu, start, 31);
-      const int rbase = start + cinc - cntl;
-      if (has) { c.astart[vo + lx] = rbase; c.adeg[vo + lx] = cntl; }
+      if (lane == 0) start = atomicAdd(&sh.ecur, total);
+      start = __shfl_sync(0xffffffffu, start, 0);
+      const int rbase = start + inc - dg;
       __syncwarp();
-      bcnt[lane] = rbase;  // from here on: the running write cursor of every row
+      binc[lane] = inc;
+      bra[lane] = ra - (inc - dg);
+      bcur[lane] = rbase;
+      bmw[lane] = 0x7f7fffff;  // FLT_MAX
       __syncwarp();
-      // ---- walk 2: write, rows stay ascending (steps in order, lanes of a step ranked inside their row) ----
+      int r = 0, nxt = binc[0];
+      constexpr int CU = 4;
       for (int e0 = 0; e0 < total; e0 += 32 * CU) {
         int32_t yy[CU];
         int rw[CU], aa[CU];
 #pragma unroll
         for (int k = 0; k < CU; k++) {
-          const int ek = e0 + 32 * k + lane;
-          const bool act = ek < total;
-          const int e = act ? ek : total - 1;
-          const int rr = batch_row_of(inc, e);
-          aa[k] = __shfl_sync(0xffffffffu, ra, rr) + e - (__shfl_sync(0xffffffffu, inc, rr) - __shfl_sync(0xffffffffu, dg, rr));
-          rw[k] = act ? rr : 32 + lane;  // idle lanes: a row of their own
-          yy[k] = act ? g.col[aa[k]] : -1;
+          const int e = e0 + 32 * k + lane;
+          if (e < total) {
+            while (e >= nxt) nxt = binc[++r];
+            rw[k] = r;
+            aa[k] = bra[r] + e;
+            yy[k] = g.col[aa[k]];
+          } else { rw[k] = 32 + lane; aa[k] = 0; yy[k] = -1; }  // idle lanes: a row of their own
         }
 #pragma unroll
         for (int k = 0; k < CU; k++) {
@@ -371,25 +362,30 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
           const unsigned above = chg & ~((2u << lane) - 1u);  // segment starts above my lane
           const int s1 = above ? __ffs(above) - 1 : 32;
           const unsigned seg = (s1 == 32 ? 0xffffffffu : ((1u << s1) - 1u)) & ~((1u << s0) - 1u);
-          const int cur = rw[k] < 32 ? bcnt[rw[k]] : 0;
+          const int cur = rw[k] < 32 ? bcur[rw[k]] : 0;
           __syncwarp();
           if (keep) {
             const int64_t o = ao + cur + __popc(km & seg & lanemask_lt());
             const double wgt = g.kappa[aa[k]] + 1.0;  // graph[a][b]['weight'] = kappa + 1   riccidist2dgm.py:225
             c.anb[o] = (uint32_t)local_id(iw, wbase, yy[k]);
             c.aw[o] = wgt;
-            atomicMin(&bmin[rw[k]], __float_as_int(__double2float_rd(wgt)));  // positive floats order like ints
+            atomicMin(&bmw[rw[k]], __float_as_int(__double2float_rd(wgt)));  // positive floats order like ints
           }
-          if (lane == s1 - 1 && rw[k] < 32) bcnt[rw[k]] = cur + __popc(km & seg);
+          if (lane == s1 - 1 && rw[k] < 32) bcur[rw[k]] = cur + __popc(km & seg);
           __syncwarp();
         }
       }
       __syncwarp();
-      if (has) c.aminw[vo + lx] = __int_as_float(bmin[lane]);  // smallest incident weight, rounded down
+      if (has) {
+        const int cntl = bcur[lane] - rbase;
+        c.astart[vo + lx] = rbase;
+        c.adeg[vo + lx] = cntl;
+        c.aminw[vo + lx] = __int_as_float(bmw[lane]);  // smallest incident weight, rounded down
+        kept_total += cntl;
+      }
       __syncwarp();
     }
-    __syncthreads();
-    const int m = sh.ecur / 2;
+    const int m = block_reduce_sum(kept_total, sh.red) / 2;
     if (tid == 0) {
       c.tn[t] = n;
       c.tm[t] = m;
@@ -442,15 +438,15 @@ void launch_ball_cache(const GraphView& g, const Params& p, const int32_t* targe
 }
 
 void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
-                           int32_t* out_m, uint8_t* out_status, double* out_bytes, const VicinityScratch& vs,
-                           int* work_counter, cudaStream_t st) {
+                           int32_t* out_m, int32_t* out_ds, uint8_t* out_status, double* out_bytes,
+                           const VicinityScratch& vs, int* work_counter, cudaStream_t st) {
   const int W = (g.N + 31) / 32;
   const bool smem = vs.bitmaps == nullptr;
   const size_t bytes = smem ? (size_t)2 * W * 4 : 0;
   set_smem((const void*)vicinity_kernel<false>, bytes);
   cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   ChunkView dummy{};
-  vicinity_kernel<false><<<vs.grid, K1_BLOCK, bytes, st>>>(g, p, targets, E, out_n, out_m, out_status, out_bytes, dummy, vs,
+  vicinity_kernel<false><<<vs.grid, K1_BLOCK, bytes, st>>>(g, p, targets, E, out_n, out_m, out_ds, out_status, out_bytes, dummy, vs,
                                                           work_counter, W, smem ? 1 : 0);
   count_launch();
 }
@@ -463,7 +459,7 @@ void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& 
   set_smem((const void*)vicinity_kernel<true>, bytes);
   cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   const int grid = vs.grid < c.T ? vs.grid : c.T;
-  vicinity_kernel<true><<<grid, K1_BLOCK, bytes, st>>>(g, p, c.tgt, c.T, nullptr, nullptr, nullptr, nullptr, c, vs, work_counter,
+  vicinity_kernel<true><<<grid, K1_BLOCK, bytes, st>>>(g, p, c.tgt, c.T, nullptr, nullptr, nullptr, nullptr, nullptr, c, vs, work_counter,
                                                       W, smem ? 1 : 0);
   count_launch();
 }

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   const int n = c.tn[t];
   if (n == 0) return;
   if (c.tstatus[t] > TLC_ST_TRIVIAL) return;
-  const int64_t vo = c.voff[t], ao = 2 * c.eoff[t];
+  const int64_t vo = c.voff[t], ao = c.aoff[t];
   const int32_t* __restrict__ astart = c.astart + vo;
   const int32_t* __restrict__ adeg = c.adeg + vo;
   const uint32_t* __restrict__ anb = c.anb + ao;

@@ -18,7 +18,7 @@ __global__ void edgelist_kernel(Params p, ChunkView c, int fb_only) {
   const int n = c.tn[t];
   if (n == 0) return;
   if (fb_only && (!c.tfb[t] || c.tstatus[t] > TLC_ST_TRIVIAL)) return;  // (all live targets when diagrams are wanted)
-  const int64_t vo = c.voff[t], eo = c.eoff[t], ao = 2 * eo;
+  const int64_t vo = c.voff[t], eo = c.eoff[t], ao = c.aoff[t];
   const int32_t* __restrict__ astart = c.astart + vo;
   const int32_t* __restrict__ adeg = c.adeg + vo;
   const uint32_t* __restrict__ anb = c.anb + ao;

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   const int n = c.tn[t];
   if (tid == 0) c.tfb[t] = 0;
   if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
-  const int64_t vo = c.voff[t], ao = 2 * c.eoff[t];
+  const int64_t vo = c.voff[t], ao = c.aoff[t];
   const double* __restrict__ fval = c.fval + vo;
   int32_t* vord = c.vord + vo;
   int32_t* vrank = c.vrank + vo;

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   const int32_t* __restrict__ bfirst = c.bfirst + vo + t;
   const int32_t* __restrict__ astart = c.astart + vo;
   const int32_t* __restrict__ adeg = c.adeg + vo;
-  const uint32_t* __restrict__ anb = c.anb + 2 * eo;
+  const uint32_t* __restrict__ anb = c.anb + c.aoff[t];
   const double* __restrict__ fval = c.fval + vo;
   PT* parent = n <= cap ? reinterpret_cast<PT*>(dyn_raw) + (size_t)wid * cap : reinterpret_cast<PT*>(c.vs2 + vo);
   RepBuf& rb = reps_all[wid];

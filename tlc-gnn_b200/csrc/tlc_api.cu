@@ -43,9 +43,10 @@ static size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
 // bytes of arena per vertex / edge / pair slot (see carve())
 static constexpr size_t BV = 4 * 6 + 8 * 3 + 8 * 3 + 4 * 6;           // vert vcls vs0 vs1 vs2 neg | fval d1 d2 | v64a v64b v64c | vord vrank bfirst astart adeg aminw
-static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1 + 2 * 12;  // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg | anb aw (2 per edge)
+static constexpr size_t BE = 4 * 4 + 8 + 4 * 4 + 8 * 2 + 1;           // elo ehi pos arank | ew | ord_asc ord_desc sp0 sp1 | sk0 sk1 | isneg
+static constexpr size_t BA = 4 + 8;                                   // anb | aw, per adjacency slot
 static constexpr size_t BP = 1 + 4 * 2 + 8 * 2;                       // pkind | pbv pdv | pbirth pdeath
-static constexpr size_t BT = 8 * 3 + 4 * 11 + 2 + 4;                  // tidx voff eoff | tn tm tlu tlv tnp tnpos tnneg tncls tnb tminv tmaxv | tstatus tfb | bfirst terminator
+static constexpr size_t BT = 8 * 4 + 4 * 11 + 2 + 4;                  // tidx voff eoff aoff | tn tm tlu tlv tnp tnpos tnneg tncls tnb tminv tmaxv | tstatus tfb | bfirst terminator
 
 struct tlc_graph {
   int device = 0;
@@ -64,7 +65,7 @@ struct tlc_graph {
   int vic_grid = 0, vic_hop = -1;
   int* work_counter = nullptr;
   // per-call device buffers
-  int32_t *d_n = nullptr, *d_m = nullptr;
+  int32_t *d_n = nullptr, *d_m = nullptr, *d_ds = nullptr;
   uint8_t* d_st = nullptr;
   double* d_bytes = nullptr;
   int64_t call_cap = 0;
@@ -98,12 +99,14 @@ static int ensure_call_buffers(tlc_graph* g, int64_t E) {
   if (E <= g->call_cap) return TLC_OK;
   if (g->d_n) cudaFree(g->d_n);
   if (g->d_m) cudaFree(g->d_m);
+  if (g->d_ds) cudaFree(g->d_ds);
   if (g->d_st) cudaFree(g->d_st);
   if (g->d_bytes) cudaFree(g->d_bytes);
-  g->d_n = g->d_m = nullptr; g->d_st = nullptr; g->d_bytes = nullptr; g->call_cap = 0;
+  g->d_n = g->d_m = g->d_ds = nullptr; g->d_st = nullptr; g->d_bytes = nullptr; g->call_cap = 0;
   const int64_t cap = E + E / 8 + 1024;
   CK(cudaMalloc((void**)&g->d_n, cap * 4));
   CK(cudaMalloc((void**)&g->d_m, cap * 4));
+  CK(cudaMalloc((void**)&g->d_ds, cap * 4));
   CK(cudaMalloc((void**)&g->d_st, cap));
   CK(cudaMalloc((void**)&g->d_bytes, cap * 8));
   g->call_cap = cap;
@@ -191,10 +194,10 @@ static int ensure_vicinity_scratch(tlc_graph* g, const Params& p) {
 }
 
 // carve the arena for a chunk with T targets, Nv vertices, Ne edges (pairs = Nv + Ne + T)
-static size_t chunk_bytes(int64_t T, int64_t Nv, int64_t Ne) {
+static size_t chunk_bytes(int64_t T, int64_t Nv, int64_t Ne, int64_t Na) {
   const int64_t Np = Nv + Ne + T;
   // every array individually aligned: 16 vertex arrays, 13 edge arrays, 5 pair arrays, 16 target arrays
-  return (size_t)(Nv * BV + Ne * BE + Np * BP + (T + 1) * BT) + ALIGN * 56;
+  return (size_t)(Nv * BV + Ne * BE + Na * BA + Np * BP + (T + 1) * BT) + ALIGN * 58;
 }
 
 template <typename T_>
@@ -204,7 +207,7 @@ static T_* take(char*& cur, int64_t count) {
   return p;
 }
 
-static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, const int32_t* d_targets) {
+static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, int64_t Na, const int32_t* d_targets) {
   ChunkView c{};
   char* cur = arena;
   const int64_t Np = Nv + Ne + T;
@@ -213,6 +216,7 @@ static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, const int
   c.tidx = take<int64_t>(cur, T);
   c.voff = take<int64_t>(cur, T + 1);
   c.eoff = take<int64_t>(cur, T + 1);
+  c.aoff = take<int64_t>(cur, T + 1);
   c.tn = take<int32_t>(cur, T); c.tm = take<int32_t>(cur, T); c.tlu = take<int32_t>(cur, T); c.tlv = take<int32_t>(cur, T);
   c.tnp = take<int32_t>(cur, T); c.tnpos = take<int32_t>(cur, T); c.tnneg = take<int32_t>(cur, T); c.tncls = take<int32_t>(cur, T);
   c.tnb = take<int32_t>(cur, T); c.tminv = take<int32_t>(cur, T); c.tmaxv = take<int32_t>(cur, T);
@@ -221,7 +225,7 @@ static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, const int
   c.vord = take<int32_t>(cur, Nv); c.vrank = take<int32_t>(cur, Nv);
   c.bfirst = take<int32_t>(cur, Nv + T);
   c.astart = take<int32_t>(cur, Nv); c.adeg = take<int32_t>(cur, Nv); c.aminw = take<float>(cur, Nv);
-  c.anb = take<uint32_t>(cur, 2 * Ne); c.aw = take<double>(cur, 2 * Ne);
+  c.anb = take<uint32_t>(cur, Na); c.aw = take<double>(cur, Na);
   c.vert = take<int32_t>(cur, Nv); c.vcls = take<int32_t>(cur, Nv); c.vs0 = take<int32_t>(cur, Nv);
   c.vs1 = take<int32_t>(cur, Nv); c.vs2 = take<int32_t>(cur, Nv); c.neg = take<int32_t>(cur, Nv);
   c.fval = take<double>(cur, Nv); c.d1 = take<double>(cur, Nv); c.d2 = take<double>(cur, Nv);
@@ -365,17 +369,20 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   VicinityScratch vs = make_vs(g);
   tm.mark(0);
   launch_ball_cache(g->gv, p, d_targets, E, vs, st);
-  launch_vicinity_sizes(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_st, g->d_bytes, vs, g->work_counter, st);
+  launch_vicinity_sizes(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->work_counter, st);
   tm.mark(-1);
   const size_t pin_need = align_up((size_t)E * 8) + (size_t)E * 9 + ALIGN;
-  if ((rc = ensure_pinned(g, align_up(pin_need) + (size_t)(E + 2) * 8 * 3 + ALIGN))) return rc;
+  const size_t pin_need2 = align_up((size_t)E * 4);  // h_ds
+  if ((rc = ensure_pinned(g, align_up(pin_need) + pin_need2 + (size_t)(E + 2) * 8 * 4 + ALIGN))) return rc;
   int32_t* h_n = reinterpret_cast<int32_t*>(g->h_pin);
   int32_t* h_m = h_n + E;
   double* h_bytes = reinterpret_cast<double*>(g->h_pin + align_up((size_t)E * 8));
   uint8_t* h_st = reinterpret_cast<uint8_t*>(h_bytes + E);
-  char* h_chunk = g->h_pin + align_up(pin_need);  // [tidx | voff | eoff] staging, (E+2)*8 each
+  int32_t* h_ds = reinterpret_cast<int32_t*>(g->h_pin + align_up(pin_need));
+  char* h_chunk = g->h_pin + align_up(pin_need) + pin_need2;  // [tidx | voff | eoff | aoff] staging, (E+2)*8 each
   CK(cudaMemcpyAsync(h_n, g->d_n, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_m, g->d_m, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_ds, g->d_ds, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_st, g->d_st, (size_t)E, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_bytes, g->d_bytes, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
   // rows of targets that never reach the image kernel stay zero (riccidist2dgm.py:363)
@@ -405,11 +412,11 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     });
   }
   int64_t need_one = 0;
-  for (int64_t i : order) need_one = std::max<int64_t>(need_one, (int64_t)chunk_bytes(1, h_n[i], h_m[i]));
+  for (int64_t i : order) need_one = std::max<int64_t>(need_one, (int64_t)chunk_bytes(1, h_n[i], h_m[i], h_ds[i]));
   if (detail) {
-    int64_t Nv = 0, Ne = 0;
-    for (int64_t i : order) { Nv += h_n[i]; Ne += h_m[i]; }
-    need_one = (int64_t)chunk_bytes(E, Nv, Ne);
+    int64_t Nv = 0, Ne = 0, Na = 0;
+    for (int64_t i : order) { Nv += h_n[i]; Ne += h_m[i]; Na += h_ds[i]; }
+    need_one = (int64_t)chunk_bytes(E, Nv, Ne, Na);
     if (Nv > detail->cap_v || Ne > detail->cap_e || Nv + Ne + E > detail->cap_p)
       return fail(TLC_E_CAPACITY, "detail capacity too small: need v=" + std::to_string(Nv) + " e=" +
                                       std::to_string(Ne) + " p=" + std::to_string(Nv + Ne + E));
@@ -421,9 +428,10 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   int64_t* h_tidx = reinterpret_cast<int64_t*>(h_chunk);
   int64_t* h_voff = h_tidx + (E + 2);
   int64_t* h_eoff = h_voff + (E + 2);
+  int64_t* h_aoff = h_eoff + (E + 2);
   while (pos < order.size()) {
     // greedy pack: same size class, fits the arena
-    int64_t T = 0, Nv = 0, Ne = 0, n_max = 0, m_max = 0;
+    int64_t T = 0, Nv = 0, Ne = 0, Na = 0, n_max = 0, m_max = 0;
     int cls0 = size_class(h_m[order[pos]]);
     size_t q = pos;
     while (q < order.size() && T < max_T) {
@@ -437,22 +445,23 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
         if (q2 - q >= (size_t)(2 * g->sm_count)) break;
         cls0 = cls1;
       }
-      if (chunk_bytes(T + 1, Nv + h_n[i], Ne + h_m[i]) > g->arena_bytes) break;
+      if (chunk_bytes(T + 1, Nv + h_n[i], Ne + h_m[i], Na + h_ds[i]) > g->arena_bytes) break;
       // the staging buffers of a chunk are reused: wait for the previous chunk's upload (stream order suffices,
       // the pinned region of this chunk is [pos, q) which no earlier chunk touches)
-      h_tidx[q] = i; h_voff[q] = Nv; h_eoff[q] = Ne;
-      Nv += h_n[i]; Ne += h_m[i];
+      h_tidx[q] = i; h_voff[q] = Nv; h_eoff[q] = Ne; h_aoff[q] = Na;
+      Nv += h_n[i]; Ne += h_m[i]; Na += h_ds[i];
       n_max = std::max<int64_t>(n_max, h_n[i]); m_max = std::max<int64_t>(m_max, h_m[i]);
       T++; q++;
     }
     if (T == 0) return fail(TLC_E_NOMEM, "a vicinity does not fit the arena");
-    ChunkView c = carve(g->arena, T, Nv, Ne, d_targets);
+    ChunkView c = carve(g->arena, T, Nv, Ne, Na, d_targets);
     c.fb_counter = g->work_counter + 4;
     // offsets: [pos, pos+T) plus the terminating total.  voff/eoff need T+1 entries; the terminator is
     // written into a separate tiny pinned slot so that the next chunk's slot `q` is not clobbered.
     CK(cudaMemcpyAsync((void*)c.tidx, h_tidx + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)c.voff, h_voff + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)c.eoff, h_eoff + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)c.aoff, h_aoff + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)(c.voff + T), &Nv, 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync((void*)(c.eoff + T), &Ne, 8, cudaMemcpyHostToDevice, st));
     std::vector<SubRange> subs;
@@ -576,7 +585,7 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaFree((void*)g->gv.rowptr); cudaFree((void*)g->gv.col); cudaFree((void*)g->gv.kappa);
   cudaFree(g->arena); cudaFree(g->bitmaps); cudaFree(g->queue); cudaFree(g->work_counter);
   cudaFree(g->ball_cache); cudaFree(g->ball_acc); cudaFree(g->ball_state); cudaFree(g->ball_list);
-  cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_st); cudaFree(g->d_bytes);
+  cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_ds); cudaFree(g->d_st); cudaFree(g->d_bytes);
   cudaFree(g->io_t); cudaFree(g->io_pi); cudaFree(g->io_st);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
@@ -634,7 +643,7 @@ int tlc_vicinity_sizes(tlc_graph* g, const int32_t* targets, int64_t E, const tl
   CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
   VicinityScratch vs = make_vs(g);
   launch_ball_cache(g->gv, p, d_t, E, vs, g->stream);
-  launch_vicinity_sizes(g->gv, p, d_t, E, g->d_n, g->d_m, g->d_st, g->d_bytes, vs, g->work_counter, g->stream);
+  launch_vicinity_sizes(g->gv, p, d_t, E, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->work_counter, g->stream);
   if (out_n) CK(cudaMemcpyAsync(out_n, g->d_n, (size_t)E * 4, cudaMemcpyDeviceToHost, g->stream));
   if (out_m) CK(cudaMemcpyAsync(out_m, g->d_m, (size_t)E * 4, cudaMemcpyDeviceToHost, g->stream));
   if (out_status) CK(cudaMemcpyAsync(out_status, g->d_st, (size_t)E, cudaMemcpyDeviceToHost, g->stream));
@@ -677,9 +686,9 @@ int tlc_union_find(int device, int32_t n, int32_t m, const double* fval, const i
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
   CK(cudaSetDevice(device));
   char* arena = nullptr;
-  const size_t bytes = chunk_bytes(1, n, m);
+  const size_t bytes = chunk_bytes(1, n, m, 0);
   CK(cudaMalloc((void**)&arena, bytes));
-  ChunkView c = carve(arena, 1, n, m, nullptr);
+  ChunkView c = carve(arena, 1, n, m, 0, nullptr);
   cudaStream_t st = nullptr;  // legacy default stream: the plain cudaMemcpy calls below order with it
   const int64_t zero = 0, nv = n, ne = m;
   const int32_t one_n = n, one_m = m, z32 = 0;

@@ -26,6 +26,7 @@ struct ChunkView {
   const int64_t* tidx;  // [T] row in the caller's output
   const int64_t* voff;  // [T+1]
   const int64_t* eoff;  // [T+1]
+  const int64_t* aoff;  // [T]   start of the target's adjacency segment (capacity: sum of the vicinity's graph degrees)
   int32_t *tn, *tm, *tlu, *tlv, *tnp, *tnpos, *tnneg, *tncls;
   int32_t *tnb, *tminv, *tmaxv;  // kernel 2v: #blocks of the vertex order, local ids of the essential pair
   uint8_t* tstatus;
@@ -39,11 +40,12 @@ struct ChunkView {
   // (n+1)-per-target arrays, addressed at voff[t] + t
   int32_t *bfirst;  // first rank of every block of the vertex order | flags in bits 31, 30 (kernel 2v), [nb] = n
   // induced adjacency (kernel 1), both directions: row of local vertex x = [astart[x], astart[x] + adeg[x])
-  // inside the target's segment, which starts at 2 * eoff[t]; rows ascending in local id
+  // inside the target's segment, which starts at aoff[t]; a row's capacity is the vertex's degree in the graph,
+  // adeg of it are used; rows ascending in local id
   int32_t *astart, *adeg;  // vertex-indexed
   float* aminw;            // vertex-indexed: smallest incident weight, rounded down (settling criterion of kernel 1b)
-  uint32_t* anb;           // [2 * sum m] neighbour local ids
-  double* aw;              // [2 * sum m] kappa + 1
+  uint32_t* anb;           // [sum D_S] neighbour local ids
+  double* aw;              // [sum D_S] kappa + 1
   // edge-indexed (canonical lexicographic (lo, hi) edge list: kernel 1c, only for the edge-sorted kernels)
   int32_t *elo, *ehi, *pos, *arank;
   double* ew;
@@ -148,8 +150,8 @@ struct VicinityScratch {
 };
 
 void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
-                           int32_t* out_m, uint8_t* out_status, double* out_bytes, const VicinityScratch& vs,
-                           int* work_counter, cudaStream_t st);
+                           int32_t* out_m, int32_t* out_ds, uint8_t* out_status, double* out_bytes,
+                           const VicinityScratch& vs, int* work_counter, cudaStream_t st);
 void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                           int* work_counter, cudaStream_t st);
 void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
