@@ -164,12 +164,23 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
         const int lx = vord[x];
         const double fx = fval[lx];
         const int xa = astart[lx], xdg = adeg[lx];
-        for (int j0 = 0; j0 < xdg && !bail; j0 += 32) {
+        // owned edges of x = its neighbours of smaller rank.  Few earlier vertices (the first ranks, typically the
+        // two roots with their huge rows): probe each of them in x's ascending row instead of scanning the row
+        const bool probe = x <= 32;
+        for (int j0 = 0; j0 < (probe ? 1 : xdg) && !bail; j0 += 32) {
           const int j = j0 + lane;
           int y = 0, ly = 0, ry = -1, lo = 0, hi = 0;
           unsigned long long K = 0;
           bool valid = false;
-          if (j < xdg) {
+          if (probe) {
+            if (lane < x) {
+              y = lane;
+              ly = vord[y];
+              int l0 = 0, h0 = xdg;  // lower bound of ly in the row
+              while (l0 < h0) { const int mid = (l0 + h0) >> 1; if ((int)anb[xa + mid] < ly) l0 = mid + 1; else h0 = mid; }
+              valid = l0 < xdg && (int)anb[xa + l0] == ly;
+            }
+          } else if (j < xdg) {
             ly = (int)anb[xa + j];
             y = vrank[ly];
             valid = y < x;  // the edge is owned by its later endpoint
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
             K = f64_to_ordered(key_asc(fx, fval[ly]));
             lo = min(lx, ly); hi = max(lx, ly);
           }
+          if (!__any_sync(FULL, valid)) continue;  // no owned edge among these 32 entries
           // first edge, in (key, lo, hi) order, per component within this chunk
           bool is_min = valid;
           for (int i = 0; i < 32; i++) {
