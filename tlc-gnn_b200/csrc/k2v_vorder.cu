@@ -13,8 +13,8 @@
 // block; only inside a block do individual edge keys matter.
 //
 // One CTA per vicinity:
-//   1. stable LSD radix sort of the n vertices on the ordered image of their float64 value
-//      (ties keep ascending local id)                    -> vord[rank] = local id, vrank[local id] = rank
+//   1. stable LSD radix sort of the n vertices on the ordered image of their value rounded down to float,
+//      runs of equal floats fixed to exact (float64 value, id) order (ties keep ascending local id)                    -> vord[rank] = local id, vrank[local id] = rank
 //   2. block starts bfirst[b], with two flags kernel 3v decides on:
 //        bit 31: the block holds distinct values (a near-tie block: edge keys inside it interleave)
 //        bit 30: every vertex of the block has a neighbour in an EARLIER block (one early-exit scan of
@@ -42,15 +42,56 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   int32_t* bfirst = c.bfirst + vo + t;
 
   // ---- 1. vertex order ----
-  unsigned long long* k0 = c.v64a + vo;
-  unsigned long long* k1 = c.v64b + vo;
+  // 32-bit pass: stable LSD radix sort on the order-preserving image of the value rounded DOWN to float (monotone,
+  // so only vertices sharing a float can be out of place); then every run of equal floats is put into exact
+  // (float64 value, id) order by the thread that finds its start -- runs are exact ties (already in id order by
+  // stability) or a handful of near-equal values.  Half the radix passes of a 64-bit sort.
+  uint32_t* k0 = reinterpret_cast<uint32_t*>(c.v64a + vo);
+  uint32_t* k1 = reinterpret_cast<uint32_t*>(c.v64b + vo);
   uint32_t* p0 = reinterpret_cast<uint32_t*>(c.vs0 + vo);
   uint32_t* p1 = reinterpret_cast<uint32_t*>(c.vs1 + vo);
-  for (int x = tid; x < n; x += nt) { k0[x] = f64_to_ordered(fval[x]); p0[x] = x; }
+  for (int x = tid; x < n; x += nt) {
+    const uint32_t b = (uint32_t)__float_as_int(__double2float_rd(fval[x]));
+    k0[x] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    p0[x] = x;
+  }
   __syncthreads();
-  const int r = block_radix_sort<unsigned long long>(k0, p0, k1, p1, n, 64, sh);
-  const unsigned long long* ks = r ? k1 : k0;
-  const uint32_t* ps = r ? p1 : p0;
+  const int r = block_radix_sort<uint32_t>(k0, p0, k1, p1, n, 32, sh);
+  const uint32_t* kf = r ? k1 : k0;
+  uint32_t* ps = r ? p1 : p0;
+  int32_t* need = c.vs2 + vo;  // need[s] = 1: the run of equal floats starting at s holds distinct float64 values
+  for (int i = tid; i < n; i += nt) need[i] = 0;
+  __syncthreads();
+  for (int i = tid + 1; i < n; i += nt) {
+    if (kf[i] != kf[i - 1] || f64_to_ordered(fval[ps[i]]) == f64_to_ordered(fval[ps[i - 1]])) continue;
+    int s0 = i - 1;
+    while (s0 > 0 && kf[s0 - 1] == kf[i]) s0--;
+    need[s0] = 1;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) {
+    if (!need[i]) continue;  // exact ties stay as the stable sort left them: ascending id
+    int j = i + 1;
+    while (j < n && kf[j] == kf[i]) j++;
+    for (int a = i + 1; a < j; a++) {  // insertion sort by (value, id)
+      const uint32_t xa = ps[a];
+      const unsigned long long ka = f64_to_ordered(fval[xa]);
+      int b = a - 1;
+      while (b >= i) {
+        const uint32_t xb = ps[b];
+        const unsigned long long kb = f64_to_ordered(fval[xb]);
+        if (kb < ka || (kb == ka && xb < xa)) break;
+        ps[b + 1] = xb;
+        b--;
+      }
+      ps[b + 1] = xa;
+    }
+  }
+  __syncthreads();
+  // exact keys in sorted order (block cuts, distinct-value flags)
+  unsigned long long* ks = (r ? c.v64a : c.v64b) + vo;  // the key buffer not holding kf
+  for (int i = tid; i < n; i += nt) ks[i] = f64_to_ordered(fval[ps[i]]);
+  __syncthreads();
   int32_t* flag = c.vs2 + vo;
   const double fmin = fval[ps[0]];
   const double pmin = __dmul_rn(__dadd_rn(fmin, 1.0), 1e-6);
@@ -95,7 +136,7 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
     const int bx = sblk[x];
     const int a = astart[x], dg = adeg[x];
     bool has = false;
-    for (int j = 0; j < dg && !has; j++) has = sblk[anb[a + j]] < bx;
+    for (int j = 0; j < dg && !has && bx > 0; j++) has = sblk[anb[a + j]] < bx;  // (block 0 has no earlier block)
     if (!has) atomicAnd(&bfirst[bx], (int32_t)~0x40000000);
   }
 }
