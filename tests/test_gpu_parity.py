@@ -91,6 +91,44 @@ def test_random_targets(name, scale, hop, cont, es):
     g.close()
 
 
+@pytest.mark.parametrize("es", [0, 1])
+@pytest.mark.parametrize("eps", [1e-10, 3e-7, 0.0])
+def test_near_tie_values(es, eps):
+    """vertex values closer than a float ulp / than the 1e-6 key perturbation and exact ties:
+    exercises the equal-float run fix of kernel 2v, the near-tie ("distinct") blocks and the representative
+    path of kernel 3v.  K common neighbours of an edge (u,v) with curvatures eps apart, some adjacent to each other,
+    plus pendant paths that create local minima and component merges."""
+    K = 40
+    edges, kap = [(0, 1)], [0.25]
+    for i in range(K):
+        x = 2 + i
+        edges += [(0, x), (1, x)]
+        kap += [0.5 + ((i * 7) % K) * eps, 0.5 - ((i * 3) % K) * eps]
+        if i % 3 == 0 and i + 1 < K:
+            edges.append((x, x + 1)); kap.append(-0.5 + i * eps)
+    base = 2 + K
+    for i in range(6):   # short cycles hanging off the roots through cheap detours
+        a, b = base + 2 * i, base + 2 * i + 1
+        edges += [(0, a), (a, b), (b, 1), (b, 2 + i)]
+        kap += [0.9 - i * eps, -0.8, 0.9 - 2 * i * eps, -0.7 + i * eps]
+    e = np.array(edges, dtype=np.int64)
+    labels, ne = gg.relabel_first_appearance(e)
+    csr = gg.build_csr(len(labels), ne, np.array(kap))
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    tg = ne[:24].astype(np.int32)
+    for hop in (1, 2):
+        for ext in (0, 1):
+            oflags = orc.F_NORM | (orc.F_EXTENDED if ext else 0)
+            flags = L.F_NORM | (L.F_EXTENDED if ext else 0) | (L.F_EDGE_SORTED if es else 0)
+            compare_detail(g, og, tg, hop, "sum", flags, oflags)
+            pi, status, cnt = g.vicinity_pi(tg, hop=hop, flags=flags)
+            o = og.run_batch(tg, hop=hop, flags=oflags)
+            assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
+            assert rel_err(pi, o["pi"]) < IMG_TOL
+    g.close()
+
+
 def test_node_mode_kd_flags():
     """PDGNN node-centred vicinities (Knowledge_Distillation/data_utils_NC.py:95-183 shape)."""
     c = gg.make_config("ppi", scale=0.25)
