@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -77,48 +76,80 @@ def config_dict(args, world):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  The timed region
+    is tens of milliseconds, so NVML is polled in-process every ~2 ms (nvidia-smi -lms cannot sample that fast);
+    falls back to a single `nvidia-smi --query-gpu` call when NVML is not importable."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.idx = gpu_index
+        self.sm, self.mask, self.max = [], 0, None
+        self.h = None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self.h = None
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if ids and i < len(ids) and ids[i].strip().isdigit():
+            return int(ids[i])
+        return i
+
+    def _sample(self):
+        if self.h is not None:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                try:
+                    self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
         try:
-            self.p.wait(timeout=5)
+            self._sample()  # at least one sample taken before the region's closing synchronize returns
         except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        for r in rows:
-            if len(r) < 9:
-                continue
-            try:
-                sm.append(float(r[1]))
-                out["sm_max_mhz"] = float(r[2])
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+            pass
+        self._stop.set()
+        self.th.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": []}
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+            out["samples"] = len(self.sm)
+            out["reasons"] = sorted(k for k, bit in self.BAD.items() if self.mask & bit)
+            out["source"] = "nvml, 2 ms poll during the timed region"
+            return out
+        try:  # no NVML: one nvidia-smi query (taken right after the region)
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            r = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=20).stdout.strip().split(", ")
+            out["sm_mhz"], out["sm_max_mhz"] = float(r[0]), float(r[1])
+            out["reasons"] = [n for n, v in zip(self.BAD, r[2:6]) if v.strip().lower().startswith("active")]
+            out["samples"] = 1
+            out["source"] = "nvidia-smi, one query at the end of the timed region"
+        except Exception:
+            pass
         return out
 
 

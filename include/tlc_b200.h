@@ -47,6 +47,16 @@ extern "C" {
                                  vertex-ordered kernels 2v+3v, which produce the identical pair sequence and hand
                                  targets they cannot finish to kernels 2+3) -- a test/diagnostic switch */
 
+#define TLC_F_NO_DIRECT 64u /* never take the graph-row route (below): always materialise the induced adjacency */
+#define TLC_F_DIRECT 128u   /* take the graph-row route for every target it supports, whatever its density.  Default:
+                               per target, when the vicinity is dense in the graph (sum of its graph degrees <=
+                               TLC_DIRECT_RATIO (env, default 3) x its induced directed edges): the filtration, vertex
+                               order and sweep kernels then read the graph's own L2-resident CSR rows through the vicinity
+                               bitmap instead of an adjacency written to HBM.  Same results bit for bit; only taken
+                               by calls that need the ascending sweep alone (no TLC_F_EXTENDED, no Pos/Neg lists) */
+#define TLC_F_ASC_ONLY 256u /* tlc_vicinity_detail: ascending sweep only -- PD_up and [min,max]; no PD_down, no edge
+                               lists / orders / Pos / Neg (those outputs are left untouched) */
+
 /* ---- pair kinds, in the reference's concatenation order    accelerated_PD.py:110, riccidist2dgm.py:328 ---- */
 #define TLC_K_UP 0      /* PD_up   : 0-dim ordinary                 accelerated_PD.py:65-66 */
 #define TLC_K_ESS 1     /* [min,max]                                accelerated_PD.py:110   */
@@ -161,6 +171,8 @@ int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_
  * out[3] = chunks, out[4] = targets the vertex-ordered sweep handed back to the edge-sorted kernels,
  * out[5..7] = blocks of the vertex order through the general path / the row check / in total (kernel 3v) */
 int tlc_last_counts(tlc_graph *g, int64_t *out8);
+/* targets of the last call that took the graph-row route (TLC_F_DIRECT / TLC_F_NO_DIRECT) */
+int64_t tlc_last_direct(tlc_graph *g);
 
 #ifdef __cplusplus
 }

@@ -126,6 +126,11 @@ def test_near_tie_values(es, eps):
             o = og.run_batch(tg, hop=hop, flags=oflags)
             assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
             assert rel_err(pi, o["pi"]) < IMG_TOL
+            if not ext and not es:  # the same through the graph-row route
+                compare_asc(g, og, tg, hop, "sum", flags | L.F_DIRECT, oflags)
+                pi_d, status_d, cnt_d = g.vicinity_pi(tg, hop=hop, flags=flags | L.F_DIRECT)
+                assert g.last_counts()["graph_row_route"] > 0
+                assert np.array_equal(pi, pi_d) and np.array_equal(status, status_d) and cnt == cnt_d
     g.close()
 
 
@@ -168,3 +173,91 @@ def test_union_find_api():
         assert np.array_equal(r["pkind"], o["pkind"])
         assert np.array_equal(r["pbirth"], o["pbirth"]) and np.array_equal(r["pdeath"], o["pdeath"])
         assert np.array_equal(r["pos"], o["pos"]) and np.array_equal(r["neg"], o["neg"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# graph-row route (TLC_F_DIRECT): no adjacency in HBM, the filtration / vertex-order / sweep kernels read the
+# graph's own CSR rows through the vicinity bitmap.  Serves ascending-sweep-only calls; must reproduce the
+# oracle's vertex set, roots, filtration values, PD_up + [min,max] pairs (ids and values) and image bit for bit.
+# ---------------------------------------------------------------------------------------------------------
+def compare_asc(g, og, targets, hop, descriptor, flags, oflags, mode=L.MODE_EDGE):
+    d = g.vicinity_detail(targets, hop=hop, mode=mode, descriptor=descriptor, flags=flags | L.F_ASC_ONLY)
+    for i, (u, v) in enumerate(targets):
+        a = g.per_target(d, i)
+        o = og.run_one(int(u), int(v), hop=hop, mode=mode, descriptor=descriptor, flags=oflags)
+        ctx = "target %d (%d,%d) status gpu %d oracle %d n %d m %d" % (i, u, v, a["status"], o["status"], o["n"], o["m"])
+        assert a["status"] == o["status"], ctx
+        assert a["n"] == o["n"], ctx
+        if o["status"] in (5,):
+            continue
+        assert np.array_equal(a["vert"], o["vert"]), ctx
+        if o["status"] > 1:
+            continue
+        assert (a["lu"], a["lv"]) == (o["lu"], o["lv"]), ctx
+        assert np.array_equal(a["fval"], o["fval"]), ctx
+        keep = np.isin(o["pkind"], (L.K_UP, L.K_ESS))
+        assert np.array_equal(a["pkind"], o["pkind"][keep]), ctx
+        assert np.array_equal(a["pbv"], o["pbv"][keep]) and np.array_equal(a["pdv"], o["pdv"][keep]), ctx
+        assert np.array_equal(a["pbirth"], o["pbirth"][keep]) and np.array_equal(a["pdeath"], o["pdeath"][keep]), ctx
+        assert rel_err(a["img"], o["img"]) < IMG_TOL, ctx
+
+
+@pytest.mark.parametrize("tag", GRAPH_CASES)
+def test_graph_row_route_golden(tag):
+    c = load_case(tag)
+    g = api.VicinityGraph(*c["csr"], device=0)
+    og = orc.OracleGraph(*c["csr"])
+    flags = L.F_NORM | L.F_DIRECT
+    pi, status, cnt = g.vicinity_pi(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=flags)
+    assert g.last_counts()["graph_row_route"] > 0
+    ref = c["pi_ext0"]  # the REAL reference's pi_sg
+    assert cnt == int(c["cnt_ext0"])
+    assert np.array_equal(ref.any(axis=1), pi.any(axis=1))
+    assert rel_err(pi, ref) < IMG_TOL
+    o = og.run_batch(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=orc.F_NORM)
+    assert np.array_equal(status, o["status"])
+    pi2, status2, cnt2 = g.vicinity_pi(c["new_targets"], hop=c["hop"], descriptor=c["descriptor"], flags=L.F_NORM | L.F_NO_DIRECT)
+    assert g.last_counts()["graph_row_route"] == 0
+    assert np.array_equal(pi, pi2) and np.array_equal(status, status2) and cnt == cnt2  # the two routes agree bit for bit
+    compare_asc(g, og, c["new_targets"], c["hop"], c["descriptor"], flags, orc.F_NORM)
+    g.close()
+
+
+@pytest.mark.parametrize("name,scale,hop,cont", [("cora", 1.0, 2, False), ("cora", 1.0, 3, False), ("pubmed", 0.3, 2, True),
+                                                 ("computers", 0.05, 2, False), ("computers", 0.05, 2, True),
+                                                 ("computers", 0.1, 1, True), ("ppi", 0.3, 1, False)])
+def test_graph_row_route_random(name, scale, hop, cont):
+    c = gg.make_config(name, scale=scale, continuous=cont)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    rng = np.random.default_rng(11)
+    tg = ne[rng.choice(len(ne), 48, replace=False)].astype(np.int32)
+    neg = rng.integers(0, len(labels), size=(16, 2)).astype(np.int32)
+    tg = np.concatenate([tg, neg, np.array([[-1, 3], [0, 0]], np.int32)])
+    compare_asc(g, og, tg, hop, "sum", L.F_NORM | L.F_DIRECT, orc.F_NORM)
+    o = og.run_batch(tg, hop=hop, flags=orc.F_NORM)
+    for fl in (L.F_DIRECT, 0, L.F_NO_DIRECT):  # forced, density-routed (mixed chunks), materialised
+        pi, status, cnt = g.vicinity_pi(tg, hop=hop, flags=L.F_NORM | fl)
+        assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
+        assert rel_err(pi, o["pi"]) < IMG_TOL
+        if fl == L.F_DIRECT:
+            pi_d = pi
+        else:
+            assert np.array_equal(pi, pi_d)
+    g.close()
+
+
+def test_graph_row_route_node_mode():
+    c = gg.make_config("ppi", scale=0.25)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    nodes = np.random.default_rng(3).choice(len(labels), 24, replace=False)
+    tg = np.stack([nodes, nodes], 1).astype(np.int32)
+    fl = L.F_NORM | L.F_KEEP_ZERO | L.F_NORM_EPS
+    for hop in (0, 1, 2):
+        compare_asc(g, og, tg, hop, "sum", fl | L.F_DIRECT, fl, mode=L.MODE_NODE)
+    g.close()

@@ -19,6 +19,13 @@
 //      compensated as CPython >= 3.12 does, or plain with TLC_F_SUM_PLAIN)  -- SURVEY.md F5;
 //   4. min / max / sum descriptors, block max-reduce, true division by the normaliser (:50-56).
 // Precondition (as for networkx's Dijkstra): kappa + 1 > 0.
+//
+// Two instantiations.  <false>: rows come from the induced adjacency kernel 1's fill pass wrote to HBM.
+// <true> (GRAPH-ROW route, dense vicinities): nothing is materialised -- the kernel builds the vicinity itself
+// (AND of the two cached ball bitmaps, word-prefix ranks, vertex list, local roots, status: what the fill pass does
+// except the adjacency) and walks the graph's own CSR rows, which stay L2-resident (<= 8 MB for every shape);
+// an entry is kept iff its graph id is in the bitmap, its local id is the bitmap rank.  The settling margin is
+// the smallest weight of the vertex's GRAPH row (<= the smallest induced weight: the criterion stays valid).
 #include <cuda_fp16.h>
 
 #include "tlc_common.cuh"
@@ -82,24 +89,86 @@ __device__ inline int block_scan_shfl(int32_t* data, int cnt, int32_t* wsum) {
   return wsum[32];
 }
 
-__global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap) {
+struct DirectArgs {
+  GraphView g;
+  const uint32_t* ball_cache;  // [N][W] closed k-hop balls (kernel 1's ball cache)
+  const float* gminw;          // [N] smallest kappa + 1 of the node's graph row, rounded down
+  int W;
+};
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap, DirectArgs da) {
   extern __shared__ unsigned long long dyn64[];
   __shared__ FiltShared sh;
   const int t = t0 + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-  const int n = c.tn[t];
-  if (n == 0) return;
-  if (c.tstatus[t] > TLC_ST_TRIVIAL) return;
-  const int64_t vo = c.voff[t], ao = c.aoff[t];
+  const bool node_mode = p.mode == TLC_MODE_NODE;
+  const int64_t vo = c.voff[t];
+  // graph-row route: vicinity bitmap [0, W) and word-prefix ranks [W, 2W), behind the per-vertex arrays
+  uint32_t* bm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dyn64) + (size_t)cap * 11);
+  const int W = da.W;
+  int n, lu, lv;
+  if (DIRECT) {
+    // ---- 0. the vicinity: nodes = set(nodes_u) & set(nodes_v), canonical local ids = ranks   riccidist2dgm.py:311-316
+    const int64_t ti = c.tidx[t];
+    const int32_t u = c.tgt[2 * ti], v = c.tgt[2 * ti + 1];
+    const GraphView& g = da.g;
+    bool bad = u < 0 || u >= g.N || (!node_mode && (v < 0 || v >= g.N));  // dict_node KeyError   :353
+    if (!bad) bad = g.rowptr[u + 1] == g.rowptr[u] || (!node_mode && g.rowptr[v + 1] == g.rowptr[v]);
+    if (bad) {
+      if (tid == 0) { c.tn[t] = 0; c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tlu[t] = -1; c.tlv[t] = -1;
+                      c.tstatus[t] = TLC_ST_UNKNOWN_NODE; }
+      return;
+    }
+    const uint32_t* __restrict__ bu = da.ball_cache + (size_t)u * W;
+    const uint32_t* __restrict__ bv = da.ball_cache + (size_t)v * W;
+    for (int w = tid; w < W; w += nt) {
+      const uint32_t x = node_mode ? bu[w] : (bu[w] & bv[w]);
+      bm[w] = x;
+      bm[W + w] = __popc(x);
+    }
+    __syncthreads();
+    n = block_scan_shfl(reinterpret_cast<int32_t*>(bm + W), W, sh.wsum);
+    __syncthreads();
+    uint32_t* gb = c.dbm + (size_t)t * 2 * W;  // kernels 2v / 3v map graph ids through it
+    for (int w = tid; w < 2 * W; w += nt) gb[w] = bm[w];
+    for (int w = wid; w < W; w += nw) {  // a warp per bitmap word: vertex list, graph rows, settling margins
+      const uint32_t bits = bm[w];
+      if (!((bits >> lane) & 1u)) continue;
+      const int lx = (int)bm[W + w] + __popc(bits & lanemask_lt());
+      const int32_t x = w * 32 + lane;
+      const int32_t ra = g.rowptr[x];
+      c.vert[vo + lx] = x;
+      c.astart[vo + lx] = ra;
+      c.adeg[vo + lx] = g.rowptr[x + 1] - ra;
+      c.aminw[vo + lx] = da.gminw[x];
+    }
+    lu = bitmap_rank(bm, W, u);
+    lv = node_mode ? lu : bitmap_rank(bm, W, v);
+    uint8_t st0 = (lu >= 0 && lv >= 0) ? TLC_ST_OK : TLC_ST_TRIVIAL;
+    // node mode: `return None, None` when the ball has no edge (data_utils_NC.py:103-104) <=> it is the lone centre
+    if (n == 0 || (node_mode && n == 1)) st0 = TLC_ST_EMPTY;  // :318
+    if (tid == 0) {
+      c.tn[t] = n; c.tlu[t] = lu; c.tlv[t] = lv; c.tstatus[t] = st0;
+      c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tncls[t] = 0;
+    }
+    __syncthreads();
+    if (n == 0 || st0 > TLC_ST_TRIVIAL) return;
+  } else {
+    n = c.tn[t];
+    if (n == 0) return;
+    if (c.tstatus[t] > TLC_ST_TRIVIAL) return;
+    lu = c.tlu[t]; lv = c.tlv[t];
+  }
+  const int64_t ao = DIRECT ? 0 : c.aoff[t];
   const int32_t* __restrict__ astart = c.astart + vo;
   const int32_t* __restrict__ adeg = c.adeg + vo;
-  const uint32_t* __restrict__ anb = c.anb + ao;
-  const double* __restrict__ aw = c.aw + ao;
+  // rows: induced adjacency segment of the target, or (graph-row route) the graph's CSR itself
+  const uint32_t* __restrict__ anb = DIRECT ? reinterpret_cast<const uint32_t*>(da.g.col) : c.anb + ao;
+  const double* __restrict__ aw = DIRECT ? da.g.kappa : c.aw + ao;
   double* d1 = c.d1 + vo;
   double* d2 = c.d2 + vo;
   double* fval = c.fval + vo;
-  const int lu = c.tlu[t], lv = c.tlv[t];
-  const bool node_mode = p.mode == TLC_MODE_NODE;
   const bool roots_in = lu >= 0 && lv >= 0;
   const bool plain = (p.flags & TLC_F_SUM_PLAIN) != 0;
   const bool two = roots_in && !node_mode && lu != lv;
@@ -209,8 +278,9 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
 #pragma unroll
               for (int k = 0; k < RU; k++) {
                 if (ai[k] < 0) continue;
-                const int y = yy[k];
-                const double w = ww[k];
+                const int y = DIRECT ? bitmap_rank(bm, W, yy[k]) : yy[k];
+                if (DIRECT && y < 0) continue;  // the neighbour is outside the vicinity
+                const double w = DIRECT ? __dadd_rn(ww[k], 1.0) : ww[k];  // weight = kappa + 1   riccidist2dgm.py:225
                 const unsigned long long dyb = dist[y];
                 const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dx[k]), w));
                 if (tb < dyb) {
@@ -231,7 +301,10 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
         __syncthreads();
         for (int i = tid; i < qn; i += nt) {
           const int x = sh.qx[i], a = sh.qbest[i];
-          if (x != root && a != 0x7fffffff) { tpar[x] = (int)anb[a]; tpw[x] = aw[a]; }
+          if (x != root && a != 0x7fffffff) {
+            tpar[x] = DIRECT ? bitmap_rank(bm, W, (int)anb[a]) : (int)anb[a];
+            tpw[x] = DIRECT ? __dadd_rn(aw[a], 1.0) : aw[a];
+          }
         }
         __syncthreads();  // the next phase overwrites the queue
       }
@@ -296,11 +369,26 @@ void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int
   int cap = (int)((n_max + 7) / 8 * 8);
   if ((size_t)cap * 11 > 190 * 1024) cap = 0;
   const size_t bytes = (size_t)cap * 11;
-  cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  cudaFuncSetAttribute((const void*)filtration_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void*)filtration_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaFuncSetAttribute((const void*)filtration_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
   if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
-  filtration_kernel<<<cnt, block, bytes, st>>>(p, c, t0, cap);
+  filtration_kernel<false><<<cnt, block, bytes, st>>>(p, c, t0, cap, DirectArgs{});
+  count_launch();
+}
+
+void launch_filtration_direct(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
+                              const float* gminw, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
+  const int W = (g.N + 31) / 32;
+  const size_t bmb = (size_t)2 * W * 4;
+  int cap = (int)((n_max + 7) / 8 * 8);
+  if ((size_t)cap * 11 + bmb > 190 * 1024) cap = 0;
+  const size_t bytes = (size_t)cap * 11 + bmb;
+  cudaFuncSetAttribute((const void*)filtration_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaFuncSetAttribute((const void*)filtration_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (block < 128) block = 128;  // the prologue walks the bitmap a warp per word
+  if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
+  filtration_kernel<true><<<cnt, block, bytes, st>>>(p, c, t0, cap, DirectArgs{g, vs.ball_cache, gminw, W});
   count_launch();
 }
 

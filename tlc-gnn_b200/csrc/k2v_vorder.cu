@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   const int n = c.tn[t];
   if (tid == 0) c.tfb[t] = 0;
   if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
-  const int64_t vo = c.voff[t], ao = c.aoff[t];
+  const int64_t vo = c.voff[t], ao = c.dbm ? 0 : c.aoff[t];
   const double* __restrict__ fval = c.fval + vo;
   int32_t* vord = c.vord + vo;
   int32_t* vrank = c.vrank + vo;
@@ -131,6 +131,22 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   __syncthreads();
   const int32_t* __restrict__ astart = c.astart + vo;
   const int32_t* __restrict__ adeg = c.adeg + vo;
+  if (c.dbm) {
+    // graph-row route: the row is the graph's CSR row, entries outside the vicinity bitmap are skipped
+    const uint32_t* __restrict__ bm = c.dbm + (size_t)t * 2 * c.W;
+    const int32_t* __restrict__ gcol = c.gcol;
+    for (int x = tid; x < n; x += nt) {
+      const int bx = sblk[x];
+      const int a = astart[x], dg = adeg[x];
+      bool has = false;
+      for (int j = 0; j < dg && !has && bx > 0; j++) {
+        const int y = bitmap_rank(bm, c.W, gcol[a + j]);
+        has = y >= 0 && sblk[y] < bx;
+      }
+      if (!has) atomicAnd(&bfirst[bx], (int32_t)~0x40000000);
+    }
+    return;
+  }
   const uint32_t* __restrict__ anb = c.anb + ao;
   for (int x = tid; x < n; x += nt) {  // x: local id
     const int bx = sblk[x];

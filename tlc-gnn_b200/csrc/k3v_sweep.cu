@@ -67,7 +67,14 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   const int32_t* __restrict__ bfirst = c.bfirst + vo + t;
   const int32_t* __restrict__ astart = c.astart + vo;
   const int32_t* __restrict__ adeg = c.adeg + vo;
-  const uint32_t* __restrict__ anb = c.anb + c.aoff[t];
+  // rows: the induced adjacency (local neighbour ids), or on the graph-row route the graph's CSR row of vert[x]
+  // mapped through the vicinity bitmap (-1: the neighbour is outside the vicinity)
+  const bool direct = c.dbm != nullptr;
+  const uint32_t* __restrict__ anb = direct ? reinterpret_cast<const uint32_t*>(c.gcol) : c.anb + c.aoff[t];
+  const uint32_t* __restrict__ bm = direct ? c.dbm + (size_t)t * 2 * c.W : nullptr;
+  const int32_t* __restrict__ vert = c.vert + vo;
+  const int bW = c.W;
+  auto nbr = [&](int pos) -> int { return direct ? bitmap_rank(bm, bW, (int)anb[pos]) : (int)anb[pos]; };
   const double* __restrict__ fval = c.fval + vo;
   PT* parent = n <= cap ? reinterpret_cast<PT*>(dyn_raw) + (size_t)wid * cap : reinterpret_cast<PT*>(c.vs2 + vo);
   RepBuf& rb = reps_all[wid];
@@ -134,7 +141,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
           const int a = astart[lx], dg = adeg[lx];
           for (int j0 = 0; j0 < dg && ok; j0 += 32) {
             const int j = j0 + lane;
-            const int ry = j < dg ? vrank[anb[a + j]] : e;  // e: "not in an earlier block", ignored
+            const int ly = j < dg ? nbr(a + j) : -1;
+            const int ry = ly >= 0 ? vrank[ly] : e;  // e: "not in an earlier block", ignored
             const bool out = ry < s;
             const int rt = out ? find_root(parent, ry) : -1;
             const unsigned bo = __ballot_sync(FULL, out);
@@ -176,14 +184,17 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
             if (lane < x) {
               y = lane;
               ly = vord[y];
+              const int key = direct ? vert[ly] : ly;  // rows ascend in graph id and in local id alike
               int l0 = 0, h0 = xdg;  // lower bound of ly in the row
-              while (l0 < h0) { const int mid = (l0 + h0) >> 1; if ((int)anb[xa + mid] < ly) l0 = mid + 1; else h0 = mid; }
-              valid = l0 < xdg && (int)anb[xa + l0] == ly;
+              while (l0 < h0) { const int mid = (l0 + h0) >> 1; if ((int)anb[xa + mid] < key) l0 = mid + 1; else h0 = mid; }
+              valid = l0 < xdg && (int)anb[xa + l0] == key;
             }
           } else if (j < xdg) {
-            ly = (int)anb[xa + j];
-            y = vrank[ly];
-            valid = y < x;  // the edge is owned by its later endpoint
+            ly = nbr(xa + j);
+            if (ly >= 0) {
+              y = vrank[ly];
+              valid = y < x;  // the edge is owned by its later endpoint
+            }
           }
           if (valid) {
             ry = find_root(parent, y);  // no union has happened in this block yet: component at block start

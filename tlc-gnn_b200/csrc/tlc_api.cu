@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -64,6 +65,8 @@ struct tlc_graph {
   int32_t *ball_state = nullptr, *ball_list = nullptr;
   int vic_grid = 0, vic_hop = -1;
   int* work_counter = nullptr;
+  float* gminw = nullptr;  // [N] smallest kappa + 1 of each node's row, rounded down (graph-row route's settling margin)
+  int64_t last_direct = 0;  // targets of the last call that took the graph-row route
   // per-call device buffers
   int32_t *d_n = nullptr, *d_m = nullptr, *d_ds = nullptr;
   uint8_t* d_st = nullptr;
@@ -194,10 +197,11 @@ static int ensure_vicinity_scratch(tlc_graph* g, const Params& p) {
 }
 
 // carve the arena for a chunk with T targets, Nv vertices, Ne edges (pairs = Nv + Ne + T)
-static size_t chunk_bytes(int64_t T, int64_t Nv, int64_t Ne, int64_t Na) {
+static size_t chunk_bytes(int64_t T, int64_t Nv, int64_t Ne, int64_t Na, int64_t Wd = 0) {
   const int64_t Np = Nv + Ne + T;
-  // every array individually aligned: 16 vertex arrays, 13 edge arrays, 5 pair arrays, 16 target arrays
-  return (size_t)(Nv * BV + Ne * BE + Na * BA + Np * BP + (T + 1) * BT) + ALIGN * 58;
+  // every array individually aligned: 16 vertex arrays, 13 edge arrays, 5 pair arrays, 16 target arrays;
+  // Wd > 0 (graph-row route): bitmap + word prefix of every target
+  return (size_t)(Nv * BV + Ne * BE + Na * BA + Np * BP + (T + 1) * BT + T * Wd * 8) + ALIGN * 60;
 }
 
 template <typename T_>
@@ -207,7 +211,8 @@ static T_* take(char*& cur, int64_t count) {
   return p;
 }
 
-static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, int64_t Na, const int32_t* d_targets) {
+static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, int64_t Na, const int32_t* d_targets,
+                       int64_t Wd = 0) {
   ChunkView c{};
   char* cur = arena;
   const int64_t Np = Nv + Ne + T;
@@ -241,6 +246,8 @@ static ChunkView carve(char* arena, int64_t T, int64_t Nv, int64_t Ne, int64_t N
   c.pkind = take<uint8_t>(cur, Np);
   c.pbv = take<int32_t>(cur, Np); c.pdv = take<int32_t>(cur, Np);
   c.pbirth = take<double>(cur, Np); c.pdeath = take<double>(cur, Np);
+  c.dbm = Wd > 0 ? take<uint32_t>(cur, T * 2 * Wd) : nullptr;
+  c.W = (int32_t)Wd;
   return c;
 }
 
@@ -294,15 +301,18 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   const int block = block_for(m_max);
   VicinityScratch vs = make_vs(g);
   tm.mark(1);
-  launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
+  if (!c.dbm) launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
-  for (const SubRange& r : subs) launch_filtration(p, c, r.t0, r.cnt, block, r.n_max, st);
+  for (const SubRange& r : subs) {
+    if (c.dbm) launch_filtration_direct(g->gv, p, c, vs, g->gminw, r.t0, r.cnt, block, r.n_max, st);
+    else launch_filtration(p, c, r.t0, r.cnt, block, r.n_max, st);
+  }
   // ascending sweep: vertex-ordered kernels 2v + 3v; targets they hand back (tfb) and, when the descending
   // sweep is wanted (diagram output, Pos/Neg lists for the loops), the edge-sorted kernels 2 + 3.  The image
   // only needs PD_up and [min,max]: PD_down and [max,min] have death <= birth, i.e. weight 0.
   const bool ext = (p.flags & TLC_F_EXTENDED) != 0;
   const bool edge_sorted = (p.flags & TLC_F_EDGE_SORTED) != 0;
-  const bool want_desc = ext || want_lists;
+  const bool want_desc = (ext || want_lists) && !(p.flags & TLC_F_ASC_ONLY);
   tm.mark(3);
   if (edge_sorted) {
     cudaMemsetAsync(c.tfb, 1, (size_t)c.T, st);
@@ -312,13 +322,15 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
     launch_sweep(p, c, 0, c.T, n_max, st);
   }
   tm.mark(5);
-  // the edge-sorted kernels work on the canonical (lo, hi) edge list, derived from the adjacency where needed
-  launch_edgelist(p, c, block, want_desc ? 0 : 1, st);
-  // kernel 3b ranks loop edges by their position in the ascending order, so `extended` needs ord_asc of every target
-  launch_sort(p, c, block, want_desc ? 3 : 1, want_desc ? 0 : 1, st);
+  if (!c.dbm) {  // (graph-row route: no adjacency to derive edges from; a chunk with handed-back targets is redone)
+    // the edge-sorted kernels work on the canonical (lo, hi) edge list, derived from the adjacency where needed
+    launch_edgelist(p, c, block, want_desc ? 0 : 1, st);
+    // kernel 3b ranks loop edges by their position in the ascending order, so `extended` needs ord_asc of every target
+    launch_sort(p, c, block, want_desc ? 3 : 1, want_desc ? 0 : 1, st);
+  }
   tm.mark(6);
   const int64_t uf_ints = 2 * n_max * 4 <= 96 * 1024 ? 2 * n_max : 0;
-  launch_union_find(p, c, block, (int)uf_ints, want_desc ? 1 : 0, want_desc ? 3 : 1, 1, st);
+  if (!c.dbm) launch_union_find(p, c, block, (int)uf_ints, want_desc ? 1 : 0, want_desc ? 3 : 1, 1, st);
   tm.mark(7);
   if (ext) {
     const int64_t lp_ints = 3 * n_max * 4 <= 200 * 1024 ? 3 * n_max : 0;
@@ -334,6 +346,8 @@ static int check_params(const tlc_params* p) {
   if (p->resolution < 1 || p->resolution > 16) return fail(TLC_E_INVALID, "resolution must be in 1..16");
   if (p->hop < 0) return fail(TLC_E_INVALID, "hop must be >= 0");
   if (p->mode != TLC_MODE_EDGE && p->mode != TLC_MODE_NODE) return fail(TLC_E_INVALID, "bad mode");
+  if ((p->flags & TLC_F_ASC_ONLY) && (p->flags & TLC_F_EXTENDED))
+    return fail(TLC_E_INVALID, "TLC_F_ASC_ONLY excludes TLC_F_EXTENDED (the loops need the Pos/Neg lists)");
   return TLC_OK;
 }
 
@@ -351,7 +365,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   for (int i = 0; i < 10; i++) g->stage_ms[i] = 0;
   g->nchunks = 0;
   g->alg_bytes = g->alg_bytes_bfs = g->alg_bytes_uf = 0;
-  g->last_live = g->last_nv = g->last_ne = g->last_fb = 0;
+  g->last_live = g->last_nv = g->last_ne = g->last_fb = g->last_direct = 0;
   CK(cudaMemsetAsync(g->work_counter + 4, 0, 4 * sizeof(int), st));
   if (cnt_compute) *cnt_compute = 0;
   if (E == 0) return TLC_OK;
@@ -373,7 +387,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   tm.mark(-1);
   const size_t pin_need = align_up((size_t)E * 8) + (size_t)E * 9 + ALIGN;
   const size_t pin_need2 = align_up((size_t)E * 4);  // h_ds
-  if ((rc = ensure_pinned(g, align_up(pin_need) + pin_need2 + (size_t)(E + 2) * 8 * 4 + ALIGN))) return rc;
+  if ((rc = ensure_pinned(g, align_up(pin_need) + pin_need2 + (size_t)(E + 2) * 8 * 4 + (size_t)(E + 2) * 4 + ALIGN))) return rc;
   int32_t* h_n = reinterpret_cast<int32_t*>(g->h_pin);
   int32_t* h_m = h_n + E;
   double* h_bytes = reinterpret_cast<double*>(g->h_pin + align_up((size_t)E * 8));
@@ -399,24 +413,44 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   for (int64_t i = 0; i < E; i++)
     if (h_st[i] == TLC_ST_OK) { g->alg_bytes += h_bytes[i]; g->last_live++; g->last_nv += h_n[i]; g->last_ne += h_m[i]; }
 
+  // ---- route: graph-row (no adjacency in HBM) or materialised, per target ----
+  // the graph-row route serves calls that need the ascending sweep only; it reads D_S graph-row entries per root
+  // where the materialised route reads the 2m induced ones, so it is taken where the vicinity is dense in the graph
+  const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
+  const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
+  const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call &&
+                         !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
+  double direct_ratio = 3.0;
+  if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);
+  auto is_direct = [&](int64_t i) {
+    if (!direct_ok) return false;
+    if (p.flags & TLC_F_DIRECT) return true;
+    return h_st[i] == TLC_ST_OK && (double)h_ds[i] <= direct_ratio * 2.0 * (double)h_m[i];
+  };
   // ---- plan chunks ----
   std::vector<int64_t> order;
   order.reserve(E);
+  bool detail_direct = false;
   if (detail) {
     for (int64_t i = 0; i < E; i++) order.push_back(i);
+    detail_direct = direct_ok && (p.flags & TLC_F_DIRECT);  // one chunk, one route
   } else {
     for (int64_t i = 0; i < E; i++) if (h_st[i] == TLC_ST_OK) order.push_back(i);
+    // graph-row targets first (chunks are route-homogeneous), each group largest first
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      const bool da = is_direct(a), db = is_direct(b);
+      if (da != db) return da;
       if (h_m[a] != h_m[b]) return h_m[a] > h_m[b];
       return h_n[a] > h_n[b];
     });
   }
   int64_t need_one = 0;
-  for (int64_t i : order) need_one = std::max<int64_t>(need_one, (int64_t)chunk_bytes(1, h_n[i], h_m[i], h_ds[i]));
+  for (int64_t i : order)
+    need_one = std::max<int64_t>(need_one, (int64_t)chunk_bytes(1, h_n[i], h_m[i], h_ds[i], is_direct(i) ? Wd : 0));
   if (detail) {
     int64_t Nv = 0, Ne = 0, Na = 0;
     for (int64_t i : order) { Nv += h_n[i]; Ne += h_m[i]; Na += h_ds[i]; }
-    need_one = (int64_t)chunk_bytes(E, Nv, Ne, Na);
+    need_one = (int64_t)chunk_bytes(E, Nv, Ne, Na, detail_direct ? Wd : 0);
     if (Nv > detail->cap_v || Ne > detail->cap_e || Nv + Ne + E > detail->cap_p)
       return fail(TLC_E_CAPACITY, "detail capacity too small: need v=" + std::to_string(Nv) + " e=" +
                                       std::to_string(Ne) + " p=" + std::to_string(Nv + Ne + E));
@@ -429,33 +463,40 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   int64_t* h_voff = h_tidx + (E + 2);
   int64_t* h_eoff = h_voff + (E + 2);
   int64_t* h_aoff = h_eoff + (E + 2);
+  int32_t* h_tm = reinterpret_cast<int32_t*>(h_aoff + (E + 2));
   while (pos < order.size()) {
-    // greedy pack: same size class, fits the arena
+    // greedy pack: same route, same size class, fits the arena
     int64_t T = 0, Nv = 0, Ne = 0, Na = 0, n_max = 0, m_max = 0;
     int cls0 = size_class(h_m[order[pos]]);
+    const bool direct = detail ? detail_direct : is_direct(order[pos]);
+    const int64_t Wc = direct ? Wd : 0;
     size_t q = pos;
     while (q < order.size() && T < max_T) {
       const int64_t i = order[q];
+      if (!detail && is_direct(i) != direct) break;
       if (!detail && size_class(h_m[i]) != cls0) {
         // a new size class starts its own chunk (own CTA width) only if it can fill the GPU about twice;
         // a handful of smaller targets ride along in the current chunk instead of paying a tail of their own
         const int cls1 = size_class(h_m[i]);
         size_t q2 = q;
-        while (q2 < order.size() && q2 - q < (size_t)(2 * g->sm_count) && size_class(h_m[order[q2]]) == cls1) q2++;
+        while (q2 < order.size() && q2 - q < (size_t)(2 * g->sm_count) && size_class(h_m[order[q2]]) == cls1 &&
+               is_direct(order[q2]) == direct) q2++;
         if (q2 - q >= (size_t)(2 * g->sm_count)) break;
         cls0 = cls1;
       }
-      if (chunk_bytes(T + 1, Nv + h_n[i], Ne + h_m[i], Na + h_ds[i]) > g->arena_bytes) break;
+      if (chunk_bytes(T + 1, Nv + h_n[i], Ne + h_m[i], Na + h_ds[i], Wc) > g->arena_bytes) break;
       // the staging buffers of a chunk are reused: wait for the previous chunk's upload (stream order suffices,
       // the pinned region of this chunk is [pos, q) which no earlier chunk touches)
-      h_tidx[q] = i; h_voff[q] = Nv; h_eoff[q] = Ne; h_aoff[q] = Na;
+      h_tidx[q] = i; h_voff[q] = Nv; h_eoff[q] = Ne; h_aoff[q] = Na; h_tm[q] = h_m[i];
       Nv += h_n[i]; Ne += h_m[i]; Na += h_ds[i];
       n_max = std::max<int64_t>(n_max, h_n[i]); m_max = std::max<int64_t>(m_max, h_m[i]);
       T++; q++;
     }
     if (T == 0) return fail(TLC_E_NOMEM, "a vicinity does not fit the arena");
-    ChunkView c = carve(g->arena, T, Nv, Ne, Na, d_targets);
+    ChunkView c = carve(g->arena, T, Nv, Ne, Na, d_targets, Wc);
     c.fb_counter = g->work_counter + 4;
+    c.gcol = g->gv.col;
+    c.gkappa = g->gv.kappa;
     // offsets: [pos, pos+T) plus the terminating total.  voff/eoff need T+1 entries; the terminator is
     // written into a separate tiny pinned slot so that the next chunk's slot `q` is not clobbered.
     CK(cudaMemcpyAsync((void*)c.tidx, h_tidx + pos, (size_t)T * 8, cudaMemcpyHostToDevice, st));
@@ -474,7 +515,26 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
         subs.push_back(SubRange{(int)a, (int)(b - a), nm});
       }
     }
-    run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
+    if (direct) {
+      // the graph-row route never counts the induced edges; tm is only reported (and read by the edge-sorted kernels)
+      CK(cudaMemcpyAsync((void*)c.tm, h_tm + pos, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+      int fb0 = 0, fb1 = 0;
+      CK(cudaMemcpyAsync(&fb0, g->work_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+      run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
+      CK(cudaMemcpyAsync(&fb1, g->work_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      g->last_direct += T;
+      if (fb1 != fb0) {
+        // kernel 3v handed targets back: their edge-sorted sweep needs the adjacency -> the chunk is redone on the
+        // materialised route (its space is reserved in every chunk), image rows and statuses are rewritten
+        c.dbm = nullptr;
+        c.W = 0;
+        g->last_direct -= T;
+        run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
+      }
+    } else {
+      run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
+    }
     g->nchunks++;
     if (detail) {
       // copy every intermediate back (input order == chunk order here)
@@ -484,8 +544,10 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
       D2H(n, c.tn, T, int32_t); D2H(m, c.tm, T, int32_t); D2H(lu, c.tlu, T, int32_t); D2H(lv, c.tlv, T, int32_t);
       D2H(npairs, c.tnp, T, int32_t); D2H(npos, c.tnpos, T, int32_t); D2H(nneg, c.tnneg, T, int32_t);
       D2H(vert, c.vert, Nv, int32_t); D2H(fval, c.fval, Nv, double); D2H(neg, c.neg, Nv, int32_t);
-      D2H(elo, c.elo, Ne, int32_t); D2H(ehi, c.ehi, Ne, int32_t); D2H(ew, c.ew, Ne, double);
-      D2H(ord_asc, c.ord_asc, Ne, int32_t); D2H(ord_desc, c.ord_desc, Ne, int32_t); D2H(pos, c.pos, Ne, int32_t);
+      if (!(p.flags & TLC_F_ASC_ONLY)) {
+        D2H(elo, c.elo, Ne, int32_t); D2H(ehi, c.ehi, Ne, int32_t); D2H(ew, c.ew, Ne, double);
+        D2H(ord_asc, c.ord_asc, Ne, int32_t); D2H(ord_desc, c.ord_desc, Ne, int32_t); D2H(pos, c.pos, Ne, int32_t);
+      }
       D2H(pbv, c.pbv, Nv + Ne + T, int32_t); D2H(pdv, c.pdv, Nv + Ne + T, int32_t);
       D2H(pbirth, c.pbirth, Nv + Ne + T, double); D2H(pdeath, c.pdeath, Nv + Ne + T, double);
 #undef D2H
@@ -573,6 +635,19 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
     CK(cudaMemcpy(d_kappa, kappa, (size_t)nnz * 8, cudaMemcpyHostToDevice));
   }
   g->gv = GraphView{N, nnz, d_rowptr, d_col, d_kappa};
+  {
+    // per node: smallest weight kappa + 1 of its row as a float rounded DOWN (settling margin of the graph-row route)
+    std::vector<float> mw((size_t)N, 3.0e38f);
+    for (int32_t x = 0; x < N; x++) {
+      double lo = 3.0e38;
+      for (int32_t e = rowptr[x]; e < rowptr[x + 1]; e++) lo = std::min(lo, kappa[e] + 1.0);
+      float f = (float)lo;
+      if ((double)f > lo) f = std::nextafterf(f, -INFINITY);
+      mw[(size_t)x] = f;
+    }
+    CK(cudaMalloc((void**)&g->gminw, (size_t)N * sizeof(float)));
+    CK(cudaMemcpy(g->gminw, mw.data(), (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
+  }
 
   CK(cudaMalloc((void**)&g->work_counter, 64));
   *out = g;
@@ -586,7 +661,7 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaFree(g->arena); cudaFree(g->bitmaps); cudaFree(g->queue); cudaFree(g->work_counter);
   cudaFree(g->ball_cache); cudaFree(g->ball_acc); cudaFree(g->ball_state); cudaFree(g->ball_list);
   cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_ds); cudaFree(g->d_st); cudaFree(g->d_bytes);
-  cudaFree(g->io_t); cudaFree(g->io_pi); cudaFree(g->io_st);
+  cudaFree(g->io_t); cudaFree(g->io_pi); cudaFree(g->io_st); cudaFree(g->gminw);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   delete g;
@@ -775,6 +850,8 @@ int tlc_last_counts(tlc_graph* g, int64_t* out5) {  // out5: 8 slots
   out5[5] = g->last_general; out5[6] = g->last_rowcheck; out5[7] = g->last_blocks;
   return TLC_OK;
 }
+
+int64_t tlc_last_direct(tlc_graph* g) { return g ? g->last_direct : 0; }
 
 int tlc_last_stage_ms(tlc_graph* g, double* out10) {
   if (!g || !out10) return 0;

@@ -46,6 +46,14 @@ struct ChunkView {
   float* aminw;            // vertex-indexed: smallest incident weight, rounded down (settling criterion of kernel 1b)
   uint32_t* anb;           // [sum D_S] neighbour local ids
   double* aw;              // [sum D_S] kappa + 1
+  // GRAPH-ROW route (dbm != nullptr): no adjacency is materialised.  Row of local vertex x = the graph's CSR row of
+  // vert[x]: astart[x] = rowptr[vert[x]] (absolute position in gcol / gkappa), adeg[x] = graph degree; an entry is
+  // an induced neighbour iff its graph id is in the target's vicinity bitmap dbm[t][0..W), its local id is the
+  // bitmap rank (word prefix dbm[t][W..2W) + popcount below the bit).  anb / aw are not written.
+  uint32_t* dbm;         // [T][2W]
+  int32_t W;             // bitmap words = ceil(N / 32)
+  const int32_t* gcol;   // the graph's col[]
+  const double* gkappa;  // the graph's kappa[]
   // edge-indexed (canonical lexicographic (lo, hi) edge list: kernel 1c, only for the edge-sorted kernels)
   int32_t *elo, *ehi, *pos, *arank;
   double* ew;
@@ -72,6 +80,13 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+}
+
+// graph-row route: local id of graph node g in the vicinity whose bitmap / word prefix is bm[0..W) / bm[W..2W), -1 if absent
+__device__ __forceinline__ int bitmap_rank(const uint32_t* bm, int W, int g) {
+  const uint32_t word = bm[g >> 5];
+  if (!((word >> (g & 31)) & 1u)) return -1;
+  return (int)bm[W + (g >> 5)] + __popc(word & ((1u << (g & 31)) - 1u));
 }
 
 // order-preserving map double -> u64 (all finite values, -0 < +0 irrelevant here)
@@ -155,6 +170,10 @@ void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* t
 void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                           int* work_counter, cudaStream_t st);
 void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
+// graph-row route: builds the vicinity (bitmap, ranks, vertex list, roots, status) itself and runs the shortest-path
+// phases over the graph's own CSR rows filtered by the bitmap (everything L2-resident, no adjacency in HBM)
+void launch_filtration_direct(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
+                              const float* gminw, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
 // canonical edge list (elo, ehi, ew) from the adjacency; fb_only: only for targets with tfb[t] != 0
 void launch_edgelist(const Params& p, const ChunkView& c, int block, int fb_only, cudaStream_t st);
 // sweep_mask: bit 0 ascending, bit 1 descending.  fb_only: the ascending sweep only for targets with tfb[t] != 0.

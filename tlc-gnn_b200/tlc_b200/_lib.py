@@ -13,6 +13,7 @@ SO_PATH = os.path.join(_HERE, "libtlc_b200.so")
 MODE_EDGE, MODE_NODE = 0, 1
 DESC = {"min": 0, "max": 1, "sum": 2}
 F_NORM, F_EXTENDED, F_KEEP_ZERO, F_NORM_EPS, F_SUM_PLAIN, F_EDGE_SORTED = 1, 2, 4, 8, 16, 32
+F_NO_DIRECT, F_DIRECT, F_ASC_ONLY = 64, 128, 256
 K_UP, K_ESS, K_DOWN, K_ESS_REV, K_ONE = 0, 1, 2, 3, 4
 ST_OK, ST_TRIVIAL, ST_EMPTY, ST_DISCONNECTED, ST_DEGENERATE, ST_UNKNOWN_NODE, ST_BAD_DESCRIPTOR, ST_NO_TREE_EDGES = range(8)
 ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NODE", "BAD_DESCRIPTOR", "NO_TREE_EDGES"]
@@ -20,7 +21,7 @@ ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NOD
 EXPORTS = ["tlc_graph_create", "tlc_graph_destroy", "tlc_vicinity_pi", "tlc_vicinity_pi_dev", "tlc_vicinity_sizes",
            "tlc_vicinity_detail", "tlc_union_find", "tlc_pimg_transform", "tlc_last_error", "tlc_version",
            "tlc_launch_count", "tlc_last_stage_ms", "tlc_last_algorithmic_bytes", "tlc_graph_set_stream",
-           "tlc_last_counts"]
+           "tlc_last_counts", "tlc_last_direct"]
 
 
 class Params(C.Structure):
@@ -87,6 +88,8 @@ def lib():
     L.tlc_graph_set_stream.argtypes = [vp, vp]
     L.tlc_last_counts.restype = C.c_int
     L.tlc_last_counts.argtypes = [vp, vp]
+    L.tlc_last_direct.restype = i64
+    L.tlc_last_direct.argtypes = [vp]
     _lib = L
     return L
 
