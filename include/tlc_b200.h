@@ -48,12 +48,12 @@ extern "C" {
                                  targets they cannot finish to kernels 2+3) -- a test/diagnostic switch */
 
 #define TLC_F_NO_DIRECT 64u /* never take the graph-row route (below): always materialise the induced adjacency */
-#define TLC_F_DIRECT 128u   /* take the graph-row route for every target it supports, whatever its density.  Default:
-                               per target, when the vicinity is dense in the graph (sum of its graph degrees <=
-                               TLC_DIRECT_RATIO (env, default 3) x its induced directed edges): the filtration, vertex
-                               order and sweep kernels then read the graph's own L2-resident CSR rows through the vicinity
-                               bitmap instead of an adjacency written to HBM.  Same results bit for bit; only taken
-                               by calls that need the ascending sweep alone (no TLC_F_EXTENDED, no Pos/Neg lists) */
+#define TLC_F_DIRECT 128u   /* take the graph-row route whatever the density.  Default: per call, when its vicinities
+                               are dense in the graph (sum of their graph degrees <= TLC_DIRECT_RATIO (env, default 2)
+                               x their induced directed edges): the filtration, vertex order and sweep kernels then
+                               read the graph's own L2-resident CSR rows through the vicinity bitmap instead of an
+                               adjacency written to HBM.  Same results bit for bit; only taken by calls that need
+                               the ascending sweep alone (no TLC_F_EXTENDED, no Pos/Neg lists) */
 #define TLC_F_ASC_ONLY 256u /* tlc_vicinity_detail: ascending sweep only -- PD_up and [min,max]; no PD_down, no edge
                                lists / orders / Pos / Neg (those outputs are left untouched) */
 

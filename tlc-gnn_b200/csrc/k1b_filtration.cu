@@ -96,7 +96,7 @@ struct DirectArgs {
   int W;
 };
 
-template <bool DIRECT>
+template <bool DIRECT, bool SMEM>
 __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap, DirectArgs da) {
   extern __shared__ unsigned long long dyn64[];
   __shared__ FiltShared sh;
@@ -177,10 +177,12 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
     // nx.NodeNotFound for every vertex -> dist = 100   riccidist2dgm.py:31-32,36-37
     for (int x = tid; x < n; x += nt) { d1[x] = 100.0; d2[x] = 100.0; }
   } else {
-    const bool in_smem = n <= cap;
-    unsigned long long* dist = in_smem ? dyn64 : c.v64a + vo;
+    // SMEM: the launch sized shared memory for the sub-range's largest vicinity (n <= cap); otherwise the per-vertex
+    // state lives in the arena.  A compile-time switch, so that the shared-memory accesses are LDS / ATOMS, not generic
+    constexpr bool in_smem = SMEM;
+    unsigned long long* dist = SMEM ? dyn64 : c.v64a + vo;
     __half* smw = reinterpret_cast<__half*>(dyn64 + cap);  // (shared-memory route only) smallest incident weight, rounded down
-    uint8_t* state = in_smem ? reinterpret_cast<uint8_t*>(smw + cap) : reinterpret_cast<uint8_t*>(c.vs1 + vo);
+    uint8_t* state = SMEM ? reinterpret_cast<uint8_t*>(smw + cap) : reinterpret_cast<uint8_t*>(c.vs1 + vo);
     int32_t* tpar = c.vs2 + vo;                            // shortest-path tree: parent and weight of the parent edge
     double* tpw = reinterpret_cast<double*>(c.v64b + vo);
     const float* __restrict__ aminw = c.aminw + vo;
@@ -287,11 +289,11 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
                   atomicMin(&dist[y], tb);
                   if (state[y] == FAR) state[y] = TENT;
                   umin = tb < umin ? tb : umin;
-                }
-                // y a parent of the row's vertex?  (d[y] is final whenever this can hold)
-                if (dyb != INF_BITS &&
-                    (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dx[k])
+                } else if (dyb != INF_BITS &&
+                           (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dx[k]) {
+                  // y a parent of the row's vertex (d[y] is final whenever this can hold; it cannot when d[x] + w < d[y])
                   atomicMin(&sh.qbest[ri[k]], ai[k]);
+                }
               }
             }
           }
@@ -364,32 +366,35 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
 
 }  // namespace
 
-void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
-  // dist (8) + minw (2) + state (1) bytes per vertex in shared memory when the chunk's largest vicinity fits
+template <bool DIRECT>
+static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max,
+                                  const DirectArgs& da, cudaStream_t st) {
+  // dist (8) + minw (2) + state (1) bytes per vertex in shared memory when the sub-range's largest vicinity fits;
+  // graph-row route: + the vicinity bitmap and its word-prefix ranks
+  const size_t bmb = DIRECT ? (size_t)2 * da.W * 4 : 0;
   int cap = (int)((n_max + 7) / 8 * 8);
-  if ((size_t)cap * 11 > 190 * 1024) cap = 0;
-  const size_t bytes = (size_t)cap * 11;
-  cudaFuncSetAttribute((const void*)filtration_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  cudaFuncSetAttribute((const void*)filtration_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if ((size_t)cap * 11 + bmb > 190 * 1024) cap = 0;
+  const size_t bytes = (size_t)cap * 11 + bmb;
+  if (DIRECT && block < 128) block = 128;  // the prologue walks the bitmap a warp per word
   // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
   if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
-  filtration_kernel<false><<<cnt, block, bytes, st>>>(p, c, t0, cap, DirectArgs{});
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<cnt, block, bytes, st>>>(p, c, t0, cap, da);
+  };
+  if (cap > 0) go(filtration_kernel<DIRECT, true>);
+  else go(filtration_kernel<DIRECT, false>);
   count_launch();
+}
+
+void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
+  launch_filtration_any<false>(p, c, t0, cnt, block, n_max, DirectArgs{}, st);
 }
 
 void launch_filtration_direct(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                               const float* gminw, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
-  const int W = (g.N + 31) / 32;
-  const size_t bmb = (size_t)2 * W * 4;
-  int cap = (int)((n_max + 7) / 8 * 8);
-  if ((size_t)cap * 11 + bmb > 190 * 1024) cap = 0;
-  const size_t bytes = (size_t)cap * 11 + bmb;
-  cudaFuncSetAttribute((const void*)filtration_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  cudaFuncSetAttribute((const void*)filtration_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (block < 128) block = 128;  // the prologue walks the bitmap a warp per word
-  if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
-  filtration_kernel<true><<<cnt, block, bytes, st>>>(p, c, t0, cap, DirectArgs{g, vs.ball_cache, gminw, W});
-  count_launch();
+  launch_filtration_any<true>(p, c, t0, cnt, block, n_max, DirectArgs{g, vs.ball_cache, gminw, (g.N + 31) / 32}, st);
 }
 
 }  // namespace tlc

@@ -27,7 +27,7 @@
 namespace tlc {
 namespace {
 
-__global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, int t0, int smem_ints) {
+__global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, int t0, int smem_ints, int bm_in_smem) {
   extern __shared__ int32_t dyn[];
   __shared__ SortShared sh;
   const int t = t0 + blockIdx.x;
@@ -133,7 +133,14 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   const int32_t* __restrict__ adeg = c.adeg + vo;
   if (c.dbm) {
     // graph-row route: the row is the graph's CSR row, entries outside the vicinity bitmap are skipped
-    const uint32_t* __restrict__ bm = c.dbm + (size_t)t * 2 * c.W;
+    // the bitmap and its word-prefix ranks staged behind the block table (shared memory) when the launch made room
+    const uint32_t* gbm = c.dbm + (size_t)t * 2 * c.W;
+    uint32_t* sbm = reinterpret_cast<uint32_t*>(dyn + smem_ints);
+    if (bm_in_smem) {
+      for (int w = tid; w < 2 * c.W; w += nt) sbm[w] = gbm[w];
+      __syncthreads();
+    }
+    const uint32_t* __restrict__ bm = bm_in_smem ? sbm : gbm;
     const int32_t* __restrict__ gcol = c.gcol;
     for (int x = tid; x < n; x += nt) {
       const int bx = sblk[x];
@@ -161,10 +168,11 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
 
 void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
   const int smem_ints = n_max * 4 <= 160 * 1024 ? (int)n_max : 0;
-  const size_t bytes = (size_t)smem_ints * 4;
+  const int bm_in_smem = c.dbm != nullptr && (size_t)c.W * 8 <= 48 * 1024;
+  const size_t bytes = (size_t)smem_ints * 4 + (bm_in_smem ? (size_t)c.W * 8 : 0);
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints);
+  vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints, bm_in_smem);
   count_launch();
 }
 

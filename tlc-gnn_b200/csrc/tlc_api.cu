@@ -420,13 +420,17 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
   const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call &&
                          !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
-  double direct_ratio = 3.0;
+  double direct_ratio = 2.0;
   if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);
-  auto is_direct = [&](int64_t i) {
-    if (!direct_ok) return false;
-    if (p.flags & TLC_F_DIRECT) return true;
-    return h_st[i] == TLC_ST_OK && (double)h_ds[i] <= direct_ratio * 2.0 * (double)h_m[i];
-  };
+  // one route per call, by the aggregate density of its live vicinities (measured on B200: mixing routes inside a call
+  // costs more in extra chunks than per-target routing gains; Computers-shaped 2-hop: ratio 1.4, PubMed / collab: > 2)
+  bool call_direct = direct_ok && (p.flags & TLC_F_DIRECT);
+  if (direct_ok && !call_direct) {
+    double sds = 0, sm2 = 0;
+    for (int64_t i = 0; i < E; i++) if (h_st[i] == TLC_ST_OK) { sds += h_ds[i]; sm2 += 2.0 * h_m[i]; }
+    call_direct = sm2 > 0 && sds <= direct_ratio * sm2;
+  }
+  auto is_direct = [&](int64_t) { return call_direct; };
   // ---- plan chunks ----
   std::vector<int64_t> order;
   order.reserve(E);

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libtlc_b200.so")
+SO_PATH = os.environ.get("TLC_LIB") or os.path.join(_HERE, "libtlc_b200.so")  # TLC_LIB: a differently tuned build (experiments)
 
 # mirrors of the header's constants
 MODE_EDGE, MODE_NODE = 0, 1
