@@ -119,7 +119,7 @@ int tlc_vicinity_sizes(tlc_graph *g, const int32_t *targets, int64_t E, const tl
  *   ord_asc, ord_desc[sum m] edge index in sweep order    (kernel 2; accelerated_PD.py:40-41,76-77)
  *   pairs: npairs[E]; pkind/pbv/pdv/pbirth/pdeath at poff (kernel 3/3b; local vertex ids)
  *   pos/neg edge indices in sweep order at eoff / voff; npos[E], nneg[E]
- *   pi[E][res*res], status[E]
+ *   pi[E][res*res], status[E]; pi_up / pi_one[E][res*res]: images of the kind-0 / kind-4 pairs alone
  * Any output pointer may be NULL.  cap_v/cap_e/cap_p are the capacities of the segment buffers
  * (TLC_E_CAPACITY if exceeded; use tlc_vicinity_sizes first). */
 typedef struct {
@@ -134,6 +134,9 @@ typedef struct {
   int32_t *pos, *neg;
   double *pi;
   uint8_t *status;
+  /* PDGNN generator images (Knowledge_Distillation/data_utils_NC.py:172-176): the image of the PD_up pairs alone
+   * (PI0 = transform(dgmOrd0)) and of the 1-dim extended pairs alone (PI1 = transform(dgmExt1)), [E][res*res] */
+  double *pi_up, *pi_one;
 } tlc_detail;
 int tlc_vicinity_detail(tlc_graph *g, const int32_t *targets, int64_t E, const tlc_params *p, tlc_detail *out);
 
@@ -149,6 +152,14 @@ int tlc_union_find(int device, int32_t n, int32_t m, const double *fval, const i
 /* PersistenceImager(resolution).transform(dgm, skew=True) (PersistenceImager.pyx:352-388): host
  * dgm[K][2] (birth, death) float64 -> out[res*res] float64, runs kernel 4 on `device`. */
 int tlc_pimg_transform(int device, const double *dgm, int64_t K, int32_t resolution, double *out);
+
+/* Hand-off of the cached image table to the decoder (baselines/TLCGNN.py:35-53): the table float64[rows][r2]
+ * (the .npy cache layout, loaddatas.py:62-64,102) stays resident in HBM; out[i][:] = (float) table[row(i)][:],
+ * row(i) = dev_index ? dev_index[i] : start + i -- what `torch.Tensor(PI[...]).cuda()` yields per decode call
+ * on the host.  All pointers are DEVICE pointers on `device`; `stream` is a cudaStream_t (NULL: default
+ * stream).  An index outside [0, rows) (numpy: IndexError) -> TLC_E_INVALID, the row is zero-filled. */
+int tlc_pi_gather(int device, const double *dev_table, int64_t rows, int32_t r2, const int64_t *dev_index,
+                  int64_t start, int64_t n, float *dev_out_f32, void *stream);
 
 /* run this graph's kernels on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
  * graph's own stream).  Lets a host framework order the work with its own (e.g. NCCL) operations. */

@@ -76,8 +76,12 @@ def make_case(tag, edges, kappa, targets, hop, descriptor="sum", stage_targets=N
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--kd-only" in sys.argv:
+        kd_cases()
+        return
     if "--pimg-only" not in sys.argv:
         graph_cases()
+        kd_cases()
     pimg_cases()
 
 
@@ -109,6 +113,48 @@ def graph_cases():
     idx = np.random.default_rng(14).choice(len(c["edges"]), 30, replace=False)
     make_case("pubmed_s_min", c["edges"], c["kappa"], c["edges"][idx], 2, descriptor="min")
     make_case("pubmed_s_max", c["edges"], c["kappa"], c["edges"][idx], 2, descriptor="max")
+
+
+def make_kd_case(tag, edges, kappa, nodes, hop):
+    """PDGNN generator fixture: the UNMODIFIED Knowledge_Distillation/data_utils_NC.py
+    compute_persistence_image(g, u, filt='ricci', hop, ricci_curv, mode='PI') (:95-183) per node -> the 9-tuple
+    (Ord0, Ext1, PI, filtration_val, edge_index, PI0, PI1, ...) in the reference's own (implementation-defined)
+    vertex order, with the new-label -> graph-node map so that tests can canonicalise."""
+    edges = np.asarray(edges, dtype=np.int64)
+    g = rh.build_nx_graph(edges)
+    ricci = rh.ricci_list(edges, [float(k) for k in kappa])
+    out = dict(edges=edges, kappa=np.asarray(kappa, dtype=np.float64), nodes=np.asarray(nodes, dtype=np.int64),
+               hop=np.int64(hop))
+    none, old, filt, ord0, ext1, ei, pi, pi0, pi1 = [], [], [], [], [], [], [], [], []
+    for u in nodes:
+        r = rh.kd_run_node(g, ricci, int(u), hop)
+        none.append(r is None)
+        if r is None:
+            r = dict(old_label=[], filt=[], ord0=[], ext1=[], edge_index=[], pi=np.zeros(25), pi0=np.zeros(25), pi1=np.zeros(25))
+        old.append(r["old_label"]); filt.append(r["filt"]); ord0.append(r["ord0"]); ext1.append(r["ext1"])
+        ei.append(np.asarray(r["edge_index"]).T if len(r["edge_index"]) else [])
+        pi.append(r["pi"]); pi0.append(r["pi0"]); pi1.append(r["pi1"])
+    out["none"] = np.asarray(none)
+    for name, lst, dt in (("old_label", old, np.int64), ("filt", filt, np.float64), ("ord0", ord0, np.float64),
+                          ("ext1", ext1, np.float64), ("edge_index", ei, np.int64)):
+        flat, off = ragged(lst, dt)
+        out["kd_%s" % name] = flat
+        out["kd_%s_off" % name] = off
+    out["pi"], out["pi0"], out["pi1"] = np.stack(pi), np.stack(pi0), np.stack(pi1)
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **out)
+    print("wrote", tag, "nodes", len(nodes), "none", int(np.sum(none)))
+
+
+def kd_cases():
+    c = gg.make_config("ppi", scale=0.1)
+    nodes = np.unique(c["edges"])[np.random.default_rng(21).choice(len(np.unique(c["edges"])), 20, replace=False)]
+    make_kd_case("kd_ppi_s_hop1", c["edges"], c["kappa"], nodes, 1)
+    c = gg.make_config("pubmed", scale=0.05, continuous=True)
+    un = np.unique(c["edges"])
+    nodes = un[np.random.default_rng(22).choice(len(un), 24, replace=False)]
+    make_kd_case("kd_pubmed_s_hop2_cont", c["edges"], c["kappa"], nodes, 2)
+    # hop 0: the ball is the lone centre -> `return None, None` (:103-104)
+    make_kd_case("kd_pubmed_s_hop0", c["edges"], c["kappa"], nodes[:3], 0)
 
 
 def pimg_cases():

@@ -21,6 +21,8 @@ import os
 import sys
 import types
 
+import numpy as np
+
 REF_ROOT = os.environ.get("TLC_REFERENCE_ROOT", "/root/reference")
 
 
@@ -143,3 +145,78 @@ def run_one_stages(pi, u_old, v_old, hop, descriptor="sum", norm=True, canonical
     out.update(PD0=PD0, Pos=Pos, Neg=Neg)
     out["PD1"] = ref.apd.Accelerate_PD(Pos, Neg, sf) if len(Neg) else None
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# PDGNN generator: Knowledge_Distillation/data_utils_NC.py imported AS-IS.
+# Its module header imports packages that are not installed here (matplotlib, gudhi, torch_geometric)
+# and sibling modules absent from the tree (learnable_filter.loaddatas_LP, loaddatas_LP_arxiv); none of
+# them is touched by compute_persistence_image(filt='ricci', mode='PI') (data_utils_NC.py:95-183),
+# so empty stub modules satisfy the imports.  `sg2dgm.PersistenceImager` and
+# `Knowledge_Distillation.accelerated_PD` resolve to the reference's own files.
+# ----------------------------------------------------------------------------------------------
+_kd_loaded = {}
+
+
+def load_kd():
+    if _kd_loaded:
+        return _kd_loaded["nc"]
+    ref = load()
+    stubs = {}
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        stubs[name] = m
+        return m
+
+    stub("matplotlib").pyplot = stub("matplotlib.pyplot")
+    stub("gudhi")
+    tg = stub("torch_geometric")
+    tg.utils = stub("torch_geometric.utils", remove_self_loops=lambda ei, *a, **k: (ei, None))
+    lf = stub("learnable_filter")
+    lf.loaddatas_LP = stub("learnable_filter.loaddatas_LP")
+    stub("loaddatas_LP_arxiv", get_edges_split=None)
+    kd_pkg = stub("Knowledge_Distillation")
+    kd_pkg.__path__ = [os.path.join(REF_ROOT, "Knowledge_Distillation")]
+    kd_pkg.accelerated_PD = ref.kd_apd
+    stubs["Knowledge_Distillation.accelerated_PD"] = ref.kd_apd
+    sg = stub("sg2dgm")
+    sg.__path__ = [os.path.join(REF_ROOT, "sg2dgm")]
+    sg.PersistenceImager = ref.pimg
+    stubs["sg2dgm.PersistenceImager"] = ref.pimg
+    saved = {k: sys.modules.get(k) for k in stubs}
+    saved.update({k: sys.modules[k] for k in list(sys.modules) if k.startswith("sg2dgm.")})
+    for k in [k for k in list(sys.modules) if k == "sg2dgm" or k.startswith("sg2dgm.")]:
+        del sys.modules[k]
+    sys.modules.update(stubs)
+    try:
+        nc = _load_source("_ref_kd_data_utils_NC", os.path.join(REF_ROOT, "Knowledge_Distillation", "data_utils_NC.py"))
+    finally:
+        for k in stubs:
+            sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    _kd_loaded["nc"] = nc
+    return nc
+
+
+def kd_run_node(g, ricci, u, hop):
+    """data_utils_NC.compute_persistence_image(g, u, filt='ricci', hop, ricci_curv, mode='PI') unmodified
+    (:95-183).  Returns None for the `return None, None` case (:103-104), else a dict with the 9-tuple's
+    fields plus `old_label` (new label -> graph node, recovered by repeating the function's own first three
+    statements, which are deterministic) so that per-vertex outputs can be put in canonical order."""
+    import networkx as nx
+    nc = load_kd()
+    r = nc.compute_persistence_image(g, u, filt="ricci", hop=hop, ricci_curv=ricci, mode="PI")
+    if r[0] is None:
+        return None
+    nodes = [u] + [x for _, x in nx.bfs_edges(g, u, depth_limit=hop)]       # :97
+    sub = nx.convert_node_labels_to_integers(g.subgraph(nodes), label_attribute="old_label")  # :98-99
+    old = [sub.nodes[i]["old_label"] for i in range(len(sub))]
+    ord0, ext1, pi, filt, edge_index, pi0, pi1, _, _ = r
+    return dict(ord0=np.asarray(ord0, dtype=np.float64).reshape(-1, 2), ext1=np.asarray(ext1, dtype=np.float64).reshape(-1, 2),
+                pi=np.asarray(pi, dtype=np.float64), pi0=np.asarray(pi0, dtype=np.float64), pi1=np.asarray(pi1, dtype=np.float64),
+                filt=np.asarray(filt, dtype=np.float64), edge_index=np.asarray(edge_index.numpy(), dtype=np.int64),
+                old_label=np.asarray(old, dtype=np.int64))

@@ -32,3 +32,45 @@ def rel_err(a, ref):
     a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
     den = np.where(ref != 0, np.abs(ref), 1.0)
     return float(np.max(np.abs(a - ref) / den)) if a.size else 0.0
+
+
+KD_CASES = ["kd_ppi_s_hop1", "kd_pubmed_s_hop2_cont", "kd_pubmed_s_hop0"]
+
+
+def load_kd_case(tag):
+    """PDGNN generator fixture (oracle/make_golden.py: make_kd_case): per node the unmodified reference's 9-tuple."""
+    z = np.load(os.path.join(GOLDEN, tag + ".npz"))
+    c = {k: z[k] for k in z.files}
+    c["hop"] = int(c["hop"])
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    c["csr"] = gg.build_csr(len(labels), ne, c["kappa"])
+    c["lut"] = {int(l): i for i, l in enumerate(labels)}
+    c["new_nodes"] = np.array([c["lut"][int(u)] for u in c["nodes"]], dtype=np.int32)
+    return c
+
+
+def kd_seg(c, name, k):
+    off = c["kd_%s_off" % name]
+    w = 2 if name in ("ord0", "ext1", "edge_index") else 1  # offsets count rows; these are [rows, 2] flattened
+    return c["kd_%s" % name][w * off[k]:w * off[k + 1]]
+
+
+def sorted_rows(a):
+    a = np.asarray(a, dtype=np.float64).reshape(-1, 2)
+    return a[np.lexsort((a[:, 1], a[:, 0]))]
+
+
+def kd_expected(c, k):
+    """node k of a KD fixture in canonical form: graph ids (first-appearance numbering) ascending, the filtration
+    values in that order, the induced edge set as sorted (lo, hi) graph-id pairs, Ord0 / Ext1 as sorted multisets
+    (the reference's own vertex / pair order is implementation-defined)."""
+    old = kd_seg(c, "old_label", k)
+    newid = np.array([c["lut"][int(x)] for x in old], dtype=np.int64)
+    order = np.argsort(newid)
+    ei = kd_seg(c, "edge_index", k).reshape(-1, 2)
+    eg = newid[ei] if len(ei) else np.zeros((0, 2), np.int64)
+    eg = np.stack([eg.min(1), eg.max(1)], 1) if len(eg) else eg
+    eg = eg[np.lexsort((eg[:, 1], eg[:, 0]))] if len(eg) else eg
+    return dict(vert=newid[order], filt=kd_seg(c, "filt", k)[order], edges=eg,
+                ord0=sorted_rows(kd_seg(c, "ord0", k)), ext1=sorted_rows(kd_seg(c, "ext1", k)),
+                pi=c["pi"][k], pi0=c["pi0"][k], pi1=c["pi1"][k], none=bool(c["none"][k]))

@@ -73,3 +73,11 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, "SO_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError):
         L.lib()
+
+
+def test_cache_filename_mapping():
+    """loaddatas.py:57-62: photo -> Photo, computers -> Computers, others unchanged."""
+    from tlc_b200.table import cache_filename
+    assert cache_filename("photo") == "./data/TLCGNN/Photo.npy"
+    assert cache_filename("computers") == "./data/TLCGNN/Computers.npy"
+    assert cache_filename("PubMed", "/x") == "/x/PubMed.npy"

@@ -74,3 +74,38 @@ def test_union_find_and_imager_mirrors():
         assert np.array_equal(np.array(PD1).reshape(-1, 2), seg(c, "pd1", k).reshape(-1, 2))
         img = pimg.PersistenceImager(resolution=5).transform(np.array(PD + PD1))
         assert img.shape == (5, 5)
+
+
+# ---- PDGNN generator mirror (sg2dgm/kd.py) vs the UNMODIFIED data_utils_NC.compute_persistence_image outputs ----
+@pytest.mark.parametrize("tag", __import__("helpers").KD_CASES)
+def test_kd_generator_tuple_matches_reference(tag):
+    from helpers import kd_expected, load_kd_case, sorted_rows
+    import sg2dgm.kd as kd
+    c = load_kd_case(tag)
+    pi = build(c)
+    res = kd.compute_persistence_images(pi, [int(u) for u in c["nodes"]], hop=c["hop"])
+    assert len(res) == len(c["nodes"])
+    for k, r in enumerate(res):
+        e = kd_expected(c, k)
+        if e["none"]:
+            assert len(r) == 2 and r[0] is None and r[1] is None          # data_utils_NC.py:103-104
+            continue
+        assert len(r) == 9
+        ord0, ext1, img, filt, edge_index, pi0, pi1, _, _ = r
+        newid = np.array([c["lut"][int(x)] for x in r.old_label])        # graph ids in first-appearance numbering
+        assert np.array_equal(newid, e["vert"])                           # canonical local order
+        assert np.array_equal(np.asarray(filt), e["filt"])                # bit-exact float64
+        eg = newid[np.asarray(edge_index)].T
+        assert np.array_equal(eg, e["edges"])                             # induced edge set, lexicographic
+        assert ord0.shape == (len(e["vert"]) - 1, 2) and ext1.shape == (len(e["edges"]) - len(e["vert"]) + 1, 2)
+        assert np.array_equal(sorted_rows(ord0), e["ord0"])               # bit-exact multisets
+        assert np.array_equal(sorted_rows(ext1), e["ext1"])
+        assert rel_err(img, e["pi"]) < 1e-5 and rel_err(pi0, e["pi0"]) < 1e-5 and rel_err(pi1, e["pi1"]) < 1e-5
+    # per-node signature of the reference (data_utils_NC.py:95)
+    u0 = int(c["nodes"][0])
+    one = kd.compute_persistence_image(pi, u0, filt="ricci", hop=c["hop"], mode="PI")
+    if res[0][0] is None:
+        assert one[0] is None and one[1] is None
+    else:
+        # (the image sums its points in CTA-size dependent order: last-bit differences between differently sized calls)
+        assert np.array_equal(one[0], res[0][0]) and rel_err(one[2], res[0][2]) < 1e-12

@@ -61,3 +61,34 @@ def test_stages_match_canonical_reference():
         assert np.stack([vert[o["elo"]][o["neg"]], vert[o["ehi"]][o["neg"]]], 1).tolist() == [list(e) for e in st["Neg"]]
         checked += 1
     assert checked >= 3
+
+
+def test_kd_generator_asis_vs_oracle():
+    """Knowledge_Distillation/data_utils_NC.compute_persistence_image (filt='ricci', mode='PI')
+    imported AS-IS (oracle/ref_harness.load_kd) on a fresh PPI-shaped graph vs the oracle's node mode + KD flags."""
+    from helpers import sorted_rows
+    c = gg.make_config("ppi", scale=0.06, continuous=True)
+    edges, kappa = c["edges"], c["kappa"]
+    g = rh.build_nx_graph(edges)
+    ricci = rh.ricci_list(edges, [float(k) for k in kappa])
+    labels, ne = gg.relabel_first_appearance(edges)
+    csr = gg.build_csr(len(labels), ne, kappa)
+    og = orc.OracleGraph(*csr)
+    lut = {int(l): i for i, l in enumerate(labels)}
+    fl = orc.F_NORM | orc.F_EXTENDED | orc.F_KEEP_ZERO | orc.F_NORM_EPS
+    rng = np.random.default_rng(5)
+    for u_old in rng.choice(labels, 6, replace=False):
+        for hop in (1, 2):
+            r = rh.kd_run_node(g, ricci, int(u_old), hop)
+            o = og.run_one(lut[int(u_old)], lut[int(u_old)], hop=hop, mode=orc.MODE_NODE, flags=fl)
+            if r is None:
+                assert o["status"] == 2
+                continue
+            newid = np.array([lut[int(x)] for x in r["old_label"]])
+            order = np.argsort(newid)
+            assert np.array_equal(newid[order], o["vert"])
+            assert np.array_equal(r["filt"][order], o["fval"])
+            up, one = o["pkind"] == 0, o["pkind"] == 4
+            assert np.array_equal(sorted_rows(r["ord0"]), sorted_rows(np.stack([o["pbirth"][up], o["pdeath"][up]], 1)))
+            assert np.array_equal(sorted_rows(r["ext1"]), sorted_rows(np.stack([o["pbirth"][one], o["pdeath"][one]], 1)))
+            assert rel_err(r["pi"], o["img"]) < 1e-10

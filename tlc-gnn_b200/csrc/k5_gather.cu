@@ -1,0 +1,48 @@
+// k5_gather.cu -- kernel 5: hand-off of the cached persistence-image table to the link-prediction decoder.
+//
+// The reference keeps pi_sg as a host float64[E, res^2] array and, on EVERY decode call, fancy-indexes the
+// step's rows on the host, converts them to float32 and uploads them (baselines/TLCGNN.py:35-53:
+// `PI = np.concatenate((self.PI[:train_pos], self.PI[train_pos:train_pos+train_neg][index]))`,
+// `new_x = torch.Tensor(PI.reshape(len(total_edges), -1)).cuda()`).  Here the table stays resident in HBM
+// (float64, the .npy cache layout of loaddatas.py:62-64,102) and the step's rows are gathered and rounded to
+// float32 on the device: out[i, :] = (float) table[row(i), :], row(i) = index ? index[i] : start + i.
+//
+// HBM-bound: 8 B read + 4 B written per element, 8 B per index.  One thread per output element, consecutive
+// threads walk consecutive elements of a row (coalesced reads within a row, fully coalesced writes).
+#include <algorithm>
+
+#include "tlc_common.cuh"
+
+namespace tlc {
+namespace {
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restrict__ table, int64_t rows, int r2,
+                                                          const int64_t* __restrict__ index, int64_t start, int64_t n,
+                                                          float* __restrict__ out, int* __restrict__ bad) {
+  const int64_t total = n * r2;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / r2;
+    const int j = (int)(e - i * r2);
+    const int64_t r = index ? index[i] : start + i;
+    if (r < 0 || r >= rows) {  // numpy raises IndexError: reported to the host, the row is zero-filled
+      if (j == 0) atomicExch(bad, 1);
+      out[e] = 0.f;
+      continue;
+    }
+    out[e] = (float)table[r * r2 + j];  // torch.Tensor(float64 ndarray): round to nearest float32
+  }
+}
+
+}  // namespace
+
+void launch_gather_rows(const double* table, int64_t rows, int r2, const int64_t* index, int64_t start, int64_t n,
+                        float* out, int* bad, int sm_count, cudaStream_t st) {
+  const int64_t total = n * r2;
+  if (total <= 0) return;
+  const int64_t want = (total + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count * 16);  // a multiple of the SM count, grid-stride
+  gather_rows_kernel<<<grid, 256, 0, st>>>(table, rows, r2, index, start, n, out, bad);
+  count_launch();
+}
+
+}  // namespace tlc

@@ -65,6 +65,7 @@ struct tlc_graph {
   int32_t *ball_state = nullptr, *ball_list = nullptr;
   int vic_grid = 0, vic_hop = -1;
   int* work_counter = nullptr;
+  ChunkView detail_chunk{};  // the chunk of the last tlc_vicinity_detail call (still carved in the arena)
   float* gminw = nullptr;  // [N] smallest kappa + 1 of each node's row, rounded down (graph-row route's settling margin)
   int64_t last_direct = 0;  // targets of the last call that took the graph-row route
   // per-call device buffers
@@ -543,6 +544,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     if (detail) {
       // copy every intermediate back (input order == chunk order here)
       CK(cudaStreamSynchronize(st));
+      g->detail_chunk = c;
 #define D2H(dst, src, count, type) \
   if (detail->dst) CK(cudaMemcpy(detail->dst, src, (size_t)(count) * sizeof(type), cudaMemcpyDeviceToHost))
       D2H(n, c.tn, T, int32_t); D2H(m, c.tm, T, int32_t); D2H(lu, c.tlu, T, int32_t); D2H(lv, c.tlv, T, int32_t);
@@ -747,9 +749,21 @@ int tlc_vicinity_detail(tlc_graph* g, const int32_t* targets, int64_t E, const t
   CK(cudaMalloc((void**)&d_st, (size_t)E));
   CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
   int64_t cnt = 0;
+  g->detail_chunk.T = 0;
   rc = run_pipeline(g, d_t, E, p, d_pi, nullptr, d_st, &cnt, out);
   if (rc == TLC_OK && out->pi) {
     if (cudaMemcpy(out->pi, d_pi, (size_t)E * r2 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(TLC_E_CUDA, "copy back failed");
+  }
+  // the two single-kind images of the PDGNN generators: kernel 4 again over the chunk the call left in the arena
+  for (int which = 0; which < 2 && rc == TLC_OK; which++) {
+    double* dst = which == 0 ? out->pi_up : out->pi_one;
+    if (!dst) continue;
+    Params pp{p->hop, p->mode, p->descriptor, p->resolution, p->flags, 1u << (which == 0 ? TLC_K_UP : TLC_K_ONE)};
+    if (cudaMemsetAsync(d_pi, 0, (size_t)E * r2 * 8, g->stream) != cudaSuccess) { rc = fail(TLC_E_CUDA, "memset failed"); break; }
+    if (g->detail_chunk.T == E) launch_pimg(pp, g->detail_chunk, d_pi, nullptr, nullptr, 64, g->stream);
+    if (cudaMemcpyAsync(dst, d_pi, (size_t)E * r2 * 8, cudaMemcpyDeviceToHost, g->stream) != cudaSuccess ||
+        cudaStreamSynchronize(g->stream) != cudaSuccess)
+      rc = fail(TLC_E_CUDA, "copy back failed");
   }
   cudaFree(d_t); cudaFree(d_pi); cudaFree(d_st);
   return rc;
@@ -839,6 +853,34 @@ int tlc_pimg_transform(int device, const double* dgm, int64_t K, int32_t resolut
   CK(cudaMemcpy(out, d_out, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost));
   CK(cudaGetLastError());
   cudaFree(d_dgm); cudaFree(d_out);
+  return TLC_OK;
+}
+
+int tlc_pi_gather(int device, const double* dev_table, int64_t rows, int32_t r2, const int64_t* dev_index, int64_t start,
+                  int64_t n, float* dev_out_f32, void* stream) {
+  if (rows < 0 || r2 < 1 || n < 0 || (n > 0 && (!dev_table || !dev_out_f32))) return fail(TLC_E_INVALID, "bad arguments");
+  if (n == 0) return TLC_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(TLC_E_INVALID, "device index out of range");
+  CK(cudaSetDevice(device));
+  static thread_local int* d_bad[64] = {nullptr};
+  static thread_local int sms[64] = {0};
+  if (device >= 64) return fail(TLC_E_INVALID, "device index out of range");
+  if (!d_bad[device]) {
+    CK(cudaMalloc((void**)&d_bad[device], sizeof(int)));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    sms[device] = prop.multiProcessorCount;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(d_bad[device], 0, sizeof(int), st));
+  launch_gather_rows(dev_table, rows, r2, dev_index, start, n, dev_out_f32, d_bad[device], sms[device], st);
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, d_bad[device], sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (bad) return fail(TLC_E_INVALID, "row index out of range");
   return TLC_OK;
 }
 

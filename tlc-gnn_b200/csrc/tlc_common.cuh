@@ -187,6 +187,9 @@ void launch_pimg(const Params& p, const ChunkView& c, double* out_pi, float* out
                  int block, cudaStream_t st);
 void launch_pimg_single(const double* dgm, int64_t K, int res, double* out, cudaStream_t st);
 
+void launch_gather_rows(const double* table, int64_t rows, int r2, const int64_t* index, int64_t start, int64_t n,
+                        float* out, int* bad, int sm_count, cudaStream_t st);
+
 int64_t launch_count();
 void count_launch();
 int vicinity_grid(int device, const GraphView& g, const Params& p, size_t* bitmap_words, bool* use_smem);

@@ -1,0 +1,67 @@
+"""Mirror of the PDGNN training-set generator's per-node call,
+Knowledge_Distillation/data_utils_NC.py:95-183 `compute_persistence_image(g, u, filt='ricci', hop, ricci_curv,
+mode='PI')`, and a batched form of it.
+
+Per node the reference returns the 9-tuple
+    (dgmOrd0 [n-1,2], dgmExt1 [m-n+1,2], PI [25], filtration_val [n], edge_index [2,m], PI0 [25], PI1 [25],
+     PD_time, PI_time)                                                                        (:183)
+or `(None, None)` when the ball has no edge (:103-104).  Here all nodes of a call go through ONE C-ABI call
+(`tlc_vicinity_detail`, node mode, KD flags: zero-persistence pairs kept, division by max + 1e-10, images of
+Ord0 u Ext1 / Ord0 / Ext1); only the filt='ricci' filtration is on the hot path (the other `filt` choices of :115-128 are
+SURVEY.md row N3).
+
+Order conventions: the reference's local vertex numbering and pair order follow networkx's sub-graph view iteration
+(implementation-defined).  This mirror uses the canonical order: local ids ascending by graph id,
+`edge_index` lexicographic (lo, hi), Ord0 / Ext1 in sweep order under that tie-break.  `old_label` gives the graph id
+of every local vertex.
+"""
+import time
+
+import numpy as np
+
+from tlc_b200 import _lib as L
+
+KD_FLAGS = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
+
+
+def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False):
+    """batched: `g2pi` is a sg2dgm.riccidist2dgm.graph2pi (graph + curvature resident on the GPU), `nodes` are ORIGINAL
+    node labels.  Returns a list with one entry per node: the reference's 9-tuple, or (None, None)."""
+    tg = g2pi._map_targets([(u, u) for u in nodes])
+    G = g2pi._graph
+    t0 = time.time()
+    d = G.vicinity_detail(tg, hop=hop, mode=L.MODE_NODE, descriptor="sum", resolution=resolution, flags=KD_FLAGS)
+    dt = (time.time() - t0) / max(1, len(nodes))
+    out = []
+    for i in range(len(nodes)):
+        a = G.per_target(d, i)
+        if a["status"] != L.ST_OK:           # lone centre / unknown node: `return None, None`   :103-104
+            out.append((None, None))
+            continue
+        pk = a["pkind"]
+        pairs = np.stack([a["pbirth"], a["pdeath"]], 1)
+        ord0, ext1 = pairs[pk == L.K_UP], pairs[pk == L.K_ONE]
+        edge_index = np.stack([a["elo"], a["ehi"]], 0).astype(np.int64)
+        if as_torch:
+            import torch
+            edge_index = torch.from_numpy(edge_index)                                           # :109
+        old = a["vert"] if g2pi.old_label is None else [g2pi.old_label[int(x)] for x in a["vert"]]
+        tup = (ord0, ext1, a["img"].copy(), list(a["fval"]), edge_index, a["img_up"].copy(), a["img_one"].copy(), dt, 0.0)
+        out.append(_KDTuple(tup, old))
+    return out
+
+
+class _KDTuple(tuple):
+    """the reference's 9-tuple, plus `.old_label` (graph label of every local vertex)."""
+
+    def __new__(cls, items, old_label):
+        self = super().__new__(cls, items)
+        self.old_label = old_label
+        return self
+
+
+def compute_persistence_image(g2pi, u, filt="ricci", hks_time=0.1, hop=2, ricci_curv=None, mode="PI", **_unused):
+    """per-node signature of data_utils_NC.py:95 (first argument: the graph2pi object that holds graph and curvature)."""
+    if filt != "ricci" or mode != "PI":
+        raise NotImplementedError("only filt='ricci', mode='PI' is on the GPU path (SURVEY.md rows A9 / N3)")
+    return compute_persistence_images(g2pi, [u], hop=hop)[0]

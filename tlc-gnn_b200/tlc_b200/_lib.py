@@ -21,7 +21,7 @@ ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NOD
 EXPORTS = ["tlc_graph_create", "tlc_graph_destroy", "tlc_vicinity_pi", "tlc_vicinity_pi_dev", "tlc_vicinity_sizes",
            "tlc_vicinity_detail", "tlc_union_find", "tlc_pimg_transform", "tlc_last_error", "tlc_version",
            "tlc_launch_count", "tlc_last_stage_ms", "tlc_last_algorithmic_bytes", "tlc_graph_set_stream",
-           "tlc_last_counts", "tlc_last_direct"]
+           "tlc_last_counts", "tlc_last_direct", "tlc_pi_gather"]
 
 
 class Params(C.Structure):
@@ -40,7 +40,7 @@ class Detail(C.Structure):
                 ("pkind", C.c_void_p), ("pbv", C.c_void_p), ("pdv", C.c_void_p),
                 ("pbirth", C.c_void_p), ("pdeath", C.c_void_p),
                 ("pos", C.c_void_p), ("neg", C.c_void_p),
-                ("pi", C.c_void_p), ("status", C.c_void_p)]
+                ("pi", C.c_void_p), ("status", C.c_void_p), ("pi_up", C.c_void_p), ("pi_one", C.c_void_p)]
 
 
 class TlcError(RuntimeError):
@@ -88,6 +88,8 @@ def lib():
     L.tlc_graph_set_stream.argtypes = [vp, vp]
     L.tlc_last_counts.restype = C.c_int
     L.tlc_last_counts.argtypes = [vp, vp]
+    L.tlc_pi_gather.restype = C.c_int
+    L.tlc_pi_gather.argtypes = [C.c_int, vp, i64, i32, vp, i64, i64, vp, vp]
     L.tlc_last_direct.restype = i64
     L.tlc_last_direct.argtypes = [vp]
     _lib = L

@@ -107,7 +107,8 @@ class VicinityGraph:
                  pkind=np.zeros(Np + 1, np.int32), pbv=np.zeros(Np + 1, np.int32), pdv=np.zeros(Np + 1, np.int32),
                  pbirth=np.zeros(Np + 1), pdeath=np.zeros(Np + 1),
                  pos=np.zeros(Ne + 1, np.int32), neg=np.zeros(Nv + 1, np.int32),
-                 pi=np.zeros((E, resolution * resolution)), status=np.zeros(E, np.uint8))
+                 pi=np.zeros((E, resolution * resolution)), status=np.zeros(E, np.uint8),
+                 pi_up=np.zeros((E, resolution * resolution)), pi_one=np.zeros((E, resolution * resolution)))
         d = L.Detail()
         d.cap_v, d.cap_e, d.cap_p = Nv, Ne, Np
         for k, arr in a.items():
@@ -122,7 +123,7 @@ class VicinityGraph:
         po = a["poff"][i]
         np_ = a["npairs"][i]
         out = dict(status=int(a["status"][i]), n=int(a["n"][i]), m=int(a["m"][i]), lu=int(a["lu"][i]), lv=int(a["lv"][i]),
-                   img=a["pi"][i])
+                   img=a["pi"][i], img_up=a["pi_up"][i], img_one=a["pi_one"][i])
         for k in ("vert", "fval"):
             out[k] = a[k][vo:ve]
         for k in ("elo", "ehi", "ew", "ord_asc", "ord_desc"):
