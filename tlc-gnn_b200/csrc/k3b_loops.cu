@@ -18,10 +18,41 @@
 // with an ordered compaction.  The sweep itself is sequential by nature and runs on warp 0 with the
 // per-vertex state (parent, rank of the parent edge, visit stamp) in shared memory; the next 32
 // positive edges are gathered by the 32 lanes at once so the sequential part never waits on HBM.
+//
+// Two schedules of the sequential sweep.  Large vicinities: one CTA per vicinity, state in shared memory, lane 0 walks.
+// Small vicinities (the reference's own settings: hop 1, or sparse graphs): ONE LANE per vicinity
+// (loops_sweep_lanes_kernel), each lane's state in its own slice of shared memory -- up to several hundred independent
+// sequential sweeps in flight per SM instead of one per resident CTA (at most 32); the parallel phases before and
+// after the sweep still run a CTA per vicinity (phase mask).
 #include "tlc_common.cuh"
 
 namespace tlc {
 namespace {
+
+constexpr int PH_PREP = 1, PH_SWEEP = 2, PH_EMIT = 4;
+
+// one positive edge (p0, p1) of rank `rc`, the k-th of the sweep: returns the child end of the loop-max edge (its parent
+// end through *by) and re-hangs the tree.  tpar / tpr / stamp: parent, rank of the parent edge, visit stamp per vertex.
+template <typename PT>
+__device__ __forceinline__ int sweep_one_edge(PT* tpar, int32_t* tpr, int32_t* stamp, int k, int p0, int p1, int rc, int* by) {
+  // path_0: p0 -> root, stamped                                                      accelerated_PD.py:131-144
+  for (int x = p0;;) { stamp[x] = k; const int px = (int)tpar[x]; if (px == x) break; x = px; }
+  int lca = p1;                                                                       // :145-151
+  while (stamp[lca] != k) lca = (int)tpar[lca];
+  int best = -1, bc = -1, in0 = 0;
+  for (int x = p0; x != lca; x = (int)tpar[x]) { const int r = tpr[x]; if (r > best) { best = r; bc = x; in0 = 1; } }
+  for (int x = p1; x != lca; x = (int)tpar[x]) { const int r = tpr[x]; if (r > best) { best = r; bc = x; in0 = 0; } }
+  *by = (int)tpar[bc];                                                                // large_edge   :155-159
+  // change the parent                                                                :168-176
+  int node = in0 ? p0 : p1, nodec = in0 ? p1 : p0;
+  for (;;) {
+    const int tp = (int)tpar[node], tr = tpr[node];
+    tpar[node] = (PT)nodec; tpr[node] = rc;
+    if (node == bc) break;
+    nodec = node; rc = tr; node = tp;
+  }
+  return bc;
+}
 
 struct LoopShared {
   int32_t wcnt[33];
@@ -29,7 +60,7 @@ struct LoopShared {
   int32_t g0[32], g1[32], gr[32];
 };
 
-__global__ void loops_kernel(Params p, ChunkView c, int smem_ints) {
+__global__ void loops_kernel(Params p, ChunkView c, int smem_ints, int phases) {
   extern __shared__ int32_t dyn[];
   __shared__ LoopShared sh;
   const int t = blockIdx.x;
@@ -55,6 +86,7 @@ __global__ void loops_kernel(Params p, ChunkView c, int smem_ints) {
   uint32_t* out_x = c.sp0 + eo;  // per positive edge: child end of the loop-max edge
   uint32_t* out_y = c.sp1 + eo;  // ... and its parent end
 
+  if (phases & PH_PREP) {
   for (int k = tid; k < m; k += nt) arank[ord_asc[k]] = k;
   for (int x = tid; x < n; x += nt) { tpar[x] = -1; stamp[x] = -1; }
   __syncthreads();
@@ -78,10 +110,11 @@ __global__ void loops_kernel(Params p, ChunkView c, int smem_ints) {
     __syncthreads();
     if (!any) break;
   }
+  }  // PH_PREP
 
   // sequential sweep over the positive edges: the lanes of warp 0 gather the next 32 positive edges
   // (endpoints, rank) into shared memory, lane 0 walks the tree
-  if (wid == 0) {
+  if ((phases & PH_SWEEP) && wid == 0) {
     for (int k0 = 0; k0 < npos; k0 += 32) {
       if (k0 + lane < npos) {
         const int pe = pos[k0 + lane];
@@ -92,29 +125,16 @@ __global__ void loops_kernel(Params p, ChunkView c, int smem_ints) {
         const int cnt = min(32, npos - k0);
         for (int j = 0; j < cnt; j++) {
           const int k = k0 + j;
-          const int p0 = sh.g0[j], p1 = sh.g1[j];
-          // path_0: p0 -> root, stamped                                            :131-144
-          for (int x = p0;;) { stamp[x] = k; const int px = tpar[x]; if (px == x) break; x = px; }
-          int lca = p1;                                                             // :145-151
-          while (stamp[lca] != k) lca = tpar[lca];
-          int best = -1, bc = -1, in0 = 0;
-          for (int x = p0; x != lca; x = tpar[x]) { const int r = tpr[x]; if (r > best) { best = r; bc = x; in0 = 1; } }
-          for (int x = p1; x != lca; x = tpar[x]) { const int r = tpr[x]; if (r > best) { best = r; bc = x; in0 = 0; } }
-          out_x[k] = (uint32_t)bc; out_y[k] = (uint32_t)tpar[bc];                   // large_edge   :155-159
-          // change the parent                                                      :168-176
-          int node = in0 ? p0 : p1, nodec = in0 ? p1 : p0, rc = sh.gr[j];
-          for (;;) {
-            const int tp = tpar[node], tr = tpr[node];
-            tpar[node] = nodec; tpr[node] = rc;
-            if (node == bc) break;
-            nodec = node; rc = tr; node = tp;
-          }
+          int y = 0;
+          const int x = sweep_one_edge<int32_t>(tpar, tpr, stamp, k, sh.g0[j], sh.g1[j], sh.gr[j], &y);
+          out_x[k] = (uint32_t)x; out_y[k] = (uint32_t)y;
         }
       }
       __syncwarp();
     }
   }
   __syncthreads();
+  if (!(phases & PH_EMIT)) return;
 
   // pairs [low_value, large_value] in positive-edge order, ordered compaction          :160-165
   const bool keep0 = (p.flags & TLC_F_KEEP_ZERO) != 0;
@@ -151,13 +171,66 @@ __global__ void loops_kernel(Params p, ChunkView c, int smem_ints) {
   if (tid == 0) c.tnp[t] = cursor;
 }
 
+// the sequential sweep of SMALL vicinities: one lane per vicinity, state in the lane's slice of shared memory
+// (parent u16, rank of the parent edge, stamp: 10 bytes per vertex, `cap` vertices per lane)
+__global__ void __launch_bounds__(128) loops_sweep_lanes_kernel(ChunkView c, int cap) {
+  extern __shared__ int32_t dyn[];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c.T) return;
+  const int n = c.tn[t];
+  if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
+  const int npos = c.tnpos[t];
+  if (c.tnneg[t] == 0) return;  // (status 7 set by the preparation phase)
+  const int64_t vo = c.voff[t], eo = c.eoff[t];
+  const int32_t* __restrict__ elo = c.elo + eo;
+  const int32_t* __restrict__ ehi = c.ehi + eo;
+  const int32_t* __restrict__ pos = c.pos + eo;
+  const int32_t* __restrict__ arank = c.arank + eo;
+  int32_t* tpr = dyn + (size_t)threadIdx.x * cap;
+  int32_t* stamp = dyn + (size_t)blockDim.x * cap + (size_t)threadIdx.x * cap;
+  uint16_t* tpar = reinterpret_cast<uint16_t*>(dyn + (size_t)2 * blockDim.x * cap) + (size_t)threadIdx.x * cap;
+  {  // the rooted tree of the preparation phase
+    const int32_t* gpar = c.vs0 + vo;
+    const int32_t* gpr = c.vs1 + vo;
+    for (int x = 0; x < n; x++) { tpar[x] = (uint16_t)gpar[x]; tpr[x] = gpr[x]; stamp[x] = -1; }
+  }
+  uint32_t* out_x = c.sp0 + eo;
+  uint32_t* out_y = c.sp1 + eo;
+  // the next positive edge is fetched while the current one walks the tree
+  int pe = npos > 0 ? pos[0] : 0;
+  int p0 = npos > 0 ? elo[pe] : 0, p1 = npos > 0 ? ehi[pe] : 0, rc = npos > 0 ? arank[pe] : 0;
+  for (int k = 0; k < npos; k++) {
+    int q0 = 0, q1 = 0, qr = 0;
+    if (k + 1 < npos) { const int pn = pos[k + 1]; q0 = elo[pn]; q1 = ehi[pn]; qr = arank[pn]; }
+    int y = 0;
+    const int x = sweep_one_edge<uint16_t>(tpar, tpr, stamp, k, p0, p1, rc, &y);
+    out_x[k] = (uint32_t)x; out_y[k] = (uint32_t)y;
+    p0 = q0; p1 = q1; rc = qr;
+  }
+}
+
 }  // namespace
 
-void launch_loops(const Params& p, const ChunkView& c, int block, int smem_ints, cudaStream_t st) {
+void launch_loops(const Params& p, const ChunkView& c, int block, int smem_ints, int64_t n_max, cudaStream_t st) {
+  // small vicinities (and enough of them to matter): CTA-parallel preparation, lane-per-vicinity sweep, CTA-parallel emit
+  const int cap = (int)((n_max + 1) / 2 * 2);                        // (even: keeps the u16 slices 4-byte aligned)
+  int lanes = cap > 0 ? (int)((size_t)200 * 1024 / ((size_t)cap * 10)) / 32 * 32 : 0;
+  if (lanes > 128) lanes = 128;
+  if (lanes >= 64 && c.T >= 2048) {
+    const size_t bytes = (size_t)lanes * cap * 10;
+    loops_kernel<<<c.T, block, 0, st>>>(p, c, 0, PH_PREP);
+    count_launch();
+    cudaFuncSetAttribute((const void*)loops_sweep_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    loops_sweep_lanes_kernel<<<(c.T + lanes - 1) / lanes, lanes, bytes, st>>>(c, cap);
+    count_launch();
+    loops_kernel<<<c.T, block, 0, st>>>(p, c, 0, PH_EMIT);
+    count_launch();
+    return;
+  }
   const size_t bytes = (size_t)smem_ints * 4;
   if (bytes > 48 * 1024)
     cudaFuncSetAttribute((const void*)loops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  loops_kernel<<<c.T, block, bytes, st>>>(p, c, smem_ints);
+  loops_kernel<<<c.T, block, bytes, st>>>(p, c, smem_ints, PH_PREP | PH_SWEEP | PH_EMIT);
   count_launch();
 }
 

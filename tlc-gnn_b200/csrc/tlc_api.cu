@@ -335,7 +335,7 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   tm.mark(7);
   if (ext) {
     const int64_t lp_ints = 3 * n_max * 4 <= 200 * 1024 ? 3 * n_max : 0;
-    launch_loops(p, c, std::min(block, 128), (int)lp_ints, st);
+    launch_loops(p, c, std::min(block, 128), (int)lp_ints, n_max, st);
   }
   tm.mark(8);
   launch_pimg(p, c, d_pi, d_pi32, d_status, std::max(32, std::min(block, 256)), st);
@@ -809,7 +809,7 @@ int tlc_union_find(int device, int32_t n, int32_t m, const double* fval, const i
   launch_union_find(p, c, block, (int)uf_ints, 1, 3, 0, st);
   if (flags & TLC_F_EXTENDED) {
     const int64_t lp_ints = 3 * (int64_t)n * 4 <= 200 * 1024 ? 3 * (int64_t)n : 0;
-    launch_loops(p, c, std::min(block, 128), (int)lp_ints, st);
+    launch_loops(p, c, std::min(block, 128), (int)lp_ints, n, st);
   }
   CK(cudaDeviceSynchronize());
   CK(cudaGetLastError());

@@ -182,7 +182,7 @@ void launch_union_find(const Params& p, const ChunkView& c, int block, int smem_
                        int fb_only, cudaStream_t st);
 void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
 void launch_sweep(const Params& p, const ChunkView& c, int t0, int cnt, int64_t n_max, cudaStream_t st);
-void launch_loops(const Params& p, const ChunkView& c, int block, int smem_ints, cudaStream_t st);
+void launch_loops(const Params& p, const ChunkView& c, int block, int smem_ints, int64_t n_max, cudaStream_t st);
 void launch_pimg(const Params& p, const ChunkView& c, double* out_pi, float* out_pi_f32, uint8_t* out_status,
                  int block, cudaStream_t st);
 void launch_pimg_single(const double* dgm, int64_t K, int res, double* out, cudaStream_t st);

@@ -63,46 +63,60 @@ class ShardedVicinity:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    def _plan(self, t):
+        """shards + the inverse permutation of the gathered layout: row e of the caller's list sits at
+        inv[e] = rank * L + slot of the [world * L] gathered table (rank = j % world, slot = j // world for order[j] = e)."""
+        import torch
+        order, L = plan_shards(t, self.rowptr, self.world)
+        j = np.arange(len(order), dtype=np.int64)
+        inv = np.empty(len(order), dtype=np.int64)
+        inv[order] = (j % self.world) * L + j // self.world
+        mine = shard_of(order, self.rank, self.world)
+        return dict(E=t.shape[0], order=order, L=L, k=len(mine), mine=mine,
+                    inv=torch.from_numpy(inv).to(self.device))
+
     def prepare(self, targets):
-        """plan the shards of a target list and make this rank's shard resident on the device."""
+        """plan the shards of a target list and make this rank's shard (and the un-permute index) resident on the device."""
         import torch
         t = np.ascontiguousarray(targets, dtype=np.int32).reshape(-1, 2)
-        order, L = plan_shards(t, self.rowptr, self.world)
-        mine = shard_of(order, self.rank, self.world)
-        shard = torch.from_numpy(np.ascontiguousarray(t[mine])).to(self.device)
-        return dict(E=t.shape[0], order=order, L=L, k=len(mine), shard=shard)
+        prep = self._plan(t)
+        prep["shard"] = torch.from_numpy(np.ascontiguousarray(t[prep["mine"]])).to(self.device)
+        return prep
 
     def run(self, prep):
         """compute this rank's shard (already resident), all-gather, un-permute."""
-        return self._finish(prep["E"], prep["order"], prep["L"], prep["k"], *self.local_fn(prep["shard"]))
+        return self._finish(prep, *self.local_fn(prep["shard"]))
 
     def compute(self, targets):
         t = np.ascontiguousarray(targets, dtype=np.int32).reshape(-1, 2)
-        order, L = plan_shards(t, self.rowptr, self.world)
-        mine = shard_of(order, self.rank, self.world)
-        pi_loc, st_loc = self.local_fn(t[mine])
-        return self._finish(t.shape[0], order, L, len(mine), pi_loc, st_loc)
+        prep = self._plan(t)
+        return self._finish(prep, *self.local_fn(t[prep["mine"]]))
 
-    def _finish(self, E, order, L, k, pi_loc, st_loc):
+    def _finish(self, prep, pi_loc, st_loc):
+        """ONE collective per batch: the shard's float32 image rows and its status (as a 26th column) are
+        all-gathered as [world * L, r2 + 1]; one index_select with the precomputed inverse permutation puts the rows
+        back into the caller's order."""
         import torch
         import torch.distributed as dist
-        mine = range(k)
-        pi_pad = torch.zeros((L, self.r2), dtype=torch.float32, device=self.device)
-        st_pad = torch.zeros((L,), dtype=torch.uint8, device=self.device)
-        pi_pad[: len(mine)] = pi_loc
-        st_pad[: len(mine)] = st_loc
+        L, k, r2 = prep["L"], prep["k"], self.r2
+        key = (L, r2)
+        if getattr(self, "_buf_key", None) != key:  # staging buffers are reused from batch to batch
+            self._pad = torch.zeros((L, r2 + 1), dtype=torch.float32, device=self.device)
+            self._gat = torch.empty((self.world * L, r2 + 1), dtype=torch.float32, device=self.device)
+            self._buf_key = key
+        pad, gat = self._pad, self._gat
+        if k < L:
+            pad[k:].zero_()
+        pad[:k, :r2] = pi_loc
+        pad[:k, r2] = st_loc
         if self.world == 1:
-            return unshard(pi_pad[None], order, 1, E), unshard(st_pad[None], order, 1, E)
-        g_pi = torch.empty((self.world * L, self.r2), dtype=torch.float32, device=self.device)
-        g_st = torch.empty((self.world * L,), dtype=torch.uint8, device=self.device)
-        if dist.get_backend(self.group) == "gloo":  # (gloo has no all_gather_into_tensor)
-            dist.all_gather(list(g_pi.view(self.world, L, self.r2).unbind(0)), pi_pad, group=self.group)
-            dist.all_gather(list(g_st.view(self.world, L).unbind(0)), st_pad, group=self.group)
+            gat.copy_(pad)
+        elif dist.get_backend(self.group) == "gloo":  # (gloo has no all_gather_into_tensor)
+            dist.all_gather(list(gat.view(self.world, L, r2 + 1).unbind(0)), pad, group=self.group)
         else:
-            dist.all_gather_into_tensor(g_pi, pi_pad, group=self.group)
-            dist.all_gather_into_tensor(g_st, st_pad, group=self.group)
-        return (unshard(g_pi.view(self.world, L, self.r2), order, self.world, E),
-                unshard(g_st.view(self.world, L), order, self.world, E))
+            dist.all_gather_into_tensor(gat, pad, group=self.group)
+        out = gat.index_select(0, prep["inv"])
+        return out[:, :r2], out[:, r2].to(torch.uint8)
 
 
 def cuda_local_fn(graph, device, hop=2, descriptor="sum", resolution=5, flags=1, mode=0):
