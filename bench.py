@@ -42,18 +42,47 @@ def parse():
     ap.add_argument("--workload", default=os.environ.get("TLC_BENCH_WORKLOAD", "computers"))
     ap.add_argument("--hop", type=int, default=2)
     ap.add_argument("--extended", type=int, default=int(os.environ.get("TLC_BENCH_EXTENDED", "0")))
+    ap.add_argument("--mode", default="edge", choices=["edge", "node"],
+                    help="node: PDGNN node-centred vicinities with the KD flags (Knowledge_Distillation/data_utils_NC.py shape)")
+    ap.add_argument("--negatives", type=int, default=0, help="append an equal number of seeded non-adjacent pairs (collab config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
 
-def make_workload(name):
+def make_workload(name, mode="edge", negatives=0):
+    """-> (config, labels, target table int64[*, 2], csr, seeded permutation of the target table).
+    edge mode: targets = the graph's edges (+ an equal number of seeded non-adjacent pairs with --negatives 1);
+    node mode: targets = every node, as (u, u); the PPI shape stacks 24 graphs block-diagonally (BASELINE.json configs[3])."""
     from tlc_b200 import graphgen as gg
-    c = gg.make_config(name)
+    c = gg.make_config(name, n_graphs=24 if (name == "ppi" and mode == "node") else 1)
     labels, ne = gg.relabel_first_appearance(c["edges"])
     csr = gg.build_csr(len(labels), ne, c["kappa"])
-    perm = np.random.default_rng(300 + gg.SHAPES[name][0]).permutation(len(ne))
-    return c, labels, ne, csr, perm
+    tt = ne
+    if mode == "node":
+        ids = np.arange(len(labels), dtype=np.int64)
+        tt = np.stack([ids, ids], 1)
+    elif negatives:
+        rng = np.random.default_rng(200 + gg.SHAPES[name][0])
+        N = len(labels)
+        key = set((np.minimum(ne[:, 0], ne[:, 1]) * N + np.maximum(ne[:, 0], ne[:, 1])).tolist())
+        neg = np.zeros((0, 2), np.int64)
+        while len(neg) < len(ne):
+            cand = rng.integers(0, N, size=(len(ne) - len(neg) + 1024, 2))
+            k = np.minimum(cand[:, 0], cand[:, 1]) * N + np.maximum(cand[:, 0], cand[:, 1])
+            ok = (cand[:, 0] != cand[:, 1]) & ~np.isin(k, np.fromiter(key, dtype=np.int64, count=len(key)))
+            neg = np.concatenate([neg, cand[ok]])[:len(ne)]
+        tt = np.concatenate([ne, neg])
+    perm = np.random.default_rng(300 + gg.SHAPES[name][0]).permutation(len(tt))
+    return c, labels, tt, csr, perm
+
+
+def path_flags(args, M):
+    """(flags, mode) of the C-ABI / oracle call (the two share the flag values)."""
+    fl = M.F_NORM | (M.F_EXTENDED if args.extended else 0)
+    if args.mode == "node":
+        fl |= M.F_KEEP_ZERO | M.F_NORM_EPS
+    return fl, (M.MODE_NODE if args.mode == "node" else M.MODE_EDGE)
 
 
 def batch_targets(ne, perm, step, rank, world, batch):
@@ -66,8 +95,13 @@ def batch_targets(ne, perm, step, rank, world, batch):
 def config_dict(args, world):
     from tlc_b200 import graphgen as gg
     _, N, M, _, _ = gg.SHAPES[args.workload]
-    return {"workload": "%s-shaped synthetic graph (%d nodes, %d edges), %d-hop edge vicinities, descriptor=sum, "
-                        "norm=True, 5x5 image, extended_flag=%s" % (args.workload, N, M, args.hop, bool(args.extended)),
+    kind = "edge vicinities" if args.mode == "edge" else "node-centred vicinities (PDGNN generator flags)"
+    if args.mode == "node" and args.workload == "ppi":
+        N, M = 24 * N, 24 * M
+    return {"workload": "%s-shaped synthetic graph (%d nodes, %d edges), %d-hop %s%s, descriptor=sum, "
+                        "norm=True, 5x5 image, extended_flag=%s" % (args.workload, N, M, args.hop, kind,
+                                                                    " + equal negatives" if args.negatives else "",
+                                                                    bool(args.extended)),
             "targets_per_gpu_per_step": args.batch, "global_targets_per_step": args.batch * world,
             "kappa": "U(-0.9,0.9) on a 1/1024 grid", "extended_flag": bool(args.extended),
             "l2": "new targets every step; per-step working set >> L2 (no flush needed)",
@@ -160,16 +194,16 @@ def cpu_baseline(csr, ne, perm, args, seconds, nthreads=0, offset=0):
     import oracle as orc
     og = orc.OracleGraph(*csr)
     cores = orc.max_threads() if nthreads <= 0 else nthreads
-    flags = orc.F_NORM | (orc.F_EXTENDED if args.extended else 0)
+    flags, omode = path_flags(args, orc)
     probe = batch_targets(ne, perm, 1000 + offset, 0, 1, max(2 * cores, 8))
     t0 = time.perf_counter()
-    og.run_batch(probe, hop=args.hop, flags=flags, nthreads=cores)
+    og.run_batch(probe, hop=args.hop, mode=omode, flags=flags, nthreads=cores)
     dt = time.perf_counter() - t0
     rate = len(probe) / dt
     sample = int(min(max(rate * seconds, len(probe)), 200000))
     tg = batch_targets(ne, perm, 2000 + offset, 0, 1, sample)
     t0 = time.perf_counter()
-    r = og.run_batch(tg, hop=args.hop, flags=flags, nthreads=cores)
+    r = og.run_batch(tg, hop=args.hop, mode=omode, flags=flags, nthreads=cores)
     dt = time.perf_counter() - t0
     return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d targets of the same workload in %.1f s (C restatement of the reference algorithm, "
@@ -183,7 +217,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    c, labels, ne, csr, perm = make_workload(args.workload)
+    c, labels, ne, csr, perm = make_workload(args.workload, args.mode, args.negatives)
     per_step = max(4.0, min(30.0, 150.0 / max(args.steps + args.warmup, 1)))
     res = []
     for s in range(args.warmup + args.steps):
@@ -215,6 +249,36 @@ def stage_alg_bytes(sum_n, sum_m, be_total, r2, live):
             "image": 4.0 * r2 * live}
 
 
+def measure_handoff(dev, peak_gbs):
+    """SURVEY.md row N1 (kernel 5): gather + float64->float32 of the decoder's rows from the HBM-resident table, the
+    shape of one training step of baselines/TLCGNN.py:35-53 on the Computers-shaped split (85 % of 245,861 positives +
+    as many sampled negatives out of the train_neg slice).  HBM-bound: 12 B per element + 8 B per row index."""
+    import torch
+    from tlc_b200.table import PITable
+    E = 2 * 245861
+    tp = int(245861 * 0.85)
+    tn = 245861
+    table = PITable(torch.rand((E, 25), dtype=torch.float64, device=dev),
+                    splits=[tp, tn, (E - tp - tn) // 4, (E - tp - tn) // 4, (E - tp - tn) // 4, E - tp - tn - 3 * ((E - tp - tn) // 4)])
+    idx = torch.cat([torch.arange(tp, device=dev), tp + torch.randint(0, tn, (tp,), device=dev)])
+    out = torch.empty((idx.numel(), 25), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2: the table is re-read from HBM every time
+    ms = []
+    for it in range(8):
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        table.gather(index=idx, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.median(ms[3:])) / 1e3
+    nbytes = idx.numel() * (25 * 12 + 8)
+    return {"kernel": "gather_rows (tlc_pi_gather)", "rows": int(idx.numel()), "ms": 1e3 * t, "rows_per_s": idx.numel() / t,
+            "achieved_gbs": nbytes / 1e9 / t, "frac_of_hbm_peak": nbytes / 1e9 / t / peak_gbs,
+            "note": "L2 flushed between repeats (256 MB write); time includes the call's own host sync"}
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -226,22 +290,27 @@ def run_cuda(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line (rank 0): anything libraries print while starting up (e.g. NCCL's version
+    # banner) is sent to stderr -- file descriptor 1 is pointed at stderr until the result line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     os.environ["TLC_STAGE_TIMING"] = "1"
 
-    c, labels, ne, csr, perm = make_workload(args.workload)
+    c, labels, ne, csr, perm = make_workload(args.workload, args.mode, args.negatives)
     g = api.VicinityGraph(*csr, device=local)
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)            # a real (non-default) stream: kernels, NCCL and the timing events share it
     g.set_stream(stream.cuda_stream)
-    flags = L.F_NORM | (L.F_EXTENDED if args.extended else 0)
+    flags, cmode = path_flags(args, L)
     B, r2 = args.batch, 25
 
     out_pi = torch.zeros((B, r2), dtype=torch.float64, device=dev)
     out_f32 = torch.zeros((B, r2), dtype=torch.float32, device=dev)
     out_st = torch.zeros((B,), dtype=torch.uint8, device=dev)
-    sv = multi.ShardedVicinity(csr[0], multi.cuda_local_fn(g, dev, hop=args.hop, flags=flags), dev) if world > 1 else None
+    sv = multi.ShardedVicinity(csr[0], multi.cuda_local_fn(g, dev, hop=args.hop, flags=flags, mode=cmode), dev) if world > 1 else None
 
     def global_targets(s):  # the step's targets of ALL ranks (weak scaling: world * B per step)
         return np.concatenate([batch_targets(ne, perm, s, r, world, B) for r in range(world)])
@@ -254,7 +323,7 @@ def run_cuda(args):
     def run(x):
         if world > 1:
             return sv.run(x)   # this rank's shard through the C-ABI, NCCL all-gather of the fp32 rows, un-permute
-        g.vicinity_pi_dev(x, out_pi, out_f32, out_st, hop=args.hop, flags=flags)
+        g.vicinity_pi_dev(x, out_pi, out_f32, out_st, hop=args.hop, mode=cmode, flags=flags)
 
     def barrier():
         torch.cuda.synchronize()
@@ -307,13 +376,17 @@ def run_cuda(args):
     if world == 1:
         gm = mirror.graph2pi.from_csr(*csr, device=local)
         e2e_batches = [batch_targets(ne, perm, 500 + s, rank, world, B) for s in range(args.steps + 1)]
-        gm.get_pimg_for_all_edges(e2e_batches[0], cores=16, hop=args.hop, norm=True, extended_flag=bool(args.extended),
-                                  resolution=5, descriptor="sum")
+        def e2e_call(tg):
+            if args.mode == "node":  # the PDGNN generators have no batch driver: the C-ABI host-buffer call itself
+                gm._graph.vicinity_pi(tg, hop=args.hop, mode=cmode, flags=flags)
+            else:
+                gm.get_pimg_for_all_edges(tg, cores=16, hop=args.hop, norm=True, extended_flag=bool(args.extended),
+                                          resolution=5, descriptor="sum")
+        e2e_call(e2e_batches[0])
         barrier()
         t0 = time.perf_counter()
         for s in range(args.steps):
-            gm.get_pimg_for_all_edges(e2e_batches[1 + s], cores=16, hop=args.hop, norm=True,
-                                      extended_flag=bool(args.extended), resolution=5, descriptor="sum")
+            e2e_call(e2e_batches[1 + s])
             for k, v in gm._graph.last_stage_ms()[0].items():
                 e2e_stage[k] = e2e_stage.get(k, 0.0) + v
         te_local = time.perf_counter() - t0
@@ -368,6 +441,12 @@ def run_cuda(args):
                     "stage_alg_gbytes_per_step": {k: v / 1e9 / args.steps for k, v in sab.items()},
                     "whole_path": {"compulsory_bytes_per_target": alg_bytes / max(1, live),
                                    "achieved_gbs": (alg_bytes / 1e9) / max(elapsed, 1e-12)}}
+        handoff = None
+        if world == 1:
+            try:
+                handoff = measure_handoff(dev, peak)
+            except Exception as ex:  # never fail the headline over the side measurement
+                handoff = {"error": str(ex)[:200]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(csr, ne, perm, args, args.cpu_seconds)
@@ -380,11 +459,16 @@ def run_cuda(args):
                         "stage_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()}},
                 "handed_back_per_step": handed_back / args.steps,
                 "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "handoff": handoff}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     g.close()
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
 
 
 if __name__ == "__main__":
