@@ -242,10 +242,16 @@ def test_graph_row_route_random(name, scale, hop, cont):
         pi, status, cnt = g.vicinity_pi(tg, hop=hop, flags=L.F_NORM | fl)
         assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
         assert rel_err(pi, o["pi"]) < IMG_TOL
+        cn = g.last_counts()
         if fl == L.F_DIRECT:
-            pi_d = pi
+            pi_d, cn_d = pi, cn
+            # (a target kernel 3v hands back needs the adjacency: the whole call is then redone on the materialised route)
+            assert cn["graph_row_route"] > 0 or cn["handed_back"] > 0
         else:
             assert np.array_equal(pi, pi_d)
+            # the edge totals agree whether kernel 1's counting pass or kernel 1b (graph-row batch call) counted them
+            assert (cn["sum_n"], cn["sum_m"], cn["live"]) == (cn_d["sum_n"], cn_d["sum_m"], cn_d["live"])
+    assert abs(g.last_algorithmic_bytes()) > 0
     g.close()
 
 

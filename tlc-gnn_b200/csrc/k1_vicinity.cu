@@ -187,6 +187,54 @@ ball_build_kernel(GraphView g, Params p, VicinityScratch vs, int W, int bm_in_sm
   }
 }
 
+// Counting pass of the GRAPH-ROW route: n, D_S and the status only -- the induced edges are not counted here (the
+// filtration kernel counts them while it reads the rows anyway).  One warp per target: the vicinity is the AND of two
+// cached ball bitmaps, n its popcount, D_S the sum of the members' graph degrees.
+__global__ void __launch_bounds__(256)
+vicinity_light_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int64_t E, int32_t* out_n, int32_t* out_m,
+                      int32_t* out_ds, uint8_t* out_status, double* out_bytes, VicinityScratch vs, int W) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool node_mode = p.mode == TLC_MODE_NODE;
+  for (int64_t t = warp; t < E; t += nwarps) {
+    const int32_t u = targets[2 * t], v = targets[2 * t + 1];
+    bool bad = u < 0 || u >= g.N || (!node_mode && (v < 0 || v >= g.N));
+    if (!bad) bad = g.rowptr[u + 1] == g.rowptr[u] || (!node_mode && g.rowptr[v + 1] == g.rowptr[v]);
+    if (bad) {
+      if (lane == 0) { out_n[t] = 0; out_m[t] = 0; out_ds[t] = 0; out_status[t] = TLC_ST_UNKNOWN_NODE; if (out_bytes) out_bytes[t] = 0.0; }
+      continue;
+    }
+    const uint32_t* __restrict__ bu = vs.ball_cache + (size_t)u * W;
+    const uint32_t* __restrict__ bv = vs.ball_cache + (size_t)v * W;
+    int n = 0;
+    long long ds = 0;
+    for (int w = lane; w < W; w += 32) {
+      uint32_t bits = node_mode ? bu[w] : (bu[w] & bv[w]);
+      n += __popc(bits);
+      while (bits) {
+        const int x = w * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        ds += g.rowptr[x + 1] - g.rowptr[x];
+      }
+    }
+    for (int o = 16; o; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); ds += __shfl_xor_sync(0xffffffffu, ds, o); }
+    if (lane == 0) {
+      out_n[t] = n;
+      out_m[t] = (int32_t)(ds / 3);  // planning estimate only (CTA width class); the exact count comes from kernel 1b
+      out_ds[t] = (int32_t)ds;
+      uint8_t st = TLC_ST_OK;
+      if (n == 0 || (node_mode && n == 1)) st = TLC_ST_EMPTY;  // :318 / data_utils_NC.py:103-104 (lone centre <=> no edge)
+      out_status[t] = st;
+      if (out_bytes) {  // compulsory bytes B_e WITHOUT the 16 m term, added once m is known
+        const unsigned long long dacc = vs.ball_acc[2 * (size_t)u] + (node_mode ? 0ull : vs.ball_acc[2 * (size_t)v]) + (unsigned long long)ds;
+        const unsigned long long xacc = vs.ball_acc[2 * (size_t)u + 1] + (node_mode ? 0ull : vs.ball_acc[2 * (size_t)v + 1]);
+        out_bytes[t] = 4.0 * (double)dacc + 8.0 * (double)(xacc + (unsigned long long)n) + 4.0 * p.resolution * p.resolution;
+      }
+    }
+  }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(K1_BLOCK)
 vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int64_t E, int32_t* out_n, int32_t* out_m,
@@ -448,6 +496,16 @@ void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* t
   ChunkView dummy{};
   vicinity_kernel<false><<<vs.grid, K1_BLOCK, bytes, st>>>(g, p, targets, E, out_n, out_m, out_ds, out_status, out_bytes, dummy, vs,
                                                           work_counter, W, smem ? 1 : 0);
+  count_launch();
+}
+
+void launch_vicinity_light(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
+                           int32_t* out_m, int32_t* out_ds, uint8_t* out_status, double* out_bytes,
+                           const VicinityScratch& vs, int sm_count, cudaStream_t st) {
+  const int W = (g.N + 31) / 32;
+  const int64_t want = (E * 32 + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count * 8);
+  vicinity_light_kernel<<<grid, 256, 0, st>>>(g, p, targets, E, out_n, out_m, out_ds, out_status, out_bytes, vs, W);
   count_launch();
 }
 

@@ -94,6 +94,7 @@ struct DirectArgs {
   const uint32_t* ball_cache;  // [N][W] closed k-hop balls (kernel 1's ball cache)
   const float* gminw;          // [N] smallest kappa + 1 of the node's graph row, rounded down
   int W;
+  int lid_table;               // 1: shared memory also holds a graph id -> local id table (uint16[N], 0xffff = absent)
 };
 
 template <bool DIRECT, bool SMEM>
@@ -143,6 +144,16 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
       c.adeg[vo + lx] = g.rowptr[x + 1] - ra;
       c.aminw[vo + lx] = da.gminw[x];
     }
+    if (da.lid_table) {  // graph id -> local id in ONE shared-memory read per row entry (instead of bitmap word + prefix + popcount)
+      uint32_t* l32 = bm + 2 * W;
+      for (int i = tid; i < (g.N + 1) / 2; i += nt) l32[i] = 0xffffffffu;
+      __syncthreads();
+      uint16_t* l16 = reinterpret_cast<uint16_t*>(l32);
+      for (int w = wid; w < W; w += nw) {
+        const uint32_t bits = bm[w];
+        if ((bits >> lane) & 1u) l16[w * 32 + lane] = (uint16_t)((int)bm[W + w] + __popc(bits & lanemask_lt()));
+      }
+    }
     lu = bitmap_rank(bm, W, u);
     lv = node_mode ? lu : bitmap_rank(bm, W, v);
     uint8_t st0 = (lu >= 0 && lv >= 0) ? TLC_ST_OK : TLC_ST_TRIVIAL;
@@ -173,9 +184,22 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   const bool plain = (p.flags & TLC_F_SUM_PLAIN) != 0;
   const bool two = roots_in && !node_mode && lu != lv;
 
+  // graph-row route, when the counting pass skipped the induced edges: every member entry read while relaxing for the
+  // first root is counted (each reached vertex's row is read exactly once); rows the relaxation never reads (vertices
+  // the first root does not reach, or no root in the vicinity at all) are counted separately below
+  const bool count_m = DIRECT && c.count_m != 0;
+  const bool use_lid = DIRECT && da.lid_table != 0;
+  const uint16_t* slid = reinterpret_cast<const uint16_t*>(bm + 2 * W);
+  int mcnt = 0;
   if (!roots_in) {
     // nx.NodeNotFound for every vertex -> dist = 100   riccidist2dgm.py:31-32,36-37
     for (int x = tid; x < n; x += nt) { d1[x] = 100.0; d2[x] = 100.0; }
+    if (count_m) {
+      for (int x = wid; x < n; x += nw) {
+        const int a = astart[x], dg = adeg[x];
+        for (int j = lane; j < dg; j += 32) mcnt += bitmap_rank(bm, W, (int)anb[a + j]) >= 0 ? 1 : 0;
+      }
+    }
   } else {
     // SMEM: the launch sized shared memory for the sub-range's largest vicinity (n <= cap); otherwise the per-vertex
     // state lives in the arena.  A compile-time switch, so that the shared-memory accesses are LDS / ATOMS, not generic
@@ -189,6 +213,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
     constexpr uint8_t FAR = 0, TENT = 1, DONE = 2;
     for (int r = 0; r < (two ? 2 : 1); r++) {
       const int root = r == 0 ? lu : lv;
+      const int cnt_this_root = (count_m && r == 0) ? 1 : 0;
       double* out = r == 0 ? d1 : d2;
       for (int x = tid; x < n; x += nt) {
         dist[x] = INF_BITS; state[x] = FAR; tpar[x] = root; tpw[x] = 0.0;
@@ -280,8 +305,13 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
 #pragma unroll
               for (int k = 0; k < RU; k++) {
                 if (ai[k] < 0) continue;
-                const int y = DIRECT ? bitmap_rank(bm, W, yy[k]) : yy[k];
-                if (DIRECT && y < 0) continue;  // the neighbour is outside the vicinity
+                int y = yy[k];
+                if (DIRECT) {
+                  if (use_lid) { const int l = (int)slid[y]; y = l == 0xffff ? -1 : l; }
+                  else y = bitmap_rank(bm, W, y);
+                  if (y < 0) continue;  // the neighbour is outside the vicinity
+                  mcnt += cnt_this_root;
+                }
                 const double w = DIRECT ? __dadd_rn(ww[k], 1.0) : ww[k];  // weight = kappa + 1   riccidist2dgm.py:225
                 const unsigned long long dyb = dist[y];
                 const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dx[k]), w));
@@ -311,6 +341,13 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
         __syncthreads();  // the next phase overwrites the queue
       }
       __syncthreads();
+      if (cnt_this_root) {  // rows of the vertices this root never reached (disconnected vicinity)
+        for (int x = wid; x < n; x += nw) {
+          if (state[x] == DONE) continue;
+          const int a = astart[x], dg = adeg[x];
+          for (int j = lane; j < dg; j += 32) mcnt += bitmap_rank(bm, W, (int)anb[a + j]) >= 0 ? 1 : 0;
+        }
+      }
       // ---- 3. python-order path sums ----
       for (int x = tid; x < n; x += nt) {
         double res;
@@ -336,6 +373,10 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   }
   __syncthreads();
 
+  if (count_m) {
+    const int tot = block_reduce_sum(mcnt, sh.wsum);
+    if (tid == 0) c.tm[t] = tot / 2;  // every induced edge was seen from both ends
+  }
   // 4. descriptors + normalisation   riccidist2dgm.py:47-56 ; data_utils_NC.py:52-54
   double mx = -1.0, sm = -1.0;
   for (int x = tid; x < n; x += nt) {
@@ -371,9 +412,15 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
                                   const DirectArgs& da, cudaStream_t st) {
   // dist (8) + minw (2) + state (1) bytes per vertex in shared memory when the sub-range's largest vicinity fits;
   // graph-row route: + the vicinity bitmap and its word-prefix ranks
-  const size_t bmb = DIRECT ? (size_t)2 * da.W * 4 : 0;
+  size_t bmb = DIRECT ? (size_t)2 * da.W * 4 : 0;
   int cap = (int)((n_max + 7) / 8 * 8);
   if ((size_t)cap * 11 + bmb > 190 * 1024) cap = 0;
+  DirectArgs da2 = da;
+  if (DIRECT) {  // the graph id -> local id table, when it fits next to the per-vertex state
+    const size_t lidb = ((size_t)da.g.N + 1) / 2 * 4;
+    da2.lid_table = (n_max < 65535 && cap > 0 && (size_t)cap * 11 + bmb + lidb <= 190 * 1024) ? 1 : 0;
+    if (da2.lid_table) bmb += lidb;
+  }
   const size_t bytes = (size_t)cap * 11 + bmb;
   if (DIRECT && block < 128) block = 128;  // the prologue walks the bitmap a warp per word
   // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
@@ -381,7 +428,7 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
   auto go = [&](auto kern) {
     cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<cnt, block, bytes, st>>>(p, c, t0, cap, da);
+    kern<<<cnt, block, bytes, st>>>(p, c, t0, cap, da2);
   };
   if (cap > 0) go(filtration_kernel<DIRECT, true>);
   else go(filtration_kernel<DIRECT, false>);
@@ -394,7 +441,7 @@ void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int
 
 void launch_filtration_direct(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                               const float* gminw, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
-  launch_filtration_any<true>(p, c, t0, cnt, block, n_max, DirectArgs{g, vs.ball_cache, gminw, (g.N + 31) / 32}, st);
+  launch_filtration_any<true>(p, c, t0, cnt, block, n_max, DirectArgs{g, vs.ball_cache, gminw, (g.N + 31) / 32, 0}, st);
 }
 
 }  // namespace tlc

@@ -21,6 +21,8 @@
 //                its adjacency row against the packed rank/block table in shared memory)
 //   3. local ids of the essential pair [min, max]        (accelerated_PD.py:35-38,110: first vertex in
 //      ascending id attaining the extreme value)
+#include <cstdlib>
+
 #include "tlc_common.cuh"
 #include "tlc_sort.cuh"
 
@@ -172,6 +174,7 @@ void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int blo
   const size_t bytes = (size_t)smem_ints * 4 + (bm_in_smem ? (size_t)c.W * 8 : 0);
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (const char* env = getenv("TLC_VORDER_BLOCK")) block = atoi(env);  // (tuning experiments)
   vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints, bm_in_smem);
   count_launch();
 }

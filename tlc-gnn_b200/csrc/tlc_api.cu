@@ -68,6 +68,9 @@ struct tlc_graph {
   ChunkView detail_chunk{};  // the chunk of the last tlc_vicinity_detail call (still carved in the arena)
   float* gminw = nullptr;  // [N] smallest kappa + 1 of each node's row, rounded down (graph-row route's settling margin)
   int64_t last_direct = 0;  // targets of the last call that took the graph-row route
+  // density probe of the graph-row route (per hop / mode): decision and calls since it was taken
+  int probe_hop = -1, probe_mode = -1, probe_age = 0;
+  bool probe_direct = false;
   // per-call device buffers
   int32_t *d_n = nullptr, *d_m = nullptr, *d_ds = nullptr;
   uint8_t* d_st = nullptr;
@@ -380,11 +383,53 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   cudaEvent_t ev_total0 = nullptr, ev_total1 = nullptr;
   if (g->timing) { cudaEventCreate(&ev_total0); cudaEventCreate(&ev_total1); cudaEventRecord(ev_total0, st); }
 
+  // ---- route: graph-row (no adjacency in HBM) or materialised, per call ----
+  // the graph-row route serves calls that need the ascending sweep only; it reads D_S graph-row entries per root
+  // where the materialised route reads the 2m induced ones, so it is taken where the vicinities are dense in the graph
+  const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
+  const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
+  const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc &&
+                         !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
+  double direct_ratio = 2.0;
+  if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);
   // ---- kernel 1, counting pass ----
   VicinityScratch vs = make_vs(g);
   tm.mark(0);
   launch_ball_cache(g->gv, p, d_targets, E, vs, st);
-  launch_vicinity_sizes(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->work_counter, st);
+  bool call_direct = direct_ok && (p.flags & TLC_F_DIRECT);
+  if (direct_ok && !call_direct) {
+    // density probe: the full counting pass on a strided sample of the call's targets (measured on B200: one route
+    // per call beats mixing; Computers-shaped 2-hop: D_S / 2m = 1.4, PubMed / collab: > 2).  The verdict is kept
+    // for the next calls with the same hop and mode and refreshed every 32 calls.
+    if (g->probe_hop == p.hop && g->probe_mode == p.mode && g->probe_age < 32) {
+      call_direct = g->probe_direct;
+      g->probe_age++;
+    } else {
+      const int64_t S = std::min<int64_t>(E, std::max<int64_t>(64, E / 64));
+      const int64_t stride = E / S;
+      int32_t* d_sample = nullptr;
+      CK(cudaMalloc((void**)&d_sample, (size_t)S * 8));
+      CK(cudaMemcpy2DAsync(d_sample, 8, d_targets, (size_t)stride * 8, 8, (size_t)S, cudaMemcpyDeviceToDevice, st));
+      launch_vicinity_sizes(g->gv, p, d_sample, S, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->work_counter, st);
+      std::vector<int32_t> sm((size_t)S), sds((size_t)S);
+      std::vector<uint8_t> sst((size_t)S);
+      CK(cudaMemcpyAsync(sm.data(), g->d_m, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(sds.data(), g->d_ds, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(sst.data(), g->d_st, (size_t)S, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      cudaFree(d_sample);
+      double a = 0, b = 0;
+      for (int64_t i = 0; i < S; i++) if (sst[(size_t)i] == TLC_ST_OK) { a += sds[(size_t)i]; b += 2.0 * sm[(size_t)i]; }
+      call_direct = b > 0 && a <= direct_ratio * b;
+      g->probe_hop = p.hop; g->probe_mode = p.mode; g->probe_age = 0; g->probe_direct = call_direct;
+    }
+  }
+  // the batch call on the graph-row route skips counting the induced edges (kernel 1b counts them as it reads the rows)
+  const bool light = call_direct && detail == nullptr;
+  if (light)
+    launch_vicinity_light(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->sm_count, st);
+  else
+    launch_vicinity_sizes(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->work_counter, st);
   tm.mark(-1);
   const size_t pin_need = align_up((size_t)E * 8) + (size_t)E * 9 + ALIGN;
   const size_t pin_need2 = align_up((size_t)E * 4);  // h_ds
@@ -412,25 +457,8 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   }
   if (d_status) CK(cudaMemcpyAsync(d_status, g->d_st, (size_t)E, cudaMemcpyDeviceToDevice, st));
   for (int64_t i = 0; i < E; i++)
-    if (h_st[i] == TLC_ST_OK) { g->alg_bytes += h_bytes[i]; g->last_live++; g->last_nv += h_n[i]; g->last_ne += h_m[i]; }
+    if (h_st[i] == TLC_ST_OK) { g->alg_bytes += h_bytes[i]; g->last_live++; g->last_nv += h_n[i]; if (!light) g->last_ne += h_m[i]; }
 
-  // ---- route: graph-row (no adjacency in HBM) or materialised, per target ----
-  // the graph-row route serves calls that need the ascending sweep only; it reads D_S graph-row entries per root
-  // where the materialised route reads the 2m induced ones, so it is taken where the vicinity is dense in the graph
-  const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
-  const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
-  const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call &&
-                         !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
-  double direct_ratio = 2.0;
-  if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);
-  // one route per call, by the aggregate density of its live vicinities (measured on B200: mixing routes inside a call
-  // costs more in extra chunks than per-target routing gains; Computers-shaped 2-hop: ratio 1.4, PubMed / collab: > 2)
-  bool call_direct = direct_ok && (p.flags & TLC_F_DIRECT);
-  if (direct_ok && !call_direct) {
-    double sds = 0, sm2 = 0;
-    for (int64_t i = 0; i < E; i++) if (h_st[i] == TLC_ST_OK) { sds += h_ds[i]; sm2 += 2.0 * h_m[i]; }
-    call_direct = sm2 > 0 && sds <= direct_ratio * sm2;
-  }
   auto is_direct = [&](int64_t) { return call_direct; };
   // ---- plan chunks ----
   std::vector<int64_t> order;
@@ -451,7 +479,8 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   }
   int64_t need_one = 0;
   for (int64_t i : order)
-    need_one = std::max<int64_t>(need_one, (int64_t)chunk_bytes(1, h_n[i], h_m[i], h_ds[i], is_direct(i) ? Wd : 0));
+    need_one = std::max<int64_t>(need_one, (int64_t)chunk_bytes(1, h_n[i], light ? 0 : h_m[i], light ? 0 : h_ds[i],
+                                                                is_direct(i) ? Wd : 0));
   if (detail) {
     int64_t Nv = 0, Ne = 0, Na = 0;
     for (int64_t i : order) { Nv += h_n[i]; Ne += h_m[i]; Na += h_ds[i]; }
@@ -489,11 +518,12 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
         if (q2 - q >= (size_t)(2 * g->sm_count)) break;
         cls0 = cls1;
       }
-      if (chunk_bytes(T + 1, Nv + h_n[i], Ne + h_m[i], Na + h_ds[i], Wc) > g->arena_bytes) break;
+      const int64_t mi = light ? 0 : h_m[i], di = light ? 0 : h_ds[i];  // (graph-row batch call: no edge / adjacency arrays)
+      if (chunk_bytes(T + 1, Nv + h_n[i], Ne + mi, Na + di, Wc) > g->arena_bytes) break;
       // the staging buffers of a chunk are reused: wait for the previous chunk's upload (stream order suffices,
       // the pinned region of this chunk is [pos, q) which no earlier chunk touches)
       h_tidx[q] = i; h_voff[q] = Nv; h_eoff[q] = Ne; h_aoff[q] = Na; h_tm[q] = h_m[i];
-      Nv += h_n[i]; Ne += h_m[i]; Na += h_ds[i];
+      Nv += h_n[i]; Ne += mi; Na += di;
       n_max = std::max<int64_t>(n_max, h_n[i]); m_max = std::max<int64_t>(m_max, h_m[i]);
       T++; q++;
     }
@@ -521,17 +551,28 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
       }
     }
     if (direct) {
-      // the graph-row route never counts the induced edges; tm is only reported (and read by the edge-sorted kernels)
-      CK(cudaMemcpyAsync((void*)c.tm, h_tm + pos, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+      c.count_m = light ? 1 : 0;
+      // tm: counted by kernel 1b (batch call) or known from the full counting pass (detail call)
+      if (!light) CK(cudaMemcpyAsync((void*)c.tm, h_tm + pos, (size_t)T * 4, cudaMemcpyHostToDevice, st));
       int fb0 = 0, fb1 = 0;
       CK(cudaMemcpyAsync(&fb0, g->work_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
       run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
       CK(cudaMemcpyAsync(&fb1, g->work_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+      if (light) CK(cudaMemcpyAsync(h_tm + pos, c.tm, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       g->last_direct += T;
+      if (light) {  // the exact edge counts: totals and the 16 m term of the compulsory bytes
+        for (int64_t k = 0; k < T; k++) { g->last_ne += h_tm[pos + k]; g->alg_bytes += 16.0 * (double)h_tm[pos + k]; }
+      }
       if (fb1 != fb0) {
-        // kernel 3v handed targets back: their edge-sorted sweep needs the adjacency -> the chunk is redone on the
-        // materialised route (its space is reserved in every chunk), image rows and statuses are rewritten
+        // kernel 3v handed targets back: their edge-sorted sweep needs the adjacency
+        if (light) {  // no adjacency space was reserved: the whole call is redone on the materialised route
+          tlc_params up2 = *up;
+          up2.flags |= TLC_F_NO_DIRECT;
+          tm.collect(g->stage_ms);
+          return run_pipeline(g, d_targets, E, &up2, d_pi, d_pi32, d_status, cnt_compute, detail);
+        }
+        // the chunk is redone on the materialised route (its space is reserved), image rows and statuses are rewritten
         c.dbm = nullptr;
         c.W = 0;
         g->last_direct -= T;

@@ -54,6 +54,7 @@ struct ChunkView {
   int32_t W;             // bitmap words = ceil(N / 32)
   const int32_t* gcol;   // the graph's col[]
   const double* gkappa;  // the graph's kappa[]
+  int32_t count_m;       // graph-row route: kernel 1b counts the induced edges into tm[] (the counting pass skipped them)
   // edge-indexed (canonical lexicographic (lo, hi) edge list: kernel 1c, only for the edge-sorted kernels)
   int32_t *elo, *ehi, *pos, *arank;
   double* ew;
@@ -167,6 +168,10 @@ struct VicinityScratch {
 void launch_vicinity_sizes(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
                            int32_t* out_m, int32_t* out_ds, uint8_t* out_status, double* out_bytes,
                            const VicinityScratch& vs, int* work_counter, cudaStream_t st);
+// graph-row route: n, D_S, status (needs the ball cache); out_m receives a planning estimate, kernel 1b counts m
+void launch_vicinity_light(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, int32_t* out_n,
+                           int32_t* out_m, int32_t* out_ds, uint8_t* out_status, double* out_bytes,
+                           const VicinityScratch& vs, int sm_count, cudaStream_t st);
 void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
                           int* work_counter, cudaStream_t st);
 void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
