@@ -31,6 +31,9 @@ extern "C" {
 /* ---- vicinity mode ---- */
 #define TLC_MODE_EDGE 0 /* ball(u) & ball(v), induced          riccidist2dgm.py:311-316 */
 #define TLC_MODE_NODE 1 /* ball(u) (PDGNN generators)          Knowledge_Distillation/data_utils_NC.py:97-100 */
+#define TLC_MODE_EDGE_FORCED 2 /* (ball(u) & ball(v)) + {u, v}: the PDGNN link-prediction generator's vicinity, the two
+                                  roots always members; no edge at all -> TLC_ST_EMPTY (`return None, None`)
+                                  Knowledge_Distillation/data_utils_LP.py:107-118 */
 
 /* ---- descriptor: which node attribute is the filtration     riccidist2dgm.py:47-49 ---- */
 #define TLC_DESC_MIN 0

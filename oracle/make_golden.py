@@ -145,7 +145,46 @@ def make_kd_case(tag, edges, kappa, nodes, hop):
     print("wrote", tag, "nodes", len(nodes), "none", int(np.sum(none)))
 
 
+def make_kd_lp_case(tag, edges, kappa, pairs, hop):
+    """edge-centred PDGNN generator fixture: the UNMODIFIED Knowledge_Distillation/data_utils_LP.py
+    compute_persistence_image(g, u, v, filt='ricci', hop, ricci_curv, mode='PI') (:105-196) per pair.
+    kind: 0 = 9-tuple, 1 = `return None, None`, 2 = the reference raised."""
+    edges = np.asarray(edges, dtype=np.int64)
+    g = rh.build_nx_graph(edges)
+    ricci = rh.ricci_list(edges, [float(k) for k in kappa])
+    out = dict(edges=edges, kappa=np.asarray(kappa, dtype=np.float64), nodes=np.asarray(pairs, dtype=np.int64).reshape(-1, 2),
+               hop=np.int64(hop))
+    kind, old, filt, ord0, ext1, ei, pi, pi0, pi1 = [], [], [], [], [], [], [], [], []
+    for u, v in out["nodes"]:
+        r = rh.kd_lp_run_edge(g, ricci, int(u), int(v), hop)
+        kind.append(1 if r is None else (2 if isinstance(r, str) else 0))
+        if not isinstance(r, dict):
+            r = dict(old_label=[], filt=[], ord0=[], ext1=[], edge_index=[], pi=np.zeros(25), pi0=np.zeros(25), pi1=np.zeros(25))
+        old.append(r["old_label"]); filt.append(r["filt"]); ord0.append(r["ord0"]); ext1.append(r["ext1"])
+        ei.append(np.asarray(r["edge_index"]).T if len(r["edge_index"]) else [])
+        pi.append(r["pi"]); pi0.append(r["pi0"]); pi1.append(r["pi1"])
+    out["kind"] = np.asarray(kind, dtype=np.int64)
+    out["none"] = out["kind"] == 1
+    for name, lst, dt in (("old_label", old, np.int64), ("filt", filt, np.float64), ("ord0", ord0, np.float64),
+                          ("ext1", ext1, np.float64), ("edge_index", ei, np.int64)):
+        flat, off = ragged(lst, dt)
+        out["kd_%s" % name] = flat
+        out["kd_%s_off" % name] = off
+    out["pi"], out["pi0"], out["pi1"] = np.stack(pi), np.stack(pi0), np.stack(pi1)
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **out)
+    print("wrote", tag, "pairs", len(out["nodes"]), "kinds", np.bincount(out["kind"], minlength=3).tolist())
+
+
 def kd_cases():
+    c = gg.make_config("pubmed", scale=0.05, continuous=True)
+    rng = np.random.default_rng(23)
+    un = np.unique(c["edges"])
+    pairs = np.concatenate([c["edges"][rng.choice(len(c["edges"]), 30, replace=False)],
+                            rng.choice(un, size=(10, 2)), np.array([[un[3], un[3]]])])
+    make_kd_lp_case("kd_lp_pubmed_s_hop2_cont", c["edges"], c["kappa"], pairs, 2)
+    c = gg.make_config("ppi", scale=0.1)
+    pairs = c["edges"][rng.choice(len(c["edges"]), 16, replace=False)]
+    make_kd_lp_case("kd_lp_ppi_s_hop1", c["edges"], c["kappa"], pairs, 1)
     c = gg.make_config("ppi", scale=0.1)
     nodes = np.unique(c["edges"])[np.random.default_rng(21).choice(len(np.unique(c["edges"])), 20, replace=False)]
     make_kd_case("kd_ppi_s_hop1", c["edges"], c["kappa"], nodes, 1)

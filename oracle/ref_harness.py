@@ -158,9 +158,10 @@ def run_one_stages(pi, u_old, v_old, hop, descriptor="sum", norm=True, canonical
 _kd_loaded = {}
 
 
-def load_kd():
-    if _kd_loaded:
-        return _kd_loaded["nc"]
+def load_kd(which="NC"):
+    """which = 'NC' (node-centred generator) or 'LP' (edge-centred generator, data_utils_LP.py)."""
+    if which in _kd_loaded:
+        return _kd_loaded[which]
     ref = load()
     stubs = {}
 
@@ -181,6 +182,7 @@ def load_kd():
     kd_pkg.__path__ = [os.path.join(REF_ROOT, "Knowledge_Distillation")]
     kd_pkg.accelerated_PD = ref.kd_apd
     stubs["Knowledge_Distillation.accelerated_PD"] = ref.kd_apd
+    kd_pkg.spectral = stub("Knowledge_Distillation.spectral", SpectralClustering=None)  # (absent sibling, data_utils_LP.py:18)
     sg = stub("sg2dgm")
     sg.__path__ = [os.path.join(REF_ROOT, "sg2dgm")]
     sg.PersistenceImager = ref.pimg
@@ -191,14 +193,15 @@ def load_kd():
         del sys.modules[k]
     sys.modules.update(stubs)
     try:
-        nc = _load_source("_ref_kd_data_utils_NC", os.path.join(REF_ROOT, "Knowledge_Distillation", "data_utils_NC.py"))
+        nc = _load_source("_ref_kd_data_utils_" + which,
+                          os.path.join(REF_ROOT, "Knowledge_Distillation", "data_utils_%s.py" % which))
     finally:
         for k in stubs:
             sys.modules.pop(k, None)
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
-    _kd_loaded["nc"] = nc
+    _kd_loaded[which] = nc
     return nc
 
 
@@ -214,6 +217,31 @@ def kd_run_node(g, ricci, u, hop):
         return None
     nodes = [u] + [x for _, x in nx.bfs_edges(g, u, depth_limit=hop)]       # :97
     sub = nx.convert_node_labels_to_integers(g.subgraph(nodes), label_attribute="old_label")  # :98-99
+    old = [sub.nodes[i]["old_label"] for i in range(len(sub))]
+    ord0, ext1, pi, filt, edge_index, pi0, pi1, _, _ = r
+    return dict(ord0=np.asarray(ord0, dtype=np.float64).reshape(-1, 2), ext1=np.asarray(ext1, dtype=np.float64).reshape(-1, 2),
+                pi=np.asarray(pi, dtype=np.float64), pi0=np.asarray(pi0, dtype=np.float64), pi1=np.asarray(pi1, dtype=np.float64),
+                filt=np.asarray(filt, dtype=np.float64), edge_index=np.asarray(edge_index.numpy(), dtype=np.int64),
+                old_label=np.asarray(old, dtype=np.int64))
+
+
+def kd_lp_run_edge(g, ricci, u, v, hop):
+    """data_utils_LP.compute_persistence_image(g, u, v, filt='ricci', hop, ricci_curv, mode='PI') unmodified (:105-196):
+    the edge-centred PDGNN generator, vicinity = (ball(u) & ball(v)) + [u] + [v].  Returns None for `return None, None`
+    (:117-118), the string 'raised' when the reference itself raises (a disconnected vicinity: Accelerate_PD's BFS tree
+    misses vertices -> KeyError, Knowledge_Distillation/accelerated_PD.py:124-137), else the fields of the 9-tuple."""
+    import networkx as nx
+    lp = load_kd("LP")
+    try:
+        r = lp.compute_persistence_image(g, u, v, filt="ricci", hop=hop, ricci_curv=ricci, mode="PI")
+    except BaseException:
+        return "raised"
+    if r[0] is None:
+        return None
+    nodes_u = [u] + [x for _, x in nx.bfs_edges(g, u, depth_limit=hop)]      # :107-110
+    nodes_v = [v] + [x for _, x in nx.bfs_edges(g, v, depth_limit=hop)]
+    nodes = list(set(nodes_u) & set(nodes_v)) + [u] + [v]                    # :111
+    sub = nx.convert_node_labels_to_integers(g.subgraph(nodes), label_attribute="old_label")
     old = [sub.nodes[i]["old_label"] for i in range(len(sub))]
     ord0, ext1, pi, filt, edge_index, pi0, pi1, _, _ = r
     return dict(ord0=np.asarray(ord0, dtype=np.float64).reshape(-1, 2), ext1=np.asarray(ext1, dtype=np.float64).reshape(-1, 2),

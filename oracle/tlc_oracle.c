@@ -26,6 +26,7 @@
 
 #define TLO_MODE_EDGE 0 /* riccidist2dgm.py:311-316 : ball(u) & ball(v)            */
 #define TLO_MODE_NODE 1 /* Knowledge_Distillation/data_utils_NC.py:97-100 : ball(u) */
+#define TLO_MODE_EDGE_FORCED 2 /* Knowledge_Distillation/data_utils_LP.py:107-112 : (ball(u) & ball(v)) + [u] + [v] */
 
 #define TLO_DESC_MIN 0
 #define TLO_DESC_MAX 1
@@ -370,7 +371,7 @@ static int run_target(const tlo_graph *g, int32_t u, int32_t v, const tlo_params
                       double *img, tlo_detail *det) {
   const int32_t res = p->resolution, N = g->N;
   const int plain = (p->flags & TLO_F_SUM_PLAIN) != 0, keep0 = (p->flags & TLO_F_KEEP_ZERO) != 0;
-  const int node_mode = p->mode == TLO_MODE_NODE;
+  const int node_mode = p->mode == TLO_MODE_NODE, forced = p->mode == TLO_MODE_EDGE_FORCED;
   for (int32_t i = 0; i < res * res; i++) img[i] = 0.0;
   if (det) { det->n = det->m = det->npairs = det->npos = det->nneg = 0; det->lu = det->lv = -1; }
   /* dict_node[u] KeyError -> zeros   riccidist2dgm.py:353 ; graph lacks isolated nodes loaddatas.py:88-92 */
@@ -389,8 +390,12 @@ static int run_target(const tlo_graph *g, int32_t u, int32_t v, const tlo_params
     int32_t *bu = (int32_t *)malloc((size_t)cu * 4);
     memcpy(bu, w->queue, (size_t)cu * 4);
     int32_t cv = ball(g, v, p->hop, w->mark_v, w->queue);
-    ws_reserve(w, cu < cv ? cu : cv, 0);
+    ws_reserve(w, (cu < cv ? cu : cv) + 2, 0);
     for (int32_t i = 0; i < cu; i++) if (w->mark_v[bu[i]]) w->vert[n++] = bu[i];
+    if (forced) { /* nodes = list(set(nodes_u) & set(nodes_v)) + [u] + [v]   data_utils_LP.py:111 (g.subgraph dedups) */
+      if (!w->mark_v[u]) w->vert[n++] = u;
+      if (v != u && !w->mark_u[v]) w->vert[n++] = v;
+    }
     for (int32_t i = 0; i < cu; i++) w->mark_u[bu[i]] = 0;
     for (int32_t i = 0; i < cv; i++) w->mark_v[w->queue[i]] = 0;
     free(bu);
@@ -422,7 +427,7 @@ static int run_target(const tlo_graph *g, int32_t u, int32_t v, const tlo_params
     if (det->ehi) memcpy(det->ehi, w->ehi, (size_t)m * 4);
     if (det->ew) memcpy(det->ew, w->ew, (size_t)m * 8);
   }
-  if (node_mode && m == 0) return TLO_ST_EMPTY; /* `return None, None` data_utils_NC.py:103-104 */
+  if ((node_mode || forced) && m == 0) return TLO_ST_EMPTY; /* `return None, None` data_utils_NC.py:103-104, data_utils_LP.py:117-118 */
 
   /* symmetric local adjacency (ascending neighbour ids) */
   for (int32_t i = 0; i <= n; i++) w->rowl[i] = 0;

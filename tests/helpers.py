@@ -35,6 +35,7 @@ def rel_err(a, ref):
 
 
 KD_CASES = ["kd_ppi_s_hop1", "kd_pubmed_s_hop2_cont", "kd_pubmed_s_hop0"]
+KD_LP_CASES = ["kd_lp_pubmed_s_hop2_cont", "kd_lp_ppi_s_hop1"]  # edge-centred generator (data_utils_LP.py), nodes = [pairs, 2]
 
 
 def load_kd_case(tag):
@@ -45,7 +46,7 @@ def load_kd_case(tag):
     labels, ne = gg.relabel_first_appearance(c["edges"])
     c["csr"] = gg.build_csr(len(labels), ne, c["kappa"])
     c["lut"] = {int(l): i for i, l in enumerate(labels)}
-    c["new_nodes"] = np.array([c["lut"][int(u)] for u in c["nodes"]], dtype=np.int32)
+    c["new_nodes"] = np.array([c["lut"][int(u)] for u in c["nodes"].reshape(-1)], dtype=np.int32).reshape(c["nodes"].shape)
     return c
 
 

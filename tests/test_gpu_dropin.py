@@ -109,3 +109,30 @@ def test_kd_generator_tuple_matches_reference(tag):
     else:
         # (the image sums its points in CTA-size dependent order: last-bit differences between differently sized calls)
         assert np.array_equal(one[0], res[0][0]) and rel_err(one[2], res[0][2]) < 1e-12
+
+
+@pytest.mark.parametrize("tag", __import__("helpers").KD_LP_CASES)
+def test_kd_lp_generator_tuple_matches_reference(tag):
+    """edge-centred PDGNN generator mirror vs the UNMODIFIED data_utils_LP.compute_persistence_image outputs."""
+    from helpers import kd_expected, load_kd_case, sorted_rows
+    import sg2dgm.kd as kd
+    c = load_kd_case(tag)
+    pi = build(c)
+    res = kd.compute_persistence_images_lp(pi, [(int(u), int(v)) for u, v in c["nodes"]], hop=c["hop"])
+    ok = 0
+    for k, r in enumerate(res):
+        e = kd_expected(c, k)
+        if e["none"] or int(c["kind"][k]) == 2 or r[0] is None:
+            assert r[0] is None and r[1] is None      # `return None, None` / outside the contract (disconnected)
+            continue
+        ord0, ext1, img, filt, edge_index, pi0, pi1, _, _ = r
+        newid = np.array([c["lut"][int(x)] for x in r.old_label])
+        assert np.array_equal(newid, e["vert"]) and np.array_equal(np.asarray(filt), e["filt"])
+        assert np.array_equal(newid[np.asarray(edge_index)].T, e["edges"])
+        assert np.array_equal(sorted_rows(ord0), e["ord0"]) and np.array_equal(sorted_rows(ext1), e["ext1"])
+        assert rel_err(img, e["pi"]) < 1e-5 and rel_err(pi0, e["pi0"]) < 1e-5 and rel_err(pi1, e["pi1"]) < 1e-5
+        ok += 1
+    assert ok >= 10
+    u0, v0 = map(int, c["nodes"][0])
+    one = kd.compute_persistence_image(pi, u0, v0, filt="ricci", hop=c["hop"], mode="PI")
+    assert (one[0] is None) == (res[0][0] is None)

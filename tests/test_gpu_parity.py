@@ -267,3 +267,22 @@ def test_graph_row_route_node_mode():
     for hop in (0, 1, 2):
         compare_asc(g, og, tg, hop, "sum", fl | L.F_DIRECT, fl, mode=L.MODE_NODE)
     g.close()
+
+
+def test_edge_forced_mode_kd_flags():
+    """PDGNN edge-centred vicinities, the two roots always members (Knowledge_Distillation/data_utils_LP.py:107-118)."""
+    c = gg.make_config("pubmed", scale=0.3, continuous=True)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    rng = np.random.default_rng(4)
+    tg = np.concatenate([ne[rng.choice(len(ne), 40, replace=False)], rng.integers(0, len(labels), size=(20, 2)),
+                         np.array([[5, 5], [-1, 2]])]).astype(np.int32)
+    flags = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
+    for hop in (1, 2):
+        compare_detail(g, og, tg, hop, "sum", flags, flags, mode=L.MODE_EDGE_FORCED)
+        pi, status, cnt = g.vicinity_pi(tg, hop=hop, mode=L.MODE_EDGE_FORCED, flags=flags)
+        o = og.run_batch(tg, hop=hop, mode=orc.MODE_EDGE_FORCED, flags=flags)
+        assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"] and rel_err(pi, o["pi"]) < IMG_TOL
+    g.close()

@@ -102,9 +102,11 @@ __device__ int build_vicinity(const GraphView& g, const Params& p, int32_t u, in
   if (vs.ball_cache) {  // both balls are cached rows: nodes = set(nodes_u) & set(nodes_v)   :315
     const uint32_t* __restrict__ bu = vs.ball_cache + (size_t)u * W;
     const uint32_t* __restrict__ bv = vs.ball_cache + (size_t)v * W;
-    const bool edge = p.mode == TLC_MODE_EDGE;
+    const bool edge = p.mode != TLC_MODE_NODE;
+    const bool forced = p.mode == TLC_MODE_EDGE_FORCED;  // nodes = list(set(nodes_u) & set(nodes_v)) + [u] + [v]   data_utils_LP.py:111
     for (int w = tid; w < W; w += nt) {
-      const uint32_t x = edge ? (bu[w] & bv[w]) : bu[w];
+      uint32_t x = edge ? (bu[w] & bv[w]) : bu[w];
+      if (forced) { if (w == (u >> 5)) x |= 1u << (u & 31); if (w == (v >> 5)) x |= 1u << (v & 31); }
       bm_u[w] = x;
       bm_v[w] = __popc(x);
     }
@@ -118,10 +120,12 @@ __device__ int build_vicinity(const GraphView& g, const Params& p, int32_t u, in
   for (int w = tid; w < 2 * W; w += nt) bm_u[w] = 0;  // bm_v follows bm_u
   __syncthreads();
   ball(g, u, p.hop, bm_u, q0, q1, sh);
-  if (p.mode == TLC_MODE_EDGE) {
+  if (p.mode != TLC_MODE_NODE) {
     ball(g, v, p.hop, bm_v, q0, q1, sh);
+    const bool forced = p.mode == TLC_MODE_EDGE_FORCED;
     for (int w = tid; w < W; w += nt) {  // nodes = set(nodes_u) & set(nodes_v)   :315
-      const uint32_t x = bm_u[w] & bm_v[w];
+      uint32_t x = bm_u[w] & bm_v[w];
+      if (forced) { if (w == (u >> 5)) x |= 1u << (u & 31); if (w == (v >> 5)) x |= 1u << (v & 31); }
       bm_u[w] = x;
       bm_v[w] = __popc(x);
     }
@@ -326,7 +330,7 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
         out_ds[t] = sh.ecur;  // D_S: sum of the vicinity vertices' degrees = capacity of the adjacency segment
         uint8_t st = TLC_ST_OK;
         if (n == 0) st = TLC_ST_EMPTY;                          // assert len(components) == 1 fails  :318
-        else if (node_mode && m == 0) st = TLC_ST_EMPTY;        // `return None, None` data_utils_NC.py:103-104
+        else if ((node_mode || p.mode == TLC_MODE_EDGE_FORCED) && m == 0) st = TLC_ST_EMPTY;  // `return None, None` data_utils_NC.py:103-104, data_utils_LP.py:117-118
         out_status[t] = st;
         // compulsory bytes B_e: int32 neighbour reads of both expansions and of the induced
         // scan, rowptr pairs, f64 weight per induced directed edge, fp32 image
@@ -442,7 +446,7 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
       c.tlu[t] = u_in ? local_id(iw, wbase, u) : -1;
       c.tlv[t] = node_mode ? c.tlu[t] : (v_in ? local_id(iw, wbase, v) : -1);
       uint8_t st = (u_in && v_in) ? TLC_ST_OK : TLC_ST_TRIVIAL;
-      if (n == 0 || (node_mode && m == 0)) st = TLC_ST_EMPTY;  // :318 / data_utils_NC.py:103-104
+      if (n == 0 || ((node_mode || p.mode == TLC_MODE_EDGE_FORCED) && m == 0)) st = TLC_ST_EMPTY;  // :318 / data_utils_NC.py:103-104
       c.tstatus[t] = st;
       c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tncls[t] = 0;
     }

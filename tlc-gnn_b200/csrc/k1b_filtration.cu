@@ -28,6 +28,8 @@
 // the smallest weight of the vertex's GRAPH row (<= the smallest induced weight: the criterion stays valid).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "tlc_common.cuh"
 
 namespace tlc {
@@ -53,7 +55,13 @@ __device__ __forceinline__ double pysum_get(const PySum& p, bool plain) {
   return p.s;
 }
 
-constexpr int QCAP = 1024;  // vertices settled per phase at most
+#ifndef FILT_QCAP
+#define FILT_QCAP 1024
+#endif
+#ifndef FILT_RU
+#define FILT_RU 4
+#endif
+constexpr int QCAP = FILT_QCAP;  // vertices settled per phase at most
 struct FiltShared {
   double redd[32];
   // the phase's settled vertices: id, first entry in the concatenated rows (exclusive degree prefix),
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
             unsigned long long dxb = dist[sh.qx[i]];
             // RU entries per lane and step: the row bookkeeping runs ahead in shared memory, then all loads of
             // the step are issued before the first use
-            constexpr int RU = 4;
+            constexpr int RU = FILT_RU;
             for (; e < e1; e += 32 * RU) {
               int ai[RU], ri[RU];
               unsigned long long dx[RU];
@@ -419,12 +427,14 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
   if (DIRECT) {  // the graph id -> local id table, when it fits next to the per-vertex state
     const size_t lidb = ((size_t)da.g.N + 1) / 2 * 4;
     da2.lid_table = (n_max < 65535 && cap > 0 && (size_t)cap * 11 + bmb + lidb <= 190 * 1024) ? 1 : 0;
+    if (getenv("TLC_NO_LID")) da2.lid_table = 0;  // (tuning experiments)
     if (da2.lid_table) bmb += lidb;
   }
   const size_t bytes = (size_t)cap * 11 + bmb;
   if (DIRECT && block < 128) block = 128;  // the prologue walks the bitmap a warp per word
   // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
   if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
+  if (const char* env = getenv("TLC_FILT_BLOCK")) block = atoi(env);  // (tuning experiments)
   auto go = [&](auto kern) {
     cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

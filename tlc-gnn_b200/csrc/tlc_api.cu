@@ -349,7 +349,7 @@ static int check_params(const tlc_params* p) {
   if (!p) return fail(TLC_E_INVALID, "params is NULL");
   if (p->resolution < 1 || p->resolution > 16) return fail(TLC_E_INVALID, "resolution must be in 1..16");
   if (p->hop < 0) return fail(TLC_E_INVALID, "hop must be >= 0");
-  if (p->mode != TLC_MODE_EDGE && p->mode != TLC_MODE_NODE) return fail(TLC_E_INVALID, "bad mode");
+  if (p->mode != TLC_MODE_EDGE && p->mode != TLC_MODE_NODE && p->mode != TLC_MODE_EDGE_FORCED) return fail(TLC_E_INVALID, "bad mode");
   if ((p->flags & TLC_F_ASC_ONLY) && (p->flags & TLC_F_EXTENDED))
     return fail(TLC_E_INVALID, "TLC_F_ASC_ONLY excludes TLC_F_EXTENDED (the loops need the Pos/Neg lists)");
   return TLC_OK;
@@ -388,7 +388,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   // where the materialised route reads the 2m induced ones, so it is taken where the vicinities are dense in the graph
   const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
   const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
-  const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc &&
+  const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc && p.mode != TLC_MODE_EDGE_FORCED &&
                          !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
   double direct_ratio = 2.0;
   if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);

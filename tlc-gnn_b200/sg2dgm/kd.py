@@ -25,15 +25,27 @@ KD_FLAGS = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
 
 
 def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False):
-    """batched: `g2pi` is a sg2dgm.riccidist2dgm.graph2pi (graph + curvature resident on the GPU), `nodes` are ORIGINAL
-    node labels.  Returns a list with one entry per node: the reference's 9-tuple, or (None, None)."""
-    tg = g2pi._map_targets([(u, u) for u in nodes])
+    """node-centred generator, batched: `g2pi` is a sg2dgm.riccidist2dgm.graph2pi (graph + curvature resident on the
+    GPU), `nodes` are ORIGINAL node labels.  Returns a list with one entry per node: the reference's 9-tuple, or
+    (None, None)."""
+    return _emit(g2pi, [(u, u) for u in nodes], L.MODE_NODE, hop, resolution, as_torch)
+
+
+def compute_persistence_images_lp(g2pi, pairs, hop=2, resolution=5, as_torch=False):
+    """edge-centred generator (Knowledge_Distillation/data_utils_LP.py:105-196), batched over (u, v) pairs of ORIGINAL
+    labels: vicinity = (ball(u) & ball(v)) + [u] + [v] (:111), filtration = distance to both roots (:35-60).  A disconnected
+    vicinity is outside the contract (the reference has no check and fails or not by accident): (None, None) here."""
+    return _emit(g2pi, [(u, v) for u, v in pairs], L.MODE_EDGE_FORCED, hop, resolution, as_torch)
+
+
+def _emit(g2pi, targets, mode, hop, resolution, as_torch):
+    tg = g2pi._map_targets(targets)
     G = g2pi._graph
     t0 = time.time()
-    d = G.vicinity_detail(tg, hop=hop, mode=L.MODE_NODE, descriptor="sum", resolution=resolution, flags=KD_FLAGS)
-    dt = (time.time() - t0) / max(1, len(nodes))
+    d = G.vicinity_detail(tg, hop=hop, mode=mode, descriptor="sum", resolution=resolution, flags=KD_FLAGS)
+    dt = (time.time() - t0) / max(1, len(targets))
     out = []
-    for i in range(len(nodes)):
+    for i in range(len(targets)):
         a = G.per_target(d, i)
         if a["status"] != L.ST_OK:           # lone centre / unknown node: `return None, None`   :103-104
             out.append((None, None))
@@ -60,8 +72,11 @@ class _KDTuple(tuple):
         return self
 
 
-def compute_persistence_image(g2pi, u, filt="ricci", hks_time=0.1, hop=2, ricci_curv=None, mode="PI", **_unused):
-    """per-node signature of data_utils_NC.py:95 (first argument: the graph2pi object that holds graph and curvature)."""
+def compute_persistence_image(g2pi, u, v=None, filt="ricci", hks_time=0.1, hop=2, ricci_curv=None, mode="PI", **_unused):
+    """per-target signatures of data_utils_NC.py:95 (g, u, ...) and data_utils_LP.py:105 (g, u, v, ...); the first
+    argument is the graph2pi object that holds graph and curvature."""
     if filt != "ricci" or mode != "PI":
         raise NotImplementedError("only filt='ricci', mode='PI' is on the GPU path (SURVEY.md rows A9 / N3)")
-    return compute_persistence_images(g2pi, [u], hop=hop)[0]
+    if v is None:
+        return compute_persistence_images(g2pi, [u], hop=hop)[0]
+    return compute_persistence_images_lp(g2pi, [(u, v)], hop=hop)[0]
