@@ -60,6 +60,10 @@ extern "C" {
 #define TLC_F_ASC_ONLY 256u /* tlc_vicinity_detail: ascending sweep only -- PD_up and [min,max]; no PD_down, no edge
                                lists / orders / Pos / Neg (those outputs are left untouched) */
 
+#define TLC_F_FILT_DEGREE 512u      /* PDGNN generators, filt='degree': filtration = induced degree / (max + 1e-10)
+                                       Knowledge_Distillation/data_utils_NC.py:126-128 (no roots, no distances) */
+#define TLC_F_FILT_CENTRALITY 1024u /* filt='centrality': nx.degree_centrality (d * 1/(n-1)) / (max + 1e-10)   :118-121 */
+
 /* ---- pair kinds, in the reference's concatenation order    accelerated_PD.py:110, riccidist2dgm.py:328 ---- */
 #define TLC_K_UP 0      /* PD_up   : 0-dim ordinary                 accelerated_PD.py:65-66 */
 #define TLC_K_ESS 1     /* [min,max]                                accelerated_PD.py:110   */

@@ -115,7 +115,7 @@ def graph_cases():
     make_case("pubmed_s_max", c["edges"], c["kappa"], c["edges"][idx], 2, descriptor="max")
 
 
-def make_kd_case(tag, edges, kappa, nodes, hop):
+def make_kd_case(tag, edges, kappa, nodes, hop, filt_name="ricci"):
     """PDGNN generator fixture: the UNMODIFIED Knowledge_Distillation/data_utils_NC.py
     compute_persistence_image(g, u, filt='ricci', hop, ricci_curv, mode='PI') (:95-183) per node -> the 9-tuple
     (Ord0, Ext1, PI, filtration_val, edge_index, PI0, PI1, ...) in the reference's own (implementation-defined)
@@ -124,10 +124,10 @@ def make_kd_case(tag, edges, kappa, nodes, hop):
     g = rh.build_nx_graph(edges)
     ricci = rh.ricci_list(edges, [float(k) for k in kappa])
     out = dict(edges=edges, kappa=np.asarray(kappa, dtype=np.float64), nodes=np.asarray(nodes, dtype=np.int64),
-               hop=np.int64(hop))
+               hop=np.int64(hop), filt_name=np.array(filt_name))
     none, old, filt, ord0, ext1, ei, pi, pi0, pi1 = [], [], [], [], [], [], [], [], []
     for u in nodes:
-        r = rh.kd_run_node(g, ricci, int(u), hop)
+        r = rh.kd_run_node(g, ricci, int(u), hop, filt=filt_name)
         none.append(r is None)
         if r is None:
             r = dict(old_label=[], filt=[], ord0=[], ext1=[], edge_index=[], pi=np.zeros(25), pi0=np.zeros(25), pi1=np.zeros(25))
@@ -188,6 +188,8 @@ def kd_cases():
     c = gg.make_config("ppi", scale=0.1)
     nodes = np.unique(c["edges"])[np.random.default_rng(21).choice(len(np.unique(c["edges"])), 20, replace=False)]
     make_kd_case("kd_ppi_s_hop1", c["edges"], c["kappa"], nodes, 1)
+    make_kd_case("kd_ppi_s_hop1_degree", c["edges"], c["kappa"], nodes[:10], 1, filt_name="degree")          # :126-128
+    make_kd_case("kd_ppi_s_hop1_centrality", c["edges"], c["kappa"], nodes[:10], 1, filt_name="centrality")  # :118-121
     c = gg.make_config("pubmed", scale=0.05, continuous=True)
     un = np.unique(c["edges"])
     nodes = un[np.random.default_rng(22).choice(len(un), 24, replace=False)]

@@ -205,14 +205,14 @@ def load_kd(which="NC"):
     return nc
 
 
-def kd_run_node(g, ricci, u, hop):
+def kd_run_node(g, ricci, u, hop, filt="ricci"):
     """data_utils_NC.compute_persistence_image(g, u, filt='ricci', hop, ricci_curv, mode='PI') unmodified
     (:95-183).  Returns None for the `return None, None` case (:103-104), else a dict with the 9-tuple's
     fields plus `old_label` (new label -> graph node, recovered by repeating the function's own first three
     statements, which are deterministic) so that per-vertex outputs can be put in canonical order."""
     import networkx as nx
     nc = load_kd()
-    r = nc.compute_persistence_image(g, u, filt="ricci", hop=hop, ricci_curv=ricci, mode="PI")
+    r = nc.compute_persistence_image(g, u, filt=filt, hop=hop, ricci_curv=ricci, mode="PI")
     if r[0] is None:
         return None
     nodes = [u] + [x for _, x in nx.bfs_edges(g, u, depth_limit=hop)]       # :97

@@ -38,6 +38,8 @@
 #define TLO_F_NORM_EPS 8u     /* KD: /(max + 1e-10)                       data_utils_NC.py:54           */
 #define TLO_F_SUM_PLAIN 16u   /* python<=3.11 sum(): plain left-to-right; default = 3.12 Neumaier (F5)  */
 #define TLO_F_ASIS_FV 32u     /* build_fv as written: one Dijkstra per (vertex, root)  :27-37           */
+#define TLO_F_FILT_DEGREE 512u      /* KD filt='degree'    : induced degree / (max + 1e-10)   data_utils_NC.py:126-128 */
+#define TLO_F_FILT_CENTRALITY 1024u /* KD filt='centrality': nx.degree_centrality / (max + 1e-10)     :118-121 */
 
 /* pair kinds, in the order the reference concatenates them (accelerated_PD.py:110, riccidist2dgm.py:328) */
 #define TLO_K_UP 0
@@ -489,6 +491,20 @@ static int run_target(const tlo_graph *g, int32_t u, int32_t v, const tlo_params
       if (p->flags & TLO_F_NORM) f = f / (p->descriptor == TLO_DESC_SUM ? ssum : smax);
       w->fval[x] = f;
     }
+  }
+  if (p->flags & (TLO_F_FILT_DEGREE | TLO_F_FILT_CENTRALITY)) {
+    /* the PDGNN generators' structural filtrations: no roots, no distances
+       degree     : [subgraph.degree()[i]]; fv / (max(filtration_val) + 1e-10)                 data_utils_NC.py:126-128
+       centrality : nx.degree_centrality = d * (1.0 / (len(G) - 1.0)) (1 for a lone vertex); fv / (max_val + 1e-10)  :118-121 */
+    double mx = -INFINITY;
+    const double sc = n > 1 ? 1.0 / ((double)n - 1.0) : 1.0;
+    for (int32_t x = 0; x < n; x++) {
+      double d = (double)(w->rowl[x + 1] - w->rowl[x]);
+      if (p->flags & TLO_F_FILT_CENTRALITY) d = n > 1 ? d * sc : 1.0;
+      w->fval[x] = d;
+      if (d > mx) mx = d;
+    }
+    for (int32_t x = 0; x < n; x++) w->fval[x] = w->fval[x] / (mx + 1e-10);
   }
   if (det && det->fval) memcpy(det->fval, w->fval, (size_t)n * 8);
   if (p->descriptor < 0 || p->descriptor > 2) return TLO_ST_BAD_DESCRIPTOR; /* KeyError accelerated_PD.py:13 */

@@ -34,7 +34,7 @@ def rel_err(a, ref):
     return float(np.max(np.abs(a - ref) / den)) if a.size else 0.0
 
 
-KD_CASES = ["kd_ppi_s_hop1", "kd_pubmed_s_hop2_cont", "kd_pubmed_s_hop0"]
+KD_CASES = ["kd_ppi_s_hop1", "kd_pubmed_s_hop2_cont", "kd_pubmed_s_hop0", "kd_ppi_s_hop1_degree", "kd_ppi_s_hop1_centrality"]
 KD_LP_CASES = ["kd_lp_pubmed_s_hop2_cont", "kd_lp_ppi_s_hop1"]  # edge-centred generator (data_utils_LP.py), nodes = [pairs, 2]
 
 
@@ -43,6 +43,7 @@ def load_kd_case(tag):
     z = np.load(os.path.join(GOLDEN, tag + ".npz"))
     c = {k: z[k] for k in z.files}
     c["hop"] = int(c["hop"])
+    c["filt_name"] = str(c["filt_name"]) if "filt_name" in c else "ricci"
     labels, ne = gg.relabel_first_appearance(c["edges"])
     c["csr"] = gg.build_csr(len(labels), ne, c["kappa"])
     c["lut"] = {int(l): i for i, l in enumerate(labels)}

@@ -83,7 +83,7 @@ def test_kd_generator_tuple_matches_reference(tag):
     import sg2dgm.kd as kd
     c = load_kd_case(tag)
     pi = build(c)
-    res = kd.compute_persistence_images(pi, [int(u) for u in c["nodes"]], hop=c["hop"])
+    res = kd.compute_persistence_images(pi, [int(u) for u in c["nodes"]], hop=c["hop"], filt=c["filt_name"])
     assert len(res) == len(c["nodes"])
     for k, r in enumerate(res):
         e = kd_expected(c, k)
@@ -103,7 +103,7 @@ def test_kd_generator_tuple_matches_reference(tag):
         assert rel_err(img, e["pi"]) < 1e-5 and rel_err(pi0, e["pi0"]) < 1e-5 and rel_err(pi1, e["pi1"]) < 1e-5
     # per-node signature of the reference (data_utils_NC.py:95)
     u0 = int(c["nodes"][0])
-    one = kd.compute_persistence_image(pi, u0, filt="ricci", hop=c["hop"], mode="PI")
+    one = kd.compute_persistence_image(pi, u0, filt=c["filt_name"], hop=c["hop"], mode="PI")
     if res[0][0] is None:
         assert one[0] is None and one[1] is None
     else:

@@ -286,3 +286,24 @@ def test_edge_forced_mode_kd_flags():
         o = og.run_batch(tg, hop=hop, mode=orc.MODE_EDGE_FORCED, flags=flags)
         assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"] and rel_err(pi, o["pi"]) < IMG_TOL
     g.close()
+
+
+@pytest.mark.parametrize("filt", ["degree", "centrality"])
+def test_structural_filtrations(filt):
+    """PDGNN generators' filt='degree' / 'centrality' (Knowledge_Distillation/data_utils_NC.py:118-128), node and edge-forced modes."""
+    c = gg.make_config("ppi", scale=0.25)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    rng = np.random.default_rng(8)
+    nodes = rng.choice(len(labels), 16, replace=False)
+    ff = {"degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY}[filt]
+    flags = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS | ff
+    compare_detail(g, og, np.stack([nodes, nodes], 1).astype(np.int32), 1, "sum", flags, flags, mode=L.MODE_NODE)
+    tg = ne[rng.choice(len(ne), 16, replace=False)].astype(np.int32)
+    compare_detail(g, og, tg, 1, "sum", flags, flags, mode=L.MODE_EDGE_FORCED)
+    pi, status, cnt = g.vicinity_pi(tg, hop=1, mode=L.MODE_EDGE_FORCED, flags=flags & ~L.F_EXTENDED)  # (never the graph-row route)
+    o = og.run_batch(tg, hop=1, mode=orc.MODE_EDGE_FORCED, flags=flags & ~L.F_EXTENDED)
+    assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"] and rel_err(pi, o["pi"]) < IMG_TOL
+    g.close()

@@ -415,6 +415,31 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
 
 }  // namespace
 
+// The PDGNN generators' structural filtrations (Knowledge_Distillation/data_utils_NC.py:118-128): induced degree, or
+// networkx's degree centrality d * (1 / (n - 1)), divided by (max + 1e-10).  No roots, no shortest paths: one CTA per
+// vicinity reads the induced degrees kernel 1's fill pass left in adeg[].
+__global__ void __launch_bounds__(256) degree_filtration_kernel(Params p, ChunkView c) {
+  __shared__ double redd[32];
+  const int t = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n = c.tn[t];
+  if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
+  const int64_t vo = c.voff[t];
+  const int32_t* __restrict__ adeg = c.adeg + vo;
+  double* fval = c.fval + vo;
+  const bool cen = (p.flags & TLC_F_FILT_CENTRALITY) != 0;
+  const double sc = n > 1 ? __ddiv_rn(1.0, __dadd_rn((double)n, -1.0)) : 1.0;
+  double mx = -1.0;
+  for (int x = tid; x < n; x += nt) {
+    double d = (double)adeg[x];
+    if (cen) d = n > 1 ? __dmul_rn(d, sc) : 1.0;
+    fval[x] = d;
+    mx = fmax(mx, d);
+  }
+  const double m = __dadd_rn(block_reduce_max(mx, redd), 1e-10);
+  for (int x = tid; x < n; x += nt) fval[x] = __ddiv_rn(fval[x], m);
+}
+
 template <bool DIRECT>
 static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max,
                                   const DirectArgs& da, cudaStream_t st) {
@@ -447,6 +472,11 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
 
 void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
   launch_filtration_any<false>(p, c, t0, cnt, block, n_max, DirectArgs{}, st);
+}
+
+void launch_degree_filtration(const Params& p, const ChunkView& c, cudaStream_t st) {
+  degree_filtration_kernel<<<c.T, 256, 0, st>>>(p, c);
+  count_launch();
 }
 
 void launch_filtration_direct(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,

@@ -307,7 +307,8 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   tm.mark(1);
   if (!c.dbm) launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
-  for (const SubRange& r : subs) {
+  if (p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY)) launch_degree_filtration(p, c, st);
+  else for (const SubRange& r : subs) {
     if (c.dbm) launch_filtration_direct(g->gv, p, c, vs, g->gminw, r.t0, r.cnt, block, r.n_max, st);
     else launch_filtration(p, c, r.t0, r.cnt, block, r.n_max, st);
   }
@@ -389,6 +390,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
   const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
   const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc && p.mode != TLC_MODE_EDGE_FORCED &&
+                         !(p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY)) &&
                          !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
   double direct_ratio = 2.0;
   if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);

@@ -7,8 +7,8 @@ Per node the reference returns the 9-tuple
      PD_time, PI_time)                                                                        (:183)
 or `(None, None)` when the ball has no edge (:103-104).  Here all nodes of a call go through ONE C-ABI call
 (`tlc_vicinity_detail`, node mode, KD flags: zero-persistence pairs kept, division by max + 1e-10, images of
-Ord0 u Ext1 / Ord0 / Ext1); only the filt='ricci' filtration is on the hot path (the other `filt` choices of :115-128 are
-SURVEY.md row N3).
+Ord0 u Ext1 / Ord0 / Ext1).  filt = 'ricci' (the hot path), 'degree' and 'centrality' (:118-128) are
+computed on the GPU; 'hks' (an eigendecomposition) and 'clustering' are not.
 
 Order conventions: the reference's local vertex numbering and pair order follow networkx's sub-graph view iteration
 (implementation-defined).  This mirror uses the canonical order: local ids ascending by graph id,
@@ -24,25 +24,30 @@ from tlc_b200 import _lib as L
 KD_FLAGS = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
 
 
-def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False):
+_FILT_FLAGS = {"ricci": 0, "degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY}   # data_utils_NC.py:115-142
+
+
+def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False, filt="ricci"):
     """node-centred generator, batched: `g2pi` is a sg2dgm.riccidist2dgm.graph2pi (graph + curvature resident on the
     GPU), `nodes` are ORIGINAL node labels.  Returns a list with one entry per node: the reference's 9-tuple, or
     (None, None)."""
-    return _emit(g2pi, [(u, u) for u in nodes], L.MODE_NODE, hop, resolution, as_torch)
+    return _emit(g2pi, [(u, u) for u in nodes], L.MODE_NODE, hop, resolution, as_torch, filt)
 
 
-def compute_persistence_images_lp(g2pi, pairs, hop=2, resolution=5, as_torch=False):
+def compute_persistence_images_lp(g2pi, pairs, hop=2, resolution=5, as_torch=False, filt="ricci"):
     """edge-centred generator (Knowledge_Distillation/data_utils_LP.py:105-196), batched over (u, v) pairs of ORIGINAL
     labels: vicinity = (ball(u) & ball(v)) + [u] + [v] (:111), filtration = distance to both roots (:35-60).  A disconnected
     vicinity is outside the contract (the reference has no check and fails or not by accident): (None, None) here."""
-    return _emit(g2pi, [(u, v) for u, v in pairs], L.MODE_EDGE_FORCED, hop, resolution, as_torch)
+    return _emit(g2pi, [(u, v) for u, v in pairs], L.MODE_EDGE_FORCED, hop, resolution, as_torch, filt)
 
 
-def _emit(g2pi, targets, mode, hop, resolution, as_torch):
+def _emit(g2pi, targets, mode, hop, resolution, as_torch, filt="ricci"):
+    if filt not in _FILT_FLAGS:
+        raise NotImplementedError("filt=%r: only 'ricci', 'degree', 'centrality' are on the GPU path (SURVEY.md row N3)" % (filt,))
     tg = g2pi._map_targets(targets)
     G = g2pi._graph
     t0 = time.time()
-    d = G.vicinity_detail(tg, hop=hop, mode=mode, descriptor="sum", resolution=resolution, flags=KD_FLAGS)
+    d = G.vicinity_detail(tg, hop=hop, mode=mode, descriptor="sum", resolution=resolution, flags=KD_FLAGS | _FILT_FLAGS[filt])
     dt = (time.time() - t0) / max(1, len(targets))
     out = []
     for i in range(len(targets)):
@@ -75,8 +80,8 @@ class _KDTuple(tuple):
 def compute_persistence_image(g2pi, u, v=None, filt="ricci", hks_time=0.1, hop=2, ricci_curv=None, mode="PI", **_unused):
     """per-target signatures of data_utils_NC.py:95 (g, u, ...) and data_utils_LP.py:105 (g, u, v, ...); the first
     argument is the graph2pi object that holds graph and curvature."""
-    if filt != "ricci" or mode != "PI":
-        raise NotImplementedError("only filt='ricci', mode='PI' is on the GPU path (SURVEY.md rows A9 / N3)")
+    if mode != "PI":
+        raise NotImplementedError("only mode='PI' is on the GPU path")
     if v is None:
-        return compute_persistence_images(g2pi, [u], hop=hop)[0]
-    return compute_persistence_images_lp(g2pi, [(u, v)], hop=hop)[0]
+        return compute_persistence_images(g2pi, [u], hop=hop, filt=filt)[0]
+    return compute_persistence_images_lp(g2pi, [(u, v)], hop=hop, filt=filt)[0]
