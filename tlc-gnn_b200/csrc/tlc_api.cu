@@ -53,6 +53,10 @@ struct tlc_graph {
   int device = 0;
   GraphView gv{};
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  // the filtration launches of a chunk's sub-ranges are independent: they run on side streams, forked from / joined to
+  // the call's stream with events, so that the tail wave of one sub-range is filled by CTAs of the next
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   int64_t last_live = 0, last_nv = 0, last_ne = 0, last_fb = 0, last_general = 0, last_rowcheck = 0, last_blocks = 0;
   char* arena = nullptr;
   size_t arena_bytes = 0, arena_req = 0;
@@ -308,9 +312,17 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   if (!c.dbm) launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
   if (p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY)) launch_degree_filtration(p, c, st);
-  else for (const SubRange& r : subs) {
-    if (c.dbm) launch_filtration_direct(g->gv, p, c, vs, g->gminw, r.t0, r.cnt, block, r.n_max, st);
-    else launch_filtration(p, c, r.t0, r.cnt, block, r.n_max, st);
+  else {
+    const bool fork = subs.size() > 1 && g->ev_fork != nullptr;
+    if (fork) cudaEventRecord(g->ev_fork, st);
+    for (size_t i = 0; i < subs.size(); i++) {
+      const SubRange& r = subs[i];
+      cudaStream_t s = st;
+      if (fork && i > 0 && i <= 3) { s = g->side[i - 1]; cudaStreamWaitEvent(s, g->ev_fork, 0); }
+      if (c.dbm) launch_filtration_direct(g->gv, p, c, vs, g->gminw, r.t0, r.cnt, block, r.n_max, s);
+      else launch_filtration(p, c, r.t0, r.cnt, block, r.n_max, s);
+      if (s != st) { cudaEventRecord(g->ev_join[i - 1], s); cudaStreamWaitEvent(st, g->ev_join[i - 1], 0); }
+    }
   }
   // ascending sweep: vertex-ordered kernels 2v + 3v; targets they hand back (tfb) and, when the descending
   // sweep is wanted (diagram output, Pos/Neg lists for the loops), the edge-sorted kernels 2 + 3.  The image
@@ -544,7 +556,8 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     CK(cudaMemcpyAsync((void*)(c.eoff + T), &Ne, 8, cudaMemcpyHostToDevice, st));
     std::vector<SubRange> subs;
     {
-      const int groups = T >= 4 * 2 * g->sm_count ? 4 : (T >= 2 * 2 * g->sm_count ? 2 : 1);
+      int groups = T >= 4 * 2 * g->sm_count ? 4 : (T >= 2 * 2 * g->sm_count ? 2 : 1);
+      if (const char* env = getenv("TLC_SUBGROUPS")) groups = std::max(1, std::min(4, atoi(env)));  // (tuning experiments)
       for (int gi = 0; gi < groups; gi++) {
         const int64_t a = T * gi / groups, b = T * (gi + 1) / groups;
         int64_t nm = 0;
@@ -673,6 +686,13 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
   g->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking));
   g->stream = g->own_stream;
+  if (!getenv("TLC_NO_SIDE_STREAMS")) {
+    CK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 3; i++) {
+      CK(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&g->ev_join[i], cudaEventDisableTiming));
+    }
+  }
   int32_t *d_rowptr = nullptr, *d_col = nullptr;
   double* d_kappa = nullptr;
   CK(cudaMalloc((void**)&d_rowptr, (size_t)(N + 1) * 4));
@@ -713,6 +733,8 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaFree(g->io_t); cudaFree(g->io_pi); cudaFree(g->io_st); cudaFree(g->gminw);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
+  for (int i = 0; i < 3; i++) { if (g->side[i]) cudaStreamDestroy(g->side[i]); if (g->ev_join[i]) cudaEventDestroy(g->ev_join[i]); }
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   delete g;
   return TLC_OK;
 }
