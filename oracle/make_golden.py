@@ -175,7 +175,48 @@ def make_kd_lp_case(tag, edges, kappa, pairs, hop):
     print("wrote", tag, "pairs", len(out["nodes"]), "kinds", np.bincount(out["kind"], minlength=3).tolist())
 
 
+def make_kd_gc_case(tag, graphs, filt_name="degree"):
+    """graph-classification PDGNN generator fixture: the UNMODIFIED Knowledge_Distillation/data_utils_GC.py
+    compute_persistence_image(g, filt, mode='PI') (:95-167) per whole graph.  graphs: list of (n, edges[m,2])."""
+    none, filt, ord0, ext1, pi, pi0, pi1, sizes, elist = [], [], [], [], [], [], [], [], []
+    for n, e in graphs:
+        r = rh.kd_gc_run_graph(n, e, filt=filt_name)
+        none.append(r is None)
+        if r is None:
+            r = dict(filt=[], ord0=[], ext1=[], pi=np.zeros(25), pi0=np.zeros(25), pi1=np.zeros(25))
+        filt.append(r["filt"]); ord0.append(r["ord0"]); ext1.append(r["ext1"])
+        pi.append(r["pi"]); pi0.append(r["pi0"]); pi1.append(r["pi1"])
+        sizes.append(n); elist.append(np.asarray(e, dtype=np.int64).reshape(-1, 2))
+    out = dict(none=np.asarray(none), sizes=np.asarray(sizes, dtype=np.int64), filt_name=np.array(filt_name),
+               pi=np.stack(pi), pi0=np.stack(pi0), pi1=np.stack(pi1))
+    for name, lst, dt in (("filt", filt, np.float64), ("ord0", ord0, np.float64), ("ext1", ext1, np.float64),
+                          ("gedges", elist, np.int64)):
+        flat, off = ragged(lst, dt)
+        out["kd_%s" % name] = flat
+        out["kd_%s_off" % name] = off
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **out)
+    print("wrote", tag, "graphs", len(graphs), "none", int(np.sum(none)))
+
+
+def gc_graphs(seed, count):
+    """small random graphs of the TU-dataset size range: mostly connected, some disconnected, one edgeless"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(count):
+        n = int(rng.integers(6, 40))
+        tree = [(int(rng.integers(0, i)), i) for i in range(1, n)]                     # random spanning tree: connected
+        extra = [tuple(sorted(map(int, rng.choice(n, 2, replace=False)))) for _ in range(int(rng.integers(0, 2 * n)))]
+        e = sorted(set(tuple(sorted(t)) for t in tree) | set(extra))
+        if k % 5 == 3:                                                                  # drop a tree edge's endpoint: maybe disconnected
+            e = [t for t in e if n - 1 not in t]
+        if k == 7:
+            e = []
+        out.append((n, np.asarray(e, dtype=np.int64).reshape(-1, 2)))
+    return out
+
+
 def kd_cases():
+    make_kd_gc_case("kd_gc_degree", gc_graphs(31, 24), "degree")
     c = gg.make_config("pubmed", scale=0.05, continuous=True)
     rng = np.random.default_rng(23)
     un = np.unique(c["edges"])

@@ -183,6 +183,9 @@ def load_kd(which="NC"):
     kd_pkg.accelerated_PD = ref.kd_apd
     stubs["Knowledge_Distillation.accelerated_PD"] = ref.kd_apd
     kd_pkg.spectral = stub("Knowledge_Distillation.spectral", SpectralClustering=None)  # (absent sibling, data_utils_LP.py:18)
+    kd_pkg.SBM_Model = stub("Knowledge_Distillation.SBM_Model", create_SBM_Model=None)  # (data_utils_GC.py:27)
+    tg.datasets = stub("torch_geometric.datasets", TUDataset=None, ZINC=None)           # (data_utils_GC.py:24)
+    stub("ogb").graphproppred = stub("ogb.graphproppred", PygGraphPropPredDataset=None)  # (data_utils_GC.py:26)
     sg = stub("sg2dgm")
     sg.__path__ = [os.path.join(REF_ROOT, "sg2dgm")]
     sg.PersistenceImager = ref.pimg
@@ -248,3 +251,21 @@ def kd_lp_run_edge(g, ricci, u, v, hop):
                 pi=np.asarray(pi, dtype=np.float64), pi0=np.asarray(pi0, dtype=np.float64), pi1=np.asarray(pi1, dtype=np.float64),
                 filt=np.asarray(filt, dtype=np.float64), edge_index=np.asarray(edge_index.numpy(), dtype=np.int64),
                 old_label=np.asarray(old, dtype=np.int64))
+
+
+def kd_gc_run_graph(n, edges, filt="degree"):
+    """data_utils_GC.compute_persistence_image(g, filt, mode='PI') unmodified (:95-167): the graph-classification
+    generator, the WHOLE graph is the vicinity (nodes 0..n-1 added in order, so subgraph.nodes() is 0..n-1).
+    Returns None for `return None, None` (no edge, or not connected, :99-100)."""
+    import networkx as nx
+    gc = load_kd("GC")
+    g = nx.Graph()
+    g.add_nodes_from(range(n))
+    g.add_edges_from([(int(a), int(b)) for a, b in edges])
+    r = gc.compute_persistence_image(g, filt=filt, mode="PI")
+    if r[0] is None:
+        return None
+    ord0, ext1, pi, fv, edge_index, pi0, pi1, _, _ = r
+    return dict(ord0=np.asarray(ord0, dtype=np.float64).reshape(-1, 2), ext1=np.asarray(ext1, dtype=np.float64).reshape(-1, 2),
+                pi=np.asarray(pi, dtype=np.float64), pi0=np.asarray(pi0, dtype=np.float64), pi1=np.asarray(pi1, dtype=np.float64),
+                filt=np.asarray(fv, dtype=np.float64), edge_index=np.asarray(edge_index.numpy(), dtype=np.int64))

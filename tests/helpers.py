@@ -76,3 +76,16 @@ def kd_expected(c, k):
     return dict(vert=newid[order], filt=kd_seg(c, "filt", k)[order], edges=eg,
                 ord0=sorted_rows(kd_seg(c, "ord0", k)), ext1=sorted_rows(kd_seg(c, "ext1", k)),
                 pi=c["pi"][k], pi0=c["pi0"][k], pi1=c["pi1"][k], none=bool(c["none"][k]))
+
+
+def load_kd_gc_case(tag="kd_gc_degree"):
+    """graph-classification generator fixture: list of (n, edges) + the unmodified reference's per-graph outputs."""
+    z = np.load(os.path.join(GOLDEN, tag + ".npz"))
+    c = {k: z[k] for k in z.files}
+    graphs = []
+    for k, n in enumerate(c["sizes"]):
+        off = c["kd_gedges_off"]
+        graphs.append((int(n), c["kd_gedges"][2 * off[k]:2 * off[k + 1]].reshape(-1, 2)))
+    c["graphs"] = graphs
+    c["filt_name"] = str(c["filt_name"])
+    return c

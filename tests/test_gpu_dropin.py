@@ -136,3 +136,24 @@ def test_kd_lp_generator_tuple_matches_reference(tag):
     u0, v0 = map(int, c["nodes"][0])
     one = kd.compute_persistence_image(pi, u0, v0, filt="ricci", hop=c["hop"], mode="PI")
     assert (one[0] is None) == (res[0][0] is None)
+
+
+def test_kd_gc_generator_matches_reference():
+    """graph-classification PDGNN generator mirror vs the UNMODIFIED data_utils_GC.compute_persistence_image (filt='degree')."""
+    from helpers import load_kd_gc_case, sorted_rows
+    import sg2dgm.kd as kd
+    c = load_kd_gc_case()
+    res = kd.compute_persistence_images_gc(c["graphs"], filt=c["filt_name"])
+    fo, o0, o1 = c["kd_filt_off"], c["kd_ord0_off"], c["kd_ext1_off"]
+    for k, r in enumerate(res):
+        if c["none"][k]:
+            assert r[0] is None and r[1] is None                               # data_utils_GC.py:99-100
+            continue
+        ord0, ext1, img, filt, edge_index, pi0, pi1, _, _ = r
+        assert np.array_equal(np.asarray(r.old_label), np.arange(c["sizes"][k]))
+        assert np.array_equal(np.asarray(filt), c["kd_filt"][fo[k]:fo[k + 1]])
+        n, e = c["graphs"][k]
+        assert np.array_equal(np.asarray(edge_index).T, np.unique(np.sort(e, axis=1), axis=0))
+        assert np.array_equal(sorted_rows(ord0), sorted_rows(c["kd_ord0"][2 * o0[k]:2 * o0[k + 1]]))
+        assert np.array_equal(sorted_rows(ext1), sorted_rows(c["kd_ext1"][2 * o1[k]:2 * o1[k + 1]]))
+        assert rel_err(img, c["pi"][k]) < 1e-5 and rel_err(pi0, c["pi0"][k]) < 1e-5 and rel_err(pi1, c["pi1"][k]) < 1e-5

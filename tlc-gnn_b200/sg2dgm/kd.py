@@ -85,3 +85,45 @@ def compute_persistence_image(g2pi, u, v=None, filt="ricci", hks_time=0.1, hop=2
     if v is None:
         return compute_persistence_images(g2pi, [u], hop=hop, filt=filt)[0]
     return compute_persistence_images_lp(g2pi, [(u, v)], hop=hop, filt=filt)[0]
+
+
+def compute_persistence_images_gc(graphs, filt="degree", resolution=5, device=0):
+    """graph-classification generator (Knowledge_Distillation/data_utils_GC.py:95-167), batched: every WHOLE graph is one
+    vicinity.  graphs: list of (n, edges[m, 2]) with nodes 0..n-1 (the TU-dataset numbering the reference's edge_index
+    assumes).  All graphs go into one block-diagonal CSR and ONE C-ABI call (node mode from node 0 with hop >= the largest
+    graph, i.e. the ball is node 0's component); a graph without edges or not connected yields (None, None) as
+    `if len(subgraph.edges()) == 0 or not nx.is_connected(subgraph)` does (:99-100).
+    filt: 'degree' / 'centrality'.  (filt='ricci' is not mirrored: as written, :118-122 indexes the curvature LIST with
+    a tuple inside a try/except, so every distance becomes 100 -- or it raises when handed a dict.)"""
+    import numpy as np
+    from tlc_b200 import api
+    from tlc_b200.graphgen import build_csr
+    if filt not in ("degree", "centrality"):
+        raise NotImplementedError("data_utils_GC mirror: filt must be 'degree' or 'centrality'")
+    sizes = [int(n) for n, _ in graphs]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    es = [np.asarray(e, dtype=np.int64).reshape(-1, 2) + offs[k] for k, (_, e) in enumerate(graphs)]
+    E = np.concatenate(es) if es else np.zeros((0, 2), np.int64)
+    E = E[E[:, 0] != E[:, 1]]
+    lo, hi = np.minimum(E[:, 0], E[:, 1]), np.maximum(E[:, 0], E[:, 1])
+    key = np.unique(lo * int(offs[-1] + 1) + hi)
+    E = np.stack([key // int(offs[-1] + 1), key % int(offs[-1] + 1)], 1)
+    G = api.VicinityGraph(*build_csr(int(offs[-1]), E, np.zeros(len(E))), device=device)
+    tg = np.stack([offs[:-1], offs[:-1]], 1).astype(np.int32)
+    t0 = time.time()
+    d = G.vicinity_detail(tg, hop=max(sizes + [1]), mode=L.MODE_NODE, descriptor="sum", resolution=resolution,
+                          flags=KD_FLAGS | _FILT_FLAGS[filt])
+    dt = (time.time() - t0) / max(1, len(graphs))
+    out = []
+    for k in range(len(graphs)):
+        a = G.per_target(d, k)
+        if a["status"] != L.ST_OK or a["n"] != sizes[k]:      # no edge / isolated node 0 / more than one component
+            out.append((None, None))
+            continue
+        pk = a["pkind"]
+        pairs = np.stack([a["pbirth"], a["pdeath"]], 1)
+        edge_index = np.stack([a["elo"], a["ehi"]], 0).astype(np.int64)
+        out.append(_KDTuple((pairs[pk == L.K_UP], pairs[pk == L.K_ONE], a["img"].copy(), list(a["fval"]), edge_index,
+                             a["img_up"].copy(), a["img_one"].copy(), dt, 0.0), a["vert"] - offs[k]))
+    G.close()
+    return out
