@@ -25,7 +25,7 @@
 namespace tlc {
 namespace {
 
-constexpr int REP_CAP = 64;
+constexpr int REP_CAP = 128;
 constexpr int SWEEP_WARPS = 1;  // one warp per CTA: the shared-memory footprint (parents of ONE vicinity) sets the residency
 
 struct RepBuf {
@@ -167,6 +167,13 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
       ngeneral++;
       const int merges_before = nmerge;
       int nrep = 0;
+      // A block of EQUAL values is swept in two stages.  Its edges into earlier blocks carry keys fl(M + fl((mu+1)e-6))
+      // with mu < M, its in-block edges the one key fl(M + fl((M+1)e-6)): stage 1 = representatives of the edges into
+      // earlier blocks (sorted, applied in order); stage 2 = the in-block edges, whose order is then purely the canonical
+      // (lo, hi) index order -- block vertices ascending, each row ascending -- and needs no buffering at all.  (A clique
+      // of k tied vertices would otherwise need k(k-1)/2 representatives.)  The strict key separation is verified below.
+      const bool staged = !distinct;
+      const int ylim0 = staged ? s : e;  // stage 1 looks at neighbours of rank < min(x, ylim0)
       for (int x = s; x < e && !bail; x++) {
         const int xrep0 = nrep;
         const int lx = vord[x];
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
           unsigned long long K = 0;
           bool valid = false;
           if (probe) {
-            if (lane < x) {
+            if (lane < min(x, ylim0)) {
               y = lane;
               ly = vord[y];
               const int key = direct ? vert[ly] : ly;  // rows ascend in graph id and in local id alike
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
             ly = nbr(xa + j);
             if (ly >= 0) {
               y = vrank[ly];
-              valid = y < x;  // the edge is owned by its later endpoint
+              valid = y < min(x, ylim0);  // the edge is owned by its later endpoint
             }
           }
           if (valid) {
@@ -240,29 +247,75 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
           rb.perm[rk] = q;
         }
         __syncwarp();
+        // the reference's union step for edge [a, b], a < b (local ids); lane 0 only
+        auto apply_edge = [&](int a, int bb) {
+          const int A = find_root(parent, vrank[a]), B = find_root(parent, vrank[bb]);
+          if (A == B) return;
+          const int la = vord[A], lb = vord[B];  // local ids of the two roots
+          const double fA = fval[la], fB = fval[lb];
+          const bool a_small = fA <= fB;         // small = pu if new[pu] <= new[pv]   :61-63
+          const int small = a_small ? A : B, large = a_small ? B : A;
+          const int llarge = a_small ? lb : la;
+          const double flarge = a_small ? fB : fA;
+          const double fa = fval[a], fb = fval[bb];
+          const int max_node = fa > fb ? a : bb;  // :64
+          const double fmaxn = fa > fb ? fa : fb;
+          if (keep0 || flarge < fmaxn) {          // :65 (KD :68-69: always)
+            c.pkind[po + np] = TLC_K_UP;
+            c.pbv[po + np] = llarge; c.pdv[po + np] = max_node;
+            c.pbirth[po + np] = flarge; c.pdeath[po + np] = fmaxn;
+            np++;
+          }
+          parent[large] = (PT)small;            // :67
+          nmerge++;
+        };
         if (lane == 0) {
           for (int i = 0; i < nrep; i++) {
             const int q = rb.perm[i];
-            const int a = rb.lo[q], bb = rb.hi[q];  // edge = [a, b], a < b (local ids)
-            const int A = find_root(parent, vrank[a]), B = find_root(parent, vrank[bb]);
-            if (A == B) continue;
-            const int la = vord[A], lb = vord[B];  // local ids of the two roots
-            const double fA = fval[la], fB = fval[lb];
-            const bool a_small = fA <= fB;         // small = pu if new[pu] <= new[pv]   :61-63
-            const int small = a_small ? A : B, large = a_small ? B : A;
-            const int llarge = a_small ? lb : la;
-            const double flarge = a_small ? fB : fA;
-            const double fa = fval[a], fb = fval[bb];
-            const int max_node = fa > fb ? a : bb;  // :64
-            const double fmaxn = fa > fb ? fa : fb;
-            if (keep0 || flarge < fmaxn) {          // :65 (KD :68-69: always)
-              c.pkind[po + np] = TLC_K_UP;
-              c.pbv[po + np] = llarge; c.pdv[po + np] = max_node;
-              c.pbirth[po + np] = flarge; c.pdeath[po + np] = fmaxn;
-              np++;
+            apply_edge(rb.lo[q], rb.hi[q]);
+          }
+        }
+        if (staged) {
+          // every stage-1 key must lie strictly below the in-block key (true whenever the smallest value is 0, i.e. a
+          // root is in the vicinity; verified rather than assumed)
+          const double M = fval[vord[s]];
+          const unsigned long long kin = f64_to_ordered(key_asc(M, M));
+          bool ok = true;
+          for (int q = lane; q < nrep; q += 32) ok = ok && rb.key[q] < kin;
+          if (!__all_sync(FULL, ok)) bail = true;
+          __syncwarp();
+          // stage 2: in-block edges in canonical order
+          for (int x = s; x < e && !bail; x++) {
+            const int lx = vord[x];
+            const int xa = astart[lx], xdg = adeg[lx];
+            // small block (typically the two roots with their huge rows): probe the <= 32 later block vertices in x's
+            // ascending row instead of scanning the row
+            const bool probe2 = e - s <= 33;
+            for (int j0 = 0; j0 < (probe2 ? 1 : xdg); j0 += 32) {
+              const int j = j0 + lane;
+              int ly = -1;
+              if (probe2) {
+                const int y = x + 1 + lane;
+                if (y < e) {
+                  const int cand = vord[y];
+                  const int key = direct ? vert[cand] : cand;
+                  int l0 = 0, h0 = xdg;
+                  while (l0 < h0) { const int mid = (l0 + h0) >> 1; if ((int)anb[xa + mid] < key) l0 = mid + 1; else h0 = mid; }
+                  if (l0 < xdg && (int)anb[xa + l0] == key) ly = cand;
+                }
+              } else if (j < xdg) {
+                ly = nbr(xa + j);
+                if (ly >= 0) { const int y = vrank[ly]; if (!(y > x && y < e)) ly = -1; }
+              }
+              unsigned mk = __ballot_sync(FULL, ly >= 0);
+              while (mk) {
+                const int i = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const int lyi = __shfl_sync(FULL, ly, i);
+                if (lane == 0) apply_edge(lx, lyi);  // (equal values: rank order == id order, so lx < lyi)
+              }
+              __syncwarp();
             }
-            parent[large] = (PT)small;            // :67
-            nmerge++;
           }
         }
         np = __shfl_sync(FULL, np, 0);
