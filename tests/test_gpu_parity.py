@@ -307,3 +307,38 @@ def test_structural_filtrations(filt):
     o = og.run_batch(tg, hop=1, mode=orc.MODE_EDGE_FORCED, flags=flags & ~L.F_EXTENDED)
     assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"] and rel_err(pi, o["pi"]) < IMG_TOL
     g.close()
+
+
+def test_handed_back_targets_on_the_graph_row_route():
+    """a near-tie block that needs more representatives than kernel 3v keeps (a clique of 24 common neighbours whose values
+    differ by ~1e-10): the targets are handed back; on the graph-row batch call exactly those are redone on the
+    materialised route and scattered back into the caller's rows."""
+    K = 24
+    edges, kap = [(0, 1)], [0.25]
+    for i in range(K):
+        x = 2 + i
+        edges += [(0, x), (1, x)]
+        kap += [0.5 + i * 1e-10, 0.5 - ((i * 5) % K) * 1e-10]
+        for j in range(i):
+            edges.append((2 + j, x)); kap.append(0.3 + (i * K + j) * 1e-9)
+    # a second, ordinary part of the graph so that the call mixes handed-back and regular targets
+    base = 2 + K
+    for i in range(30):
+        edges += [(base + i, base + (i + 1) % 30), (base + i, base + (i + 7) % 30)]
+        kap += [0.1 * ((i % 5) - 2), 0.05 * ((i % 7) - 3)]
+    edges.append((0, base)); kap.append(0.4)
+    e = np.array(edges, dtype=np.int64)
+    labels, ne = gg.relabel_first_appearance(e)
+    csr = gg.build_csr(len(labels), ne, np.array(kap))
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    tg = np.concatenate([ne[:40], ne[-50:]]).astype(np.int32)
+    o = og.run_batch(tg, hop=2, flags=orc.F_NORM)
+    pi, status, cnt = g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_DIRECT)
+    cn = g.last_counts()
+    assert cn["handed_back"] > 0 and 0 < cn["graph_row_route"] < cn["live"]      # some redone, the rest stayed on the route
+    assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"] and rel_err(pi, o["pi"]) < IMG_TOL
+    pi_m, status_m, cnt_m = g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_NO_DIRECT)
+    assert np.array_equal(pi, pi_m) and np.array_equal(status, status_m) and cnt == cnt_m
+    compare_asc(g, og, tg[:8], 2, "sum", L.F_NORM | L.F_DIRECT, orc.F_NORM)
+    g.close()

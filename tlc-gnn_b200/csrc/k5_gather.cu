@@ -33,7 +33,31 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restri
   }
 }
 
+// rows of a sub-call back to their place in the caller's tables: dst[idx[i], :] = src[i, :]
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const double* __restrict__ src_pi, const float* __restrict__ src_pi32,
+                                                           const uint8_t* __restrict__ src_st, const int64_t* __restrict__ idx,
+                                                           int64_t k, int r2, double* dst_pi, float* dst_pi32, uint8_t* dst_st) {
+  const int64_t total = k * r2;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / r2;
+    const int j = (int)(e - i * r2);
+    const int64_t r = idx[i];
+    dst_pi[r * r2 + j] = src_pi[e];
+    if (dst_pi32) dst_pi32[r * r2 + j] = src_pi32[e];
+    if (j == 0 && dst_st) dst_st[r] = src_st[i];
+  }
+}
+
 }  // namespace
+
+void launch_scatter_rows(const double* src_pi, const float* src_pi32, const uint8_t* src_st, const int64_t* idx, int64_t k,
+                         int r2, double* dst_pi, float* dst_pi32, uint8_t* dst_st, int sm_count, cudaStream_t st) {
+  if (k <= 0) return;
+  const int64_t want = (k * r2 + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count * 16);
+  scatter_rows_kernel<<<grid, 256, 0, st>>>(src_pi, src_pi32, src_st, idx, k, r2, dst_pi, dst_pi32, dst_st);
+  count_launch();
+}
 
 void launch_gather_rows(const double* table, int64_t rows, int r2, const int64_t* index, int64_t start, int64_t n,
                         float* out, int* bad, int sm_count, cudaStream_t st) {

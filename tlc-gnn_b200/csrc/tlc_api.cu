@@ -506,6 +506,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   if ((rc = ensure_arena(g, (size_t)need_one))) return rc;
 
   const int64_t max_T = 1 << 16;
+  std::vector<int64_t> redo;  // graph-row batch call: rows of the targets kernel 3v handed back
   size_t pos = 0;
   int64_t* h_tidx = reinterpret_cast<int64_t*>(h_chunk);
   int64_t* h_voff = h_tidx + (E + 2);
@@ -581,17 +582,17 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
       }
       if (fb1 != fb0) {
         // kernel 3v handed targets back: their edge-sorted sweep needs the adjacency
-        if (light) {  // no adjacency space was reserved: the whole call is redone on the materialised route
-          tlc_params up2 = *up;
-          up2.flags |= TLC_F_NO_DIRECT;
-          tm.collect(g->stage_ms);
-          return run_pipeline(g, d_targets, E, &up2, d_pi, d_pi32, d_status, cnt_compute, detail);
-        }
+        if (light) {  // no adjacency space was reserved: those targets are redone on the materialised route below
+          std::vector<uint8_t> fbv((size_t)T);
+          CK(cudaMemcpy(fbv.data(), c.tfb, (size_t)T, cudaMemcpyDeviceToHost));
+          for (int64_t k = 0; k < T; k++) if (fbv[(size_t)k]) redo.push_back(h_tidx[pos + k]);
+        } else {
         // the chunk is redone on the materialised route (its space is reserved), image rows and statuses are rewritten
         c.dbm = nullptr;
         c.W = 0;
         g->last_direct -= T;
         run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
+        }
       }
     } else {
       run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
@@ -629,6 +630,43 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
       CK(cudaStreamSynchronize(st));
     }
     pos = q;
+  }
+  if (!redo.empty()) {
+    // the handed-back targets of a graph-row call, as their own call on the materialised route; rows scattered back
+    const int64_t k = (int64_t)redo.size();
+    std::vector<int32_t> h_all((size_t)E * 2), h_sub((size_t)k * 2);
+    CK(cudaMemcpy(h_all.data(), d_targets, (size_t)E * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < k; i++) { h_sub[2 * i] = h_all[2 * redo[i]]; h_sub[2 * i + 1] = h_all[2 * redo[i] + 1]; }
+    int32_t* d_sub = nullptr; int64_t* d_idx = nullptr; double* s_pi = nullptr; float* s_pi32 = nullptr; uint8_t* s_st = nullptr;
+    CK(cudaMalloc((void**)&d_sub, (size_t)k * 8));
+    CK(cudaMalloc((void**)&d_idx, (size_t)k * 8));
+    CK(cudaMalloc((void**)&s_pi, (size_t)k * r2 * 8));
+    CK(cudaMalloc((void**)&s_pi32, (size_t)k * r2 * 4));
+    CK(cudaMalloc((void**)&s_st, (size_t)k));
+    CK(cudaMemcpy(d_sub, h_sub.data(), (size_t)k * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_idx, redo.data(), (size_t)k * 8, cudaMemcpyHostToDevice));
+    // keep this call's statistics: the sub-call resets them
+    const int64_t o_live = g->last_live, o_nv = g->last_nv, o_ne = g->last_ne, o_direct = g->last_direct;
+    const int o_chunks = g->nchunks;
+    const double o_bytes = g->alg_bytes;
+    double o_ms[10];
+    tm.collect(g->stage_ms);
+    for (int i = 0; i < 10; i++) o_ms[i] = g->stage_ms[i];
+    tlc_params up2 = *up;
+    up2.flags = (up2.flags | TLC_F_NO_DIRECT) & ~TLC_F_DIRECT;
+    rc = run_pipeline(g, d_sub, k, &up2, s_pi, s_pi32, s_st, nullptr, nullptr);
+    if (rc == TLC_OK) {
+      launch_scatter_rows(s_pi, d_pi32 ? s_pi32 : nullptr, d_status ? s_st : nullptr, d_idx, k, r2, d_pi, d_pi32, d_status,
+                          g->sm_count, st);
+      cudaStreamSynchronize(st);
+    }
+    cudaFree(d_sub); cudaFree(d_idx); cudaFree(s_pi); cudaFree(s_pi32); cudaFree(s_st);
+    if (rc) return rc;
+    const int64_t sub_fb = g->last_fb;
+    g->last_live = o_live; g->last_nv = o_nv; g->last_ne = o_ne; g->last_direct = o_direct - k; g->alg_bytes = o_bytes;
+    g->nchunks += o_chunks;
+    for (int i = 0; i < 10; i++) g->stage_ms[i] += o_ms[i];
+    (void)sub_fb;  // (the sweep counters read back below are the sub-call's: the same k targets handed back again)
   }
   if (g->timing) {
     cudaEventRecord(ev_total1, st);

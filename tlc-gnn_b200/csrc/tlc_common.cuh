@@ -196,6 +196,9 @@ void launch_pimg_single(const double* dgm, int64_t K, int res, double* out, cuda
 void launch_gather_rows(const double* table, int64_t rows, int r2, const int64_t* index, int64_t start, int64_t n,
                         float* out, int* bad, int sm_count, cudaStream_t st);
 
+void launch_scatter_rows(const double* src_pi, const float* src_pi32, const uint8_t* src_st, const int64_t* idx, int64_t k,
+                         int r2, double* dst_pi, float* dst_pi32, uint8_t* dst_st, int sm_count, cudaStream_t st);
+
 int64_t launch_count();
 void count_launch();
 int vicinity_grid(int device, const GraphView& g, const Params& p, size_t* bitmap_words, bool* use_smem);
