@@ -36,7 +36,10 @@ def test_binding_constants_match_header():
     for k, v in [("TLC_F_NORM", L.F_NORM), ("TLC_F_EXTENDED", L.F_EXTENDED), ("TLC_F_KEEP_ZERO", L.F_KEEP_ZERO),
                  ("TLC_F_NORM_EPS", L.F_NORM_EPS), ("TLC_F_SUM_PLAIN", L.F_SUM_PLAIN), ("TLC_F_EDGE_SORTED", L.F_EDGE_SORTED),
                  ("TLC_MODE_EDGE", L.MODE_EDGE), ("TLC_MODE_NODE", L.MODE_NODE), ("TLC_K_UP", L.K_UP), ("TLC_K_ONE", L.K_ONE),
-                 ("TLC_ST_OK", L.ST_OK), ("TLC_ST_NO_TREE_EDGES", L.ST_NO_TREE_EDGES), ("TLC_DESC_SUM", L.DESC["sum"])]:
+                 ("TLC_ST_OK", L.ST_OK), ("TLC_ST_NO_TREE_EDGES", L.ST_NO_TREE_EDGES), ("TLC_DESC_SUM", L.DESC["sum"]),
+                 ("TLC_MODE_EDGE_FORCED", L.MODE_EDGE_FORCED), ("TLC_F_NO_DIRECT", L.F_NO_DIRECT), ("TLC_F_DIRECT", L.F_DIRECT),
+                 ("TLC_F_ASC_ONLY", L.F_ASC_ONLY), ("TLC_F_FILT_DEGREE", L.F_FILT_DEGREE),
+                 ("TLC_F_FILT_CENTRALITY", L.F_FILT_CENTRALITY)]:
         assert int(macros[k]) == v, k
     assert C.sizeof(L.Params) == 24
 
@@ -81,3 +84,30 @@ def test_cache_filename_mapping():
     assert cache_filename("photo") == "./data/TLCGNN/Photo.npy"
     assert cache_filename("computers") == "./data/TLCGNN/Computers.npy"
     assert cache_filename("PubMed", "/x") == "/x/PubMed.npy"
+
+
+def test_oracle_and_binding_flag_values_agree():
+    """tests pass one flag word to both sides: the oracle's TLO_* and the library's TLC_* values must coincide."""
+    import oracle as orc
+    for name in ("F_NORM", "F_EXTENDED", "F_KEEP_ZERO", "F_NORM_EPS", "F_SUM_PLAIN", "F_FILT_DEGREE", "F_FILT_CENTRALITY",
+                 "MODE_EDGE", "MODE_NODE", "MODE_EDGE_FORCED"):
+        assert getattr(orc, name) == getattr(L, name), name
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference algorithm on the host cores) runs without a GPU and prints ONE JSON
+    line with the contract's keys; a tiny workload keeps it to seconds."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cora",
+                          "--steps", "1", "--warmup", "0", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
