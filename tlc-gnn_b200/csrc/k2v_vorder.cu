@@ -52,13 +52,23 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   uint32_t* k1 = reinterpret_cast<uint32_t*>(c.v64b + vo);
   uint32_t* p0 = reinterpret_cast<uint32_t*>(c.vs0 + vo);
   uint32_t* p1 = reinterpret_cast<uint32_t*>(c.vs1 + vo);
+  // normalised filtrations live in [0, 1]: a 24-bit fixed-point image floor(f * 2^24) is monotone too and saves a radix
+  // pass; collisions (values closer than 6e-8) are equal-key runs, fixed below exactly like equal floats
+  int out_of_unit = 0;
+  for (int x = tid; x < n; x += nt) { const double f = fval[x]; out_of_unit |= !(f >= 0.0 && f <= 1.0); }
+  const bool unit = __syncthreads_or(out_of_unit) == 0;
   for (int x = tid; x < n; x += nt) {
-    const uint32_t b = (uint32_t)__float_as_int(__double2float_rd(fval[x]));
-    k0[x] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    if (unit) {
+      const double q = floor(fval[x] * 16777216.0);
+      k0[x] = q >= 16777215.0 ? 16777215u : (uint32_t)q;
+    } else {
+      const uint32_t b = (uint32_t)__float_as_int(__double2float_rd(fval[x]));
+      k0[x] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    }
     p0[x] = x;
   }
   __syncthreads();
-  const int r = block_radix_sort<uint32_t>(k0, p0, k1, p1, n, 32, sh);
+  const int r = block_radix_sort<uint32_t>(k0, p0, k1, p1, n, unit ? 24 : 32, sh);
   const uint32_t* kf = r ? k1 : k0;
   uint32_t* ps = r ? p1 : p0;
   int32_t* need = c.vs2 + vo;  // need[s] = 1: the run of equal floats starting at s holds distinct float64 values
