@@ -436,7 +436,9 @@ def run_cuda(args):
                     "kernel_ms_per_step": dom_ms / max(1, args.steps),
                     "note": "achieved = algorithmic bytes of the dominant stage kernel over the step's targets (DESIGN.md "
                             "section 4) / its device time (CUDA events on the library's stream); traffic = ncu dram bytes "
-                            "of the same kernel scaled to the step's targets",
+                            "of the same kernel scaled to the step's targets.  On the graph-row route the rows come from "
+                            "the L2-resident CSR, so DRAM traffic is far below the algorithmic bytes: the HBM roof is the "
+                            "contractual yardstick, the kernel itself is issue/latency bound (DESIGN.md section 6)",
                     "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()},
                     "stage_alg_gbytes_per_step": {k: v / 1e9 / args.steps for k, v in sab.items()},
                     "whole_path": {"compulsory_bytes_per_target": alg_bytes / max(1, live),
