@@ -106,7 +106,7 @@ struct DirectArgs {
 };
 
 template <bool DIRECT, bool SMEM>
-__global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap, DirectArgs da) {
+__global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap, int bpv, DirectArgs da) {
   extern __shared__ unsigned long long dyn64[];
   __shared__ FiltShared sh;
   const int t = t0 + blockIdx.x;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   const bool node_mode = p.mode == TLC_MODE_NODE;
   const int64_t vo = c.voff[t];
   // graph-row route: vicinity bitmap [0, W) and word-prefix ranks [W, 2W), behind the per-vertex arrays
-  uint32_t* bm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dyn64) + (size_t)cap * 11);
+  uint32_t* bm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dyn64) + (size_t)cap * bpv);
   const int W = da.W;
   int n, lu, lv;
   if (DIRECT) {
@@ -213,8 +213,13 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
     // state lives in the arena.  A compile-time switch, so that the shared-memory accesses are LDS / ATOMS, not generic
     constexpr bool in_smem = SMEM;
     unsigned long long* dist = SMEM ? dyn64 : c.v64a + vo;
-    __half* smw = reinterpret_cast<__half*>(dyn64 + cap);  // (shared-memory route only) smallest incident weight, rounded down
-    uint8_t* state = SMEM ? reinterpret_cast<uint8_t*>(smw + cap) : reinterpret_cast<uint8_t*>(c.vs1 + vo);
+    // shared-memory state per vertex: dist (8 B), state (1 B) and -- unless the launch went LEAN to fit a very large
+    // vicinity (bpv == 9) -- the settling margin as a half rounded down (2 B); lean launches read the float margin
+    // from the arena instead (coalesced, once per tentative vertex and phase)
+    const bool margins_in_smem = SMEM && bpv == 11;
+    __half* smw = reinterpret_cast<__half*>(dyn64 + cap);
+    uint8_t* state = SMEM ? (margins_in_smem ? reinterpret_cast<uint8_t*>(smw + cap) : reinterpret_cast<uint8_t*>(dyn64 + cap))
+                          : reinterpret_cast<uint8_t*>(c.vs1 + vo);
     int32_t* tpar = c.vs2 + vo;                            // shortest-path tree: parent and weight of the parent edge
     double* tpw = reinterpret_cast<double*>(c.v64b + vo);
     const float* __restrict__ aminw = c.aminw + vo;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
       double* out = r == 0 ? d1 : d2;
       for (int x = tid; x < n; x += nt) {
         dist[x] = INF_BITS; state[x] = FAR; tpar[x] = root; tpw[x] = 0.0;
-        if (in_smem && r == 0) smw[x] = __float2half_rd(fminf(aminw[x], 60000.f));  // rounded DOWN: the criterion stays valid
+        if (margins_in_smem && r == 0) smw[x] = __float2half_rd(fminf(aminw[x], 60000.f));  // rounded DOWN: the criterion stays valid
       }
       if (tid == 0) { sh.nmin[0] = 0ull; sh.nmin[1] = INF_BITS; sh.qn[0] = 0; sh.qn[1] = 0; }
       __syncthreads();
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
           unsigned long long d = INF_BITS;
           if (x < n && state[x] == TENT) {
             d = dist[x];
-            const double mw = in_smem ? (double)__half2float(smw[x]) : (double)aminw[x];
+            const double mw = margins_in_smem ? (double)__half2float(smw[x]) : (double)aminw[x];
             take = __longlong_as_double((long long)d) <= __dadd_rn(dmin, mw);
           }
           const unsigned bal = __ballot_sync(0xffffffffu, take);
@@ -446,16 +451,19 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
   // dist (8) + minw (2) + state (1) bytes per vertex in shared memory when the sub-range's largest vicinity fits;
   // graph-row route: + the vicinity bitmap and its word-prefix ranks
   size_t bmb = DIRECT ? (size_t)2 * da.W * 4 : 0;
+  constexpr size_t BUDGET = 208 * 1024;  // dynamic shared memory next to the 17 KB of static queues (227 KB per CTA)
   int cap = (int)((n_max + 7) / 8 * 8);
-  if ((size_t)cap * 11 + bmb > 190 * 1024) cap = 0;
+  int bpv = 11;
+  if ((size_t)cap * 11 + bmb > 190 * 1024) bpv = 9;            // very large vicinity: lean state (margins stay in the arena)
+  if ((size_t)cap * bpv + bmb > BUDGET) cap = 0;               // larger still: per-vertex state in the arena
   DirectArgs da2 = da;
   if (DIRECT) {  // the graph id -> local id table, when it fits next to the per-vertex state
     const size_t lidb = ((size_t)da.g.N + 1) / 2 * 4;
-    da2.lid_table = (n_max < 65535 && cap > 0 && (size_t)cap * 11 + bmb + lidb <= 190 * 1024) ? 1 : 0;
+    da2.lid_table = (n_max < 65535 && cap > 0 && (size_t)cap * bpv + bmb + lidb <= 190 * 1024) ? 1 : 0;
     if (getenv("TLC_NO_LID")) da2.lid_table = 0;  // (tuning experiments)
     if (da2.lid_table) bmb += lidb;
   }
-  const size_t bytes = (size_t)cap * 11 + bmb;
+  const size_t bytes = (size_t)cap * bpv + bmb;
   if (DIRECT && block < 128) block = 128;  // the prologue walks the bitmap a warp per word
   // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
   if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
@@ -463,7 +471,7 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
   auto go = [&](auto kern) {
     cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<cnt, block, bytes, st>>>(p, c, t0, cap, da2);
+    kern<<<cnt, block, bytes, st>>>(p, c, t0, cap, bpv, da2);
   };
   if (cap > 0) go(filtration_kernel<DIRECT, true>);
   else go(filtration_kernel<DIRECT, false>);

@@ -94,7 +94,36 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   int cur_first = 0, nxt_first = 0;
   if (lane <= nb) nxt_first = bfirst[lane];
   int carry = 0;  // bfirst[b] of the current block (flags), handed over from the previous iteration
-  for (int b = 0; b < nb && !bail; b++) {
+  bool one_block = false;
+  if (nb == 1 && !keep0) {
+    // ONE block: every vertex carries the same value (e.g. both roots outside the vicinity: all distances 100).  No merge
+    // can emit a pair (`old[large] < old[max_node]` never holds, accelerated_PD.py:65), so only connectivity matters
+    // (riccidist2dgm.py:318): a warp-parallel breadth-first search from rank 0 instead of m sequential unions.
+    // parent[r] == 0 marks "reached" (rank 0 itself included).
+    one_block = true;
+    int32_t* queue = c.vs0 + vo;  // (kernel 2v's sort payload: free by now)
+    if (lane == 0) queue[0] = 0;
+    __syncwarp();
+    int head = 0, tail = 1;
+    while (head < tail) {
+      const int lx = vord[queue[head++]];
+      const int a = astart[lx], dg = adeg[lx];
+      for (int j0 = 0; j0 < dg; j0 += 32) {
+        const int j = j0 + lane;
+        int ry = -1;
+        if (j < dg) {
+          const int ly = nbr(a + j);
+          if (ly >= 0) { ry = vrank[ly]; if (parent[ry] == 0) ry = -1; }
+        }
+        const unsigned bal = __ballot_sync(FULL, ry >= 0);
+        if (ry >= 0) { parent[ry] = (PT)0; queue[tail + __popc(bal & lanemask_lt())] = ry; }
+        tail += __popc(bal);
+        __syncwarp();
+      }
+    }
+    nmerge = tail - 1;
+  }
+  for (int b = 0; b < nb && !bail && !one_block; b++) {
     if ((b & 31) == 0) {
       cur_first = nxt_first;
       const int i = b + 32 + lane;
@@ -285,6 +314,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
           if (!__all_sync(FULL, ok)) bail = true;
           __syncwarp();
           // stage 2: in-block edges in canonical order
+          int stage2_edges = 0;
           for (int x = s; x < e && !bail; x++) {
             const int lx = vord[x];
             const int xa = astart[lx], xdg = adeg[lx];
@@ -308,6 +338,9 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
                 if (ly >= 0) { const int y = vrank[ly]; if (!(y > x && y < e)) ly = -1; }
               }
               unsigned mk = __ballot_sync(FULL, ly >= 0);
+              // the in-block unions run on one lane: a block with thousands of them goes to the edge-sorted kernels instead
+              stage2_edges += __popc(mk);
+              if (stage2_edges > 4096) { bail = true; break; }
               while (mk) {
                 const int i = __ffs(mk) - 1;
                 mk &= mk - 1;

@@ -267,6 +267,9 @@ static int block_for(int64_t m_max) {
   return 32;
 }
 static int size_class(int64_t m) { return block_for(m); }
+// kernel 1b keeps 9 - 11 bytes of state per vertex in shared memory: 0 = does not fit at all (state in the arena),
+// 1 = fits only in the lean layout, 2 = fits (thresholds a little under the kernel's own limits, which also hold bitmaps)
+static int smem_class(int64_t n) { return n > 22000 ? 0 : (n > 16000 ? 1 : 2); }
 
 struct StageTimer {
   bool on;
@@ -328,8 +331,10 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   // sweep is wanted (diagram output, Pos/Neg lists for the loops), the edge-sorted kernels 2 + 3.  The image
   // only needs PD_up and [min,max]: PD_down and [max,min] have death <= birth, i.e. weight 0.
   const bool ext = (p.flags & TLC_F_EXTENDED) != 0;
-  const bool edge_sorted = (p.flags & TLC_F_EDGE_SORTED) != 0;
   const bool want_desc = (ext || want_lists) && !(p.flags & TLC_F_ASC_ONLY);
+  // keep-zero calls (PDGNN generators) that sort the edges anyway for the descending sweep: the vertex-ordered sweep has
+  // no trivial blocks there (every merge emits a pair), so the ascending sweep rides on the edge-sorted kernels too
+  const bool edge_sorted = (p.flags & TLC_F_EDGE_SORTED) != 0 || ((p.flags & TLC_F_KEEP_ZERO) != 0 && want_desc);
   tm.mark(3);
   if (edge_sorted) {
     cudaMemsetAsync(c.tfb, 1, (size_t)c.T, st);
@@ -484,9 +489,13 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   } else {
     for (int64_t i = 0; i < E; i++) if (h_st[i] == TLC_ST_OK) order.push_back(i);
     // graph-row targets first (chunks are route-homogeneous), each group largest first
+    // ... and, ahead of everything, the few vicinities too large for kernel 1b's shared-memory state (heavy-tailed
+    // graphs): they get sub-ranges of their own (below) instead of dragging a whole size group onto the arena path
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
       const bool da = is_direct(a), db = is_direct(b);
       if (da != db) return da;
+      const int ca = smem_class(h_n[a]), cb = smem_class(h_n[b]);
+      if (ca != cb) return ca < cb;
       if (h_m[a] != h_m[b]) return h_m[a] > h_m[b];
       return h_n[a] > h_n[b];
     });
@@ -559,8 +568,22 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     {
       int groups = T >= 4 * 2 * g->sm_count ? 4 : (T >= 2 * 2 * g->sm_count ? 2 : 1);
       if (const char* env = getenv("TLC_SUBGROUPS")) groups = std::max(1, std::min(4, atoi(env)));  // (tuning experiments)
-      for (int gi = 0; gi < groups; gi++) {
-        const int64_t a = T * gi / groups, b = T * (gi + 1) / groups;
+      // the shared-memory classes first (a chunk is sorted by them), then the rest in `groups` equal parts
+      int64_t first = 0;
+      for (int cls = 0; cls < 2; cls++) {
+        int64_t b = first;
+        while (b < T && smem_class(h_n[order[pos + b]]) == cls) b++;
+        if (b > first) {
+          int64_t nm = 0;
+          for (int64_t k = first; k < b; k++) nm = std::max<int64_t>(nm, h_n[order[pos + k]]);
+          subs.push_back(SubRange{(int)first, (int)(b - first), nm});
+          first = b;
+        }
+      }
+      const int64_t rest = T - first;
+      for (int gi = 0; gi < groups && rest > 0; gi++) {
+        const int64_t a = first + rest * gi / groups, b = first + rest * (gi + 1) / groups;
+        if (b <= a) continue;
         int64_t nm = 0;
         for (int64_t k = a; k < b; k++) nm = std::max<int64_t>(nm, h_n[order[pos + k]]);
         subs.push_back(SubRange{(int)a, (int)(b - a), nm});
