@@ -130,6 +130,10 @@ class ClockSampler:
         except Exception:
             self.h = None
         self.th = threading.Thread(target=self._loop, daemon=True)
+
+    def start(self):
+        """begin polling (NVML was initialised in the constructor, outside the timed region: on rank 0 that takes
+        ~10 ms, which the other ranks would otherwise spend waiting in the first all-gather of the timed region)"""
         self.th.start()
 
     @staticmethod
@@ -334,13 +338,15 @@ def run_cuda(args):
     batches = [step(s) for s in range(args.warmup + args.steps)]
     for s in range(args.warmup):
         run(batches[s])
+    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     stage_acc = {}
     alg_bytes = 0.0
     handed_back = 0
     sum_n = sum_m = live = 0
     launches0 = api.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # library kernels, the all-gather and these events are all on torch's current stream
     ev0.record()
