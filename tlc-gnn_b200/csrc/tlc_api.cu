@@ -144,8 +144,15 @@ static int ensure_io_buffers(tlc_graph* g, int64_t E, int r2) {
   return TLC_OK;
 }
 
-static int ensure_arena(tlc_graph* g, size_t need_min) {
-  if (g->arena && g->arena_bytes >= need_min) return TLC_OK;
+// grow-only arena: at least `need_min` (one chunk must fit), preferably `need_all` (the whole call in one chunk), never
+// more than the configured size (tlc_graph_create's arena_bytes, TLC_ARENA_GB, default 24 GiB) or 85 % of free memory
+static int ensure_arena(tlc_graph* g, size_t need_min, size_t need_all) {
+  if (g->arena && g->arena_bytes >= need_min) {
+    // large enough for a chunk; grow only if the call would otherwise be split and there is headroom left
+    size_t limit = g->arena_req;
+    if (limit == 0) { const char* env = getenv("TLC_ARENA_GB"); limit = (size_t)((env ? atof(env) : 24.0) * (double)(1ull << 30)); }
+    if (g->arena_bytes >= std::min(need_all, limit)) return TLC_OK;
+  }
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   if (g->arena) { free_b += g->arena_bytes; cudaFree(g->arena); g->arena = nullptr; g->arena_bytes = 0; }
@@ -155,7 +162,7 @@ static int ensure_arena(tlc_graph* g, size_t need_min) {
     const double gb = env ? atof(env) : 24.0;
     want = (size_t)(gb * (double)(1ull << 30));
   }
-  want = std::max(want, need_min);
+  want = std::max(std::min(want, need_all + need_all / 2), need_min);  // (no 24 GiB for a handful of small vicinities; 50 % headroom: calls of similar size do not reallocate)
   const size_t cap = (size_t)((double)free_b * 0.85);
   if (want > cap) want = cap;
   if (want < need_min)
@@ -515,7 +522,13 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
       return fail(TLC_E_CAPACITY, "detail capacity too small: need v=" + std::to_string(Nv) + " e=" +
                                       std::to_string(Ne) + " p=" + std::to_string(Nv + Ne + E));
   }
-  if ((rc = ensure_arena(g, (size_t)need_one))) return rc;
+  size_t need_all = (size_t)need_one;
+  if (!detail) {
+    int64_t Nv = 0, Ne = 0, Na = 0;
+    for (int64_t i : order) { Nv += h_n[i]; if (!light) { Ne += h_m[i]; Na += h_ds[i]; } }
+    need_all = std::max(need_all, chunk_bytes((int64_t)order.size(), Nv, Ne, Na, call_direct ? Wd : 0));
+  }
+  if ((rc = ensure_arena(g, (size_t)need_one, need_all))) return rc;
 
   const int64_t max_T = 1 << 16;
   std::vector<int64_t> redo;  // graph-row batch call: rows of the targets kernel 3v handed back
