@@ -140,19 +140,6 @@ __device__ __forceinline__ int32_t local_id(const uint32_t* iw, const uint32_t* 
   return (int32_t)wbase[y >> 5] + __popc(iw[y >> 5] & ((1u << (y & 31)) - 1u));
 }
 
-// A batch = the vicinity vertices of one bitmap word: lane k holds the CSR row (start ra, degree dg) of vertex
-// 32*w + k (dg = 0 if the bit is clear).  The rows are walked as ONE concatenated sequence, 32 consecutive entries
-// per step, so every load of a step is independent of the previous step; `inc` is the inclusive degree prefix.
-__device__ __forceinline__ int batch_row_of(int inc, int e) {  // smallest lane r with inc[r] > e   (warp-wide)
-  int r = 0;
-#pragma unroll
-  for (int s = 16; s; s >>= 1) {
-    const int v = __shfl_sync(0xffffffffu, inc, (r + s - 1) & 31);
-    if (v <= e) r += s;
-  }
-  return r;
-}
-
 // ---- ball cache ----
 __global__ void ball_mark_kernel(const int32_t* __restrict__ targets, int64_t E, int node_mode, GraphView g,
                                  VicinityScratch vs) {
@@ -246,7 +233,7 @@ vicinity_kernel(GraphView g, Params p, const int32_t* __restrict__ targets, int6
                 int W, int bm_in_smem) {
   extern __shared__ uint32_t dyn_smem[];
   __shared__ K1Shared sh;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
   uint32_t* bm_u = bm_in_smem ? dyn_smem : vs.bitmaps + (size_t)blockIdx.x * 2 * W;
   uint32_t* bm_v = bm_u + W;
   int32_t* q0 = vs.queue ? vs.queue + (size_t)blockIdx.x * 2 * g.N : nullptr;

@@ -211,7 +211,6 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   } else {
     // SMEM: the launch sized shared memory for the sub-range's largest vicinity (n <= cap); otherwise the per-vertex
     // state lives in the arena.  A compile-time switch, so that the shared-memory accesses are LDS / ATOMS, not generic
-    constexpr bool in_smem = SMEM;
     unsigned long long* dist = SMEM ? dyn64 : c.v64a + vo;
     // shared-memory state per vertex: dist (8 B), state (1 B) and -- unless the launch went LEAN to fit a very large
     // vicinity (bpv == 9) -- the settling margin as a half rounded down (2 B); lean launches read the float margin

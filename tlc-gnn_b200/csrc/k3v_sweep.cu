@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   if (t >= tend) return;
   const int n = c.tn[t];
   if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
-  const int64_t vo = c.voff[t], eo = c.eoff[t], po = c.poff(t);
+  const int64_t vo = c.voff[t], po = c.poff(t);
   const int32_t* __restrict__ vord = c.vord + vo;
   const int32_t* __restrict__ vrank = c.vrank + vo;
   const int32_t* __restrict__ bfirst = c.bfirst + vo + t;
