@@ -231,6 +231,7 @@ def kd_cases():
     make_kd_case("kd_ppi_s_hop1", c["edges"], c["kappa"], nodes, 1)
     make_kd_case("kd_ppi_s_hop1_degree", c["edges"], c["kappa"], nodes[:10], 1, filt_name="degree")          # :126-128
     make_kd_case("kd_ppi_s_hop1_centrality", c["edges"], c["kappa"], nodes[:10], 1, filt_name="centrality")  # :118-121
+    make_kd_case("kd_ppi_s_hop1_clustering", c["edges"], c["kappa"], nodes[:8], 1, filt_name="clustering")   # :122-125
     c = gg.make_config("pubmed", scale=0.05, continuous=True)
     un = np.unique(c["edges"])
     nodes = un[np.random.default_rng(22).choice(len(un), 24, replace=False)]

@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "libtlc_oracle.so")
 MODE_EDGE, MODE_NODE, MODE_EDGE_FORCED = 0, 1, 2
 DESC = {"min": 0, "max": 1, "sum": 2}
 F_NORM, F_EXTENDED, F_KEEP_ZERO, F_NORM_EPS, F_SUM_PLAIN, F_ASIS_FV = 1, 2, 4, 8, 16, 32
-F_FILT_DEGREE, F_FILT_CENTRALITY = 512, 1024
+F_FILT_DEGREE, F_FILT_CENTRALITY, F_FILT_CLUSTERING = 512, 1024, 2048
 K_UP, K_ESS, K_DOWN, K_ESS_REV, K_ONE = 0, 1, 2, 3, 4
 ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NODE", "BAD_DESCRIPTOR", "NO_TREE_EDGES"]
 

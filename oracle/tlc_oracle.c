@@ -40,6 +40,7 @@
 #define TLO_F_ASIS_FV 32u     /* build_fv as written: one Dijkstra per (vertex, root)  :27-37           */
 #define TLO_F_FILT_DEGREE 512u      /* KD filt='degree'    : induced degree / (max + 1e-10)   data_utils_NC.py:126-128 */
 #define TLO_F_FILT_CENTRALITY 1024u /* KD filt='centrality': nx.degree_centrality / (max + 1e-10)     :118-121 */
+#define TLO_F_FILT_CLUSTERING 2048u /* KD filt='clustering': nx.clustering / (max + 1e-10)            :122-125 */
 
 /* pair kinds, in the order the reference concatenates them (accelerated_PD.py:110, riccidist2dgm.py:328) */
 #define TLO_K_UP 0
@@ -491,6 +492,31 @@ static int run_target(const tlo_graph *g, int32_t u, int32_t v, const tlo_params
       if (p->flags & TLO_F_NORM) f = f / (p->descriptor == TLO_DESC_SUM ? ssum : smax);
       w->fval[x] = f;
     }
+  }
+  if (p->flags & TLO_F_FILT_CLUSTERING) {
+    /* nx.clustering (unweighted): t / (d * (d - 1)) with t = sum over neighbours w of |N(v) & N(w)| (= twice the
+       triangles through v), 0 when t == 0; python int / int = the correctly rounded quotient.   networkx cluster.py
+       then fv / (max_val + 1e-10)                                                        data_utils_NC.py:122-125 */
+    double mx = -INFINITY;
+    for (int32_t x = 0; x < n; x++) {
+      const int32_t a0 = w->rowl[x], a1 = w->rowl[x + 1];
+      long long t = 0;
+      for (int32_t e = a0; e < a1; e++) {
+        const int32_t y = w->adj[e];
+        /* both local rows ascend?  adj rows hold lower neighbours first then higher, each ascending: ascending overall */
+        int32_t i = a0, j = w->rowl[y];
+        const int32_t j1 = w->rowl[y + 1];
+        while (i < a1 && j < j1) {
+          const int32_t u1 = w->adj[i], u2 = w->adj[j];
+          if (u1 == u2) { t++; i++; j++; } else if (u1 < u2) i++; else j++;
+        }
+      }
+      const long long d = a1 - a0;
+      const double cval = t == 0 ? 0.0 : (double)t / (double)(d * (d - 1));
+      w->fval[x] = cval;
+      if (cval > mx) mx = cval;
+    }
+    for (int32_t x = 0; x < n; x++) w->fval[x] = w->fval[x] / (mx + 1e-10);
   }
   if (p->flags & (TLO_F_FILT_DEGREE | TLO_F_FILT_CENTRALITY)) {
     /* the PDGNN generators' structural filtrations: no roots, no distances

@@ -34,7 +34,8 @@ def rel_err(a, ref):
     return float(np.max(np.abs(a - ref) / den)) if a.size else 0.0
 
 
-KD_CASES = ["kd_ppi_s_hop1", "kd_pubmed_s_hop2_cont", "kd_pubmed_s_hop0", "kd_ppi_s_hop1_degree", "kd_ppi_s_hop1_centrality"]
+KD_CASES = ["kd_ppi_s_hop1", "kd_pubmed_s_hop2_cont", "kd_pubmed_s_hop0", "kd_ppi_s_hop1_degree", "kd_ppi_s_hop1_centrality",
+            "kd_ppi_s_hop1_clustering"]
 KD_LP_CASES = ["kd_lp_pubmed_s_hop2_cont", "kd_lp_ppi_s_hop1"]  # edge-centred generator (data_utils_LP.py), nodes = [pairs, 2]
 
 

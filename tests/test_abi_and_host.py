@@ -39,7 +39,7 @@ def test_binding_constants_match_header():
                  ("TLC_ST_OK", L.ST_OK), ("TLC_ST_NO_TREE_EDGES", L.ST_NO_TREE_EDGES), ("TLC_DESC_SUM", L.DESC["sum"]),
                  ("TLC_MODE_EDGE_FORCED", L.MODE_EDGE_FORCED), ("TLC_F_NO_DIRECT", L.F_NO_DIRECT), ("TLC_F_DIRECT", L.F_DIRECT),
                  ("TLC_F_ASC_ONLY", L.F_ASC_ONLY), ("TLC_F_FILT_DEGREE", L.F_FILT_DEGREE),
-                 ("TLC_F_FILT_CENTRALITY", L.F_FILT_CENTRALITY)]:
+                 ("TLC_F_FILT_CENTRALITY", L.F_FILT_CENTRALITY), ("TLC_F_FILT_CLUSTERING", L.F_FILT_CLUSTERING)]:
         assert int(macros[k]) == v, k
     assert C.sizeof(L.Params) == 24
 
@@ -89,7 +89,7 @@ def test_cache_filename_mapping():
 def test_oracle_and_binding_flag_values_agree():
     """tests pass one flag word to both sides: the oracle's TLO_* and the library's TLC_* values must coincide."""
     import oracle as orc
-    for name in ("F_NORM", "F_EXTENDED", "F_KEEP_ZERO", "F_NORM_EPS", "F_SUM_PLAIN", "F_FILT_DEGREE", "F_FILT_CENTRALITY",
+    for name in ("F_NORM", "F_EXTENDED", "F_KEEP_ZERO", "F_NORM_EPS", "F_SUM_PLAIN", "F_FILT_DEGREE", "F_FILT_CENTRALITY", "F_FILT_CLUSTERING",
                  "MODE_EDGE", "MODE_NODE", "MODE_EDGE_FORCED"):
         assert getattr(orc, name) == getattr(L, name), name
 

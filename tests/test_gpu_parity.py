@@ -288,7 +288,7 @@ def test_edge_forced_mode_kd_flags():
     g.close()
 
 
-@pytest.mark.parametrize("filt", ["degree", "centrality"])
+@pytest.mark.parametrize("filt", ["degree", "centrality", "clustering"])
 def test_structural_filtrations(filt):
     """PDGNN generators' filt='degree' / 'centrality' (Knowledge_Distillation/data_utils_NC.py:118-128), node and edge-forced modes."""
     c = gg.make_config("ppi", scale=0.25)
@@ -298,7 +298,7 @@ def test_structural_filtrations(filt):
     og = orc.OracleGraph(*csr)
     rng = np.random.default_rng(8)
     nodes = rng.choice(len(labels), 16, replace=False)
-    ff = {"degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY}[filt]
+    ff = {"degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY, "clustering": L.F_FILT_CLUSTERING}[filt]
     flags = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS | ff
     compare_detail(g, og, np.stack([nodes, nodes], 1).astype(np.int32), 1, "sum", flags, flags, mode=L.MODE_NODE)
     tg = ne[rng.choice(len(ne), 16, replace=False)].astype(np.int32)

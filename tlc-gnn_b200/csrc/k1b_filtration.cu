@@ -444,6 +444,45 @@ __global__ void __launch_bounds__(256) degree_filtration_kernel(Params p, ChunkV
   for (int x = tid; x < n; x += nt) fval[x] = __ddiv_rn(fval[x], m);
 }
 
+// nx.clustering as a filtration (Knowledge_Distillation/data_utils_NC.py:122-125): c(v) = t / (d (d - 1)), t = sum over the
+// neighbours w of |N(v) & N(w)| (twice the triangles through v), 0 when t == 0, then / (max + 1e-10).  One CTA per
+// vicinity, a warp per vertex: for every neighbour w the lanes take the entries of w's (ascending) induced row and
+// look each up in v's row by bisection.
+__global__ void __launch_bounds__(256) clustering_filtration_kernel(Params p, ChunkView c) {
+  __shared__ double redd[32];
+  const int t = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int n = c.tn[t];
+  if (n == 0 || c.tstatus[t] > TLC_ST_TRIVIAL) return;
+  const int64_t vo = c.voff[t], ao = c.aoff[t];
+  const int32_t* __restrict__ astart = c.astart + vo;
+  const int32_t* __restrict__ adeg = c.adeg + vo;
+  const uint32_t* __restrict__ anb = c.anb + ao;
+  double* fval = c.fval + vo;
+  double mx = -1.0;
+  for (int x = wid; x < n; x += nw) {
+    const int xa = astart[x], xd = adeg[x];
+    long long tri = 0;
+    for (int e = 0; e < xd; e++) {
+      const int y = (int)anb[xa + e];
+      const int ya = astart[y], yd = adeg[y];
+      for (int j = lane; j < yd; j += 32) {
+        const int z = (int)anb[ya + j];
+        int lo = 0, hi = xd;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)anb[xa + mid] < z) lo = mid + 1; else hi = mid; }
+        tri += (lo < xd && (int)anb[xa + lo] == z) ? 1 : 0;
+      }
+    }
+    for (int o = 16; o; o >>= 1) tri += __shfl_xor_sync(0xffffffffu, tri, o);
+    const long long d = xd;
+    const double cv = tri == 0 ? 0.0 : __ddiv_rn((double)tri, (double)(d * (d - 1)));
+    if (lane == 0) fval[x] = cv;
+    mx = fmax(mx, cv);
+  }
+  const double m = __dadd_rn(block_reduce_max(mx, redd), 1e-10);
+  for (int x = tid; x < n; x += nt) fval[x] = __ddiv_rn(fval[x], m);
+}
+
 template <bool DIRECT>
 static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max,
                                   const DirectArgs& da, cudaStream_t st) {
@@ -482,7 +521,8 @@ void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int
 }
 
 void launch_degree_filtration(const Params& p, const ChunkView& c, cudaStream_t st) {
-  degree_filtration_kernel<<<c.T, 256, 0, st>>>(p, c);
+  if (p.flags & TLC_F_FILT_CLUSTERING) clustering_filtration_kernel<<<c.T, 256, 0, st>>>(p, c);
+  else degree_filtration_kernel<<<c.T, 256, 0, st>>>(p, c);
   count_launch();
 }
 

@@ -321,7 +321,7 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   tm.mark(1);
   if (!c.dbm) launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
-  if (p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY)) launch_degree_filtration(p, c, st);
+  if (p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)) launch_degree_filtration(p, c, st);
   else {
     const bool fork = subs.size() > 1 && g->ev_fork != nullptr;
     if (fork) cudaEventRecord(g->ev_fork, st);
@@ -414,7 +414,7 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
   const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
   const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc && p.mode != TLC_MODE_EDGE_FORCED &&
-                         !(p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY)) &&
+                         !(p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)) &&
                          !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
   double direct_ratio = 2.0;
   if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);

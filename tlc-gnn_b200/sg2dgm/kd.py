@@ -7,8 +7,8 @@ Per node the reference returns the 9-tuple
      PD_time, PI_time)                                                                        (:183)
 or `(None, None)` when the ball has no edge (:103-104).  Here all nodes of a call go through ONE C-ABI call
 (`tlc_vicinity_detail`, node mode, KD flags: zero-persistence pairs kept, division by max + 1e-10, images of
-Ord0 u Ext1 / Ord0 / Ext1).  filt = 'ricci' (the hot path), 'degree' and 'centrality' (:118-128) are
-computed on the GPU; 'hks' (an eigendecomposition) and 'clustering' are not.
+Ord0 u Ext1 / Ord0 / Ext1).  filt = 'ricci' (the hot path), 'degree', 'centrality' and 'clustering' (:118-128)
+are computed on the GPU; 'hks' (an eigendecomposition) is not.
 
 Order conventions: the reference's local vertex numbering and pair order follow networkx's sub-graph view iteration
 (implementation-defined).  This mirror uses the canonical order: local ids ascending by graph id,
@@ -24,7 +24,7 @@ from tlc_b200 import _lib as L
 KD_FLAGS = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
 
 
-_FILT_FLAGS = {"ricci": 0, "degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY}   # data_utils_NC.py:115-142
+_FILT_FLAGS = {"ricci": 0, "degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY, "clustering": L.F_FILT_CLUSTERING}   # data_utils_NC.py:115-142
 
 
 def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False, filt="ricci"):
@@ -43,7 +43,7 @@ def compute_persistence_images_lp(g2pi, pairs, hop=2, resolution=5, as_torch=Fal
 
 def _emit(g2pi, targets, mode, hop, resolution, as_torch, filt="ricci"):
     if filt not in _FILT_FLAGS:
-        raise NotImplementedError("filt=%r: only 'ricci', 'degree', 'centrality' are on the GPU path (SURVEY.md row N3)" % (filt,))
+        raise NotImplementedError("filt=%r: only 'ricci', 'degree', 'centrality', 'clustering' are on the GPU path (SURVEY.md row N3)" % (filt,))
     tg = g2pi._map_targets(targets)
     G = g2pi._graph
     t0 = time.time()

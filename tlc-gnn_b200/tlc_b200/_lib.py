@@ -14,7 +14,7 @@ MODE_EDGE, MODE_NODE, MODE_EDGE_FORCED = 0, 1, 2
 DESC = {"min": 0, "max": 1, "sum": 2}
 F_NORM, F_EXTENDED, F_KEEP_ZERO, F_NORM_EPS, F_SUM_PLAIN, F_EDGE_SORTED = 1, 2, 4, 8, 16, 32
 F_NO_DIRECT, F_DIRECT, F_ASC_ONLY = 64, 128, 256
-F_FILT_DEGREE, F_FILT_CENTRALITY = 512, 1024
+F_FILT_DEGREE, F_FILT_CENTRALITY, F_FILT_CLUSTERING = 512, 1024, 2048
 K_UP, K_ESS, K_DOWN, K_ESS_REV, K_ONE = 0, 1, 2, 3, 4
 ST_OK, ST_TRIVIAL, ST_EMPTY, ST_DISCONNECTED, ST_DEGENERATE, ST_UNKNOWN_NODE, ST_BAD_DESCRIPTOR, ST_NO_TREE_EDGES = range(8)
 ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NODE", "BAD_DESCRIPTOR", "NO_TREE_EDGES"]
