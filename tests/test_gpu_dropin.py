@@ -157,3 +157,24 @@ def test_kd_gc_generator_matches_reference():
         assert np.array_equal(sorted_rows(ord0), sorted_rows(c["kd_ord0"][2 * o0[k]:2 * o0[k + 1]]))
         assert np.array_equal(sorted_rows(ext1), sorted_rows(c["kd_ext1"][2 * o1[k]:2 * o1[k + 1]]))
         assert rel_err(img, c["pi"][k]) < 1e-5 and rel_err(pi0, c["pi0"][k]) < 1e-5 and rel_err(pi1, c["pi1"][k]) < 1e-5
+
+
+def test_kd_emitter_batches_large_requests():
+    """the PDGNN emitter splits a long node list into several C-ABI calls (every intermediate comes back to the host):
+    a tiny budget forces many batches; results equal those of one call."""
+    import sg2dgm.kd as kd
+    import sg2dgm.riccidist2dgm as r
+    from tlc_b200 import graphgen as gg
+    c = gg.make_config("ppi", scale=0.2)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    pi = r.graph2pi.from_csr(*gg.build_csr(len(labels), ne, c["kappa"]))
+    nodes = list(range(0, 120))
+    one = kd.compute_persistence_images(pi, nodes, hop=1)
+    many = kd.compute_persistence_images(pi, nodes, hop=1, budget=2000)
+    assert len(one) == len(many) == len(nodes)
+    for a, b in zip(one, many):
+        assert (a[0] is None) == (b[0] is None)
+        if a[0] is None:
+            continue
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(np.asarray(a[3]), np.asarray(b[3]))
+        assert rel_err(a[2], b[2]) < 1e-12 and np.array_equal(a[4], b[4])

@@ -27,11 +27,11 @@ KD_FLAGS = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
 _FILT_FLAGS = {"ricci": 0, "degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY, "clustering": L.F_FILT_CLUSTERING}   # data_utils_NC.py:115-142
 
 
-def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False, filt="ricci"):
+def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False, filt="ricci", budget=None):
     """node-centred generator, batched: `g2pi` is a sg2dgm.riccidist2dgm.graph2pi (graph + curvature resident on the
     GPU), `nodes` are ORIGINAL node labels.  Returns a list with one entry per node: the reference's 9-tuple, or
     (None, None)."""
-    return _emit(g2pi, [(u, u) for u in nodes], L.MODE_NODE, hop, resolution, as_torch, filt)
+    return _emit(g2pi, [(u, u) for u in nodes], L.MODE_NODE, hop, resolution, as_torch, filt, budget)
 
 
 def compute_persistence_images_lp(g2pi, pairs, hop=2, resolution=5, as_torch=False, filt="ricci"):
@@ -41,11 +41,38 @@ def compute_persistence_images_lp(g2pi, pairs, hop=2, resolution=5, as_torch=Fal
     return _emit(g2pi, [(u, v) for u, v in pairs], L.MODE_EDGE_FORCED, hop, resolution, as_torch, filt)
 
 
-def _emit(g2pi, targets, mode, hop, resolution, as_torch, filt="ricci"):
+EMIT_BUDGET = 8_000_000   # vertices + edges of the vicinities handed to ONE tlc_vicinity_detail call (every intermediate of
+                          # a call comes back to the host: ~100 bytes per simplex)
+
+
+def _batches(G, tg, hop, mode, budget):
+    """split a target list into consecutive batches whose vicinities hold at most `budget` simplices in total"""
+    n, m, _ = G.vicinity_sizes(tg, hop=hop, mode=mode)
+    cost = n.astype(np.int64) + m.astype(np.int64) + 1
+    out, start, acc = [], 0, 0
+    for i, c in enumerate(cost.tolist()):
+        if i > start and acc + c > budget:
+            out.append((start, i))
+            start, acc = i, 0
+        acc += c
+    if start < len(tg):
+        out.append((start, len(tg)))
+    return out
+
+
+def _emit(g2pi, targets, mode, hop, resolution, as_torch, filt="ricci", budget=None):
     if filt not in _FILT_FLAGS:
         raise NotImplementedError("filt=%r: only 'ricci', 'degree', 'centrality', 'clustering' are on the GPU path (SURVEY.md row N3)" % (filt,))
     tg = g2pi._map_targets(targets)
     G = g2pi._graph
+    out = []
+    for lo, hi in _batches(G, tg, hop, mode, EMIT_BUDGET if budget is None else budget):
+        out += _emit_batch(g2pi, G, tg[lo:hi], mode, hop, resolution, as_torch, filt)
+    return out
+
+
+def _emit_batch(g2pi, G, tg, mode, hop, resolution, as_torch, filt):
+    targets = tg
     t0 = time.time()
     d = G.vicinity_detail(tg, hop=hop, mode=mode, descriptor="sum", resolution=resolution, flags=KD_FLAGS | _FILT_FLAGS[filt])
     dt = (time.time() - t0) / max(1, len(targets))
