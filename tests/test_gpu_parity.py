@@ -342,3 +342,28 @@ def test_handed_back_targets_on_the_graph_row_route():
     assert np.array_equal(pi, pi_m) and np.array_equal(status, status_m) and cnt == cnt_m
     compare_asc(g, og, tg[:8], 2, "sum", L.F_NORM | L.F_DIRECT, orc.F_NORM)
     g.close()
+
+
+def test_plain_path_sums_and_other_resolutions():
+    """TLC_F_SUM_PLAIN: path sums added left to right as CPython <= 3.11's sum() does -- the interpreter the reference pins
+    (3.7); default is the Neumaier-compensated sum() of CPython >= 3.12.  Continuous curvature, so the
+    two differ in the last bits.  Also batch calls at resolutions other than 5 (PersistenceImager(resolution), :207)."""
+    c = gg.make_config("pubmed", scale=0.3, continuous=True)
+    labels, ne = gg.relabel_first_appearance(c["edges"])
+    csr = gg.build_csr(len(labels), ne, c["kappa"])
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    rng = np.random.default_rng(17)
+    tg = ne[rng.choice(len(ne), 64, replace=False)].astype(np.int32)
+    compare_detail(g, og, tg[:24], 2, "sum", L.F_NORM | L.F_EXTENDED | L.F_SUM_PLAIN, orc.F_NORM | orc.F_EXTENDED | orc.F_SUM_PLAIN)
+    compare_asc(g, og, tg[:24], 2, "sum", L.F_NORM | L.F_SUM_PLAIN | L.F_DIRECT, orc.F_NORM | orc.F_SUM_PLAIN)
+    d0 = g.vicinity_detail(tg[:24], hop=2, flags=L.F_NORM)
+    d1 = g.vicinity_detail(tg[:24], hop=2, flags=L.F_NORM | L.F_SUM_PLAIN)
+    assert not np.array_equal(d0["fval"], d1["fval"])          # the flag does change last bits on continuous weights
+    for res in (3, 8):
+        for fl in (0, L.F_DIRECT, L.F_EXTENDED):
+            pi, status, cnt = g.vicinity_pi(tg, hop=2, resolution=res, flags=L.F_NORM | fl)
+            o = og.run_batch(tg, hop=2, resolution=res, flags=orc.F_NORM | (orc.F_EXTENDED if fl == L.F_EXTENDED else 0))
+            assert pi.shape == (len(tg), res * res)
+            assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"] and rel_err(pi, o["pi"]) < IMG_TOL
+    g.close()

@@ -17,10 +17,14 @@ _DESCRIPTORS = ("min", "max", "sum")
 
 
 class graph2pi():
-    def __init__(self, g, ricci_curv, device=0):
+    def __init__(self, g, ricci_curv, device=0, plain_sum=False):
         """g: networkx-like graph (needs .nodes() and .edges()); ricci_curv: [[n1, n2, kappa], ...]
         (both directions, loaddatas.py:117-121).  Nodes are relabelled to integers in g.nodes() order
-        exactly as nx.convert_node_labels_to_integers does (riccidist2dgm.py:217-220)."""
+        exactly as nx.convert_node_labels_to_integers does (riccidist2dgm.py:217-220).
+        plain_sum: add the path weights of build_fv (:30,35) left to right, as sum() of CPython <= 3.11 does (the
+        reference pins 3.7); default: the Neumaier-compensated sum() of CPython >= 3.12.  The two only
+        differ in the last bits, and only for weights that are not exactly representable sums."""
+        self.plain_sum = bool(plain_sum)
         nodes = list(g.nodes())
         self.dict_node = {old: new for new, old in enumerate(nodes)}
         self.old_label = nodes
@@ -66,6 +70,7 @@ class graph2pi():
     def from_csr(cls, rowptr, col, kappa, device=0):
         """graph already in integer ids 0..N-1 (CSR, ascending rows): skips the networkx ingestion."""
         self = cls.__new__(cls)
+        self.plain_sum = False
         self.csr = (rowptr, col, kappa)
         self._graph = api.VicinityGraph(rowptr, col, kappa, device=device)
         self.N = self._graph.N
@@ -100,9 +105,9 @@ class graph2pi():
             out[i, 1] = dn.get(b, -1)
         return out
 
-    @staticmethod
-    def _flags(norm, extended_flag):
-        return (L.F_NORM if norm else 0) | (L.F_EXTENDED if extended_flag else 0)
+    def _flags(self, norm, extended_flag):
+        return ((L.F_NORM if norm else 0) | (L.F_EXTENDED if extended_flag else 0) |
+                (L.F_SUM_PLAIN if getattr(self, "plain_sum", False) else 0))
 
     # -- reference surface -----------------------------------------------------------------------
     def sg2dgm_accelerate(self, u, v, hop, extended_flag=False, descriptor="seal", resolution=5, norm=False, cnt=0):
