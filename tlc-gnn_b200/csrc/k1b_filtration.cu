@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   int mcnt = 0;
   if (!roots_in) {
     // nx.NodeNotFound for every vertex -> dist = 100   riccidist2dgm.py:31-32,36-37
-    for (int x = tid; x < n; x += nt) { d1[x] = 100.0; d2[x] = 100.0; c.neg[vo + x] = -1; }
+    for (int x = tid; x < n; x += nt) { d1[x] = 100.0; d2[x] = 100.0; c.neg[vo + x] = -1; c.vcls[vo + x] = -1; }
     if (count_m) {
       for (int x = wid; x < n; x += nw) {
         const int a = astart[x], dg = adeg[x];
@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
     // a true induced neighbour of every vertex that lies nearer to a root (its tree parent), or -1: kernel 2v tries it
     // first when it looks for "a neighbour in an earlier block" (c.neg is free until the edge-sorted kernels run)
     int32_t* hint = c.neg + vo;
+    int32_t* hint0 = c.vcls + vo;  // ... and the parent towards the FIRST root (c.vcls: kernel 2's value classes come later)
     double* tpw = reinterpret_cast<double*>(c.v64b + vo);
     const float* __restrict__ aminw = c.aminw + vo;
     constexpr uint8_t FAR = 0, TENT = 1, DONE = 2;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
       double* out = r == 0 ? d1 : d2;
       for (int x = tid; x < n; x += nt) {
         dist[x] = INF_BITS; state[x] = FAR; tpar[x] = root; tpw[x] = 0.0;
-        if (r == 0) hint[x] = -1;
+        if (r == 0) { hint[x] = -1; hint0[x] = -1; }
         if (margins_in_smem && r == 0) smw[x] = __float2half_rd(fminf(aminw[x], 60000.f));  // rounded DOWN: the criterion stays valid
       }
       if (tid == 0) { sh.nmin[0] = 0ull; sh.nmin[1] = INF_BITS; sh.qn[0] = 0; sh.qn[1] = 0; }
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
           const int x = sh.qx[i], a = sh.qbest[i];
           if (x != root && a != 0x7fffffff) {
             tpar[x] = DIRECT ? bitmap_rank(bm, W, (int)anb[a]) : (int)anb[a];
-            hint[x] = tpar[x];
+            (r == 0 ? hint0 : hint)[x] = tpar[x];
             tpw[x] = DIRECT ? __dadd_rn(aw[a], 1.0) : aw[a];
           }
         }
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(256) degree_filtration_kernel(Params p, ChunkV
     double d = (double)adeg[x];
     if (cen) d = n > 1 ? __dmul_rn(d, sc) : 1.0;
     fval[x] = d;
-    c.neg[vo + x] = -1;  // (no shortest-path tree here: kernel 2v gets no neighbour hint)
+    c.neg[vo + x] = -1; c.vcls[vo + x] = -1;  // (no shortest-path tree here: kernel 2v gets no neighbour hint)
     mx = fmax(mx, d);
   }
   const double m = __dadd_rn(block_reduce_max(mx, redd), 1e-10);
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(256) clustering_filtration_kernel(Params p, Ch
     for (int o = 16; o; o >>= 1) tri += __shfl_xor_sync(0xffffffffu, tri, o);
     const long long d = xd;
     const double cv = tri == 0 ? 0.0 : __ddiv_rn((double)tri, (double)(d * (d - 1)));
-    if (lane == 0) { fval[x] = cv; c.neg[vo + x] = -1; }
+    if (lane == 0) { fval[x] = cv; c.neg[vo + x] = -1; c.vcls[vo + x] = -1; }
     mx = fmax(mx, cv);
   }
   const double m = __dadd_rn(block_reduce_max(mx, redd), 1e-10);

@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   __syncthreads();
   const int32_t* __restrict__ astart = c.astart + vo;
   const int32_t* __restrict__ adeg = c.adeg + vo;
-  const int32_t* __restrict__ hint = c.neg + vo;  // kernel 1b's tree parents (-1: none)
+  const int32_t* __restrict__ hint = c.neg + vo;  // kernel 1b's tree parents (-1: none): towards the last root ...
+  const int32_t* __restrict__ hint0 = in_smem ? c.vcls + vo : nullptr;  // ... and the first (c.vcls doubles as the block table when it does not fit shared memory)
   if (c.dbm) {
     // graph-row route: the row is the graph's CSR row, entries outside the vicinity bitmap are skipped
     // the bitmap and its word-prefix ranks staged behind the block table (shared memory) when the launch made room
@@ -158,8 +159,8 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
     for (int x = tid; x < n; x += nt) {
       const int bx = sblk[x];
       const int a = astart[x], dg = adeg[x];
-      const int h = hint[x];                       // kernel 1b's tree parent: usually already in an earlier block
-      bool has = h >= 0 && sblk[h] < bx;
+      const int h = hint[x], h0 = hint0 ? hint0[x] : -1;  // kernel 1b's tree parents: usually already in an earlier block
+      bool has = (h >= 0 && sblk[h] < bx) || (h0 >= 0 && sblk[h0] < bx);
       for (int j = 0; j < dg && !has && bx > 0; j++) {
         const int y = bitmap_rank(bm, c.W, gcol[a + j]);
         has = y >= 0 && sblk[y] < bx;
@@ -172,8 +173,8 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
   for (int x = tid; x < n; x += nt) {  // x: local id
     const int bx = sblk[x];
     const int a = astart[x], dg = adeg[x];
-    const int h = hint[x];
-    bool has = h >= 0 && sblk[h] < bx;
+    const int h = hint[x], h0 = hint0 ? hint0[x] : -1;
+    bool has = (h >= 0 && sblk[h] < bx) || (h0 >= 0 && sblk[h0] < bx);
     for (int j = 0; j < dg && !has && bx > 0; j++) has = sblk[anb[a + j]] < bx;  // (block 0 has no earlier block)
     if (!has) atomicAnd(&bfirst[bx], (int32_t)~0x40000000);
   }
