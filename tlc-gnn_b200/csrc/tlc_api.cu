@@ -1,11 +1,14 @@
 // tlc_api.cu -- host orchestration and the C-ABI of libtlc_b200.so (include/tlc_b200.h).
 //
-// A call processes its targets in CHUNKS.  The counting pass of kernel 1 gives every target's
-// vicinity size (n, m); the host sorts live targets by size (largest first: longest-processing-time
-// scheduling, and size-homogeneous chunks), packs as many as fit the HBM arena, and runs the stage
-// kernels over the chunk: 1 fill -> 1b filtration -> 2 sort -> 3 union-find -> [3b loops] -> 4 image.
-// Per-target segments of every array are addressed through exclusive offsets uploaded per chunk; the
-// image kernel scatters rows to their final position, so results keep the caller's target order.
+// A call processes its targets in CHUNKS.  The counting pass of kernel 1 gives every target's vicinity size; the host
+// orders the live targets (route, shared-memory class, size: largest first), packs as many as fit the HBM arena, and
+// runs the stage kernels over the chunk.  Two routes (chosen per call, same results bit for bit):
+//   materialised : 1 fill -> 1b filtration -> 2v vertex order -> 3v sweep -> [1c edge list -> 2 sort -> 3 union-find
+//                  (descending sweep, Pos/Neg lists, targets 3v handed back)] -> [3b loops] -> 4 image
+//   graph-row    : (light counting pass) -> 1b filtration on the graph's own CSR rows -> 2v -> 3v -> 4 image
+//                  -- ascending-sweep-only calls on vicinities that are dense in the graph; no adjacency in HBM
+// Per-target segments of every array are addressed through exclusive offsets uploaded per chunk; the image kernel
+// scatters rows to their final position, so results keep the caller's target order.
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
