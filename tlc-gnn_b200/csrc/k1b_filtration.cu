@@ -334,10 +334,10 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
                 const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dx[k]), w));
                 if (tb < dyb) {
                   atomicMin(&dist[y], tb);
-                  if (state[y] == FAR) state[y] = TENT;
+                  state[y] = TENT;  // (y is FAR or TENT: a settled vertex's distance is final and cannot be improved)
                   umin = tb < umin ? tb : umin;
-                } else if (dyb != INF_BITS &&
-                           (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dx[k]) {
+                } else if ((unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dx[k]) {
+                  // (an unreached y carries +inf: inf + w never equals the finite d[x])
                   // y a parent of the row's vertex (d[y] is final whenever this can hold; it cannot when d[x] + w < d[y])
                   atomicMin(&sh.qbest[ri[k]], ai[k]);
                 }

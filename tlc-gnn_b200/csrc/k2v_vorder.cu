@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, i
     int f = 1;
     if (i > 0) {
       // same block as the predecessor unless every key owned by it is strictly below every key owned here
-      const double fp = fval[ps[i - 1]], fx = fval[x];
+      // (the exact values in sorted order were just written to ks[] as ordered bit patterns: decode instead of gathering)
+      const double fp = ordered_to_f64(ks[i - 1]), fx = ordered_to_f64(ks[i]);
       const double hi_prev = __dadd_rn(fp, __dmul_rn(__dadd_rn(fp, 1.0), 1e-6));
       const double lo_here = __dadd_rn(fx, pmin);
       f = hi_prev < lo_here ? 1 : 0;

@@ -96,6 +96,11 @@ __device__ __forceinline__ unsigned long long f64_to_ordered(double x) {
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+__device__ __forceinline__ double ordered_to_f64(unsigned long long k) {  // inverse of f64_to_ordered
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
 // block-wide exclusive scan of `n` ints in (global or shared) memory, in place; returns the total.
 // Each thread owns a contiguous slice; `sh` needs blockDim.x + 1 ints.  All threads must call.
 __device__ inline int block_exclusive_scan(int32_t* data, int n, int32_t* sh) {
