@@ -92,3 +92,26 @@ def test_kd_generator_asis_vs_oracle():
             assert np.array_equal(sorted_rows(r["ord0"]), sorted_rows(np.stack([o["pbirth"][up], o["pdeath"][up]], 1)))
             assert np.array_equal(sorted_rows(r["ext1"]), sorted_rows(np.stack([o["pbirth"][one], o["pdeath"][one]], 1)))
             assert rel_err(r["pi"], o["img"]) < 1e-10
+
+
+@pytest.mark.parametrize("hop,descriptor,ext", [(3, "sum", True), (1, "max", True), (2, "min", False)])
+def test_edge_cases_match_reference(hop, descriptor, ext):
+    """targets the committed fixtures do not hold: self pairs (u, u), repeated targets, reversed pairs, unknown labels,
+    far-apart pairs; hop 3; min / max descriptors with the loops -- the as-is reference batch call vs the oracle."""
+    c = gg.make_config("pubmed", scale=0.04, continuous=True)
+    e = c["edges"]
+    rng = np.random.default_rng(23)
+    pick = e[rng.choice(len(e), 10, replace=False)]
+    un = np.unique(e)
+    tg = np.concatenate([pick, pick[:3], pick[:3, ::-1], np.stack([un[:4], un[:4]], 1), rng.choice(un, size=(6, 2)),
+                         np.array([[10 ** 7, int(un[0])], [int(un[1]), 10 ** 7 + 1]])])
+    pi_ref, cnt_ref, _ = rh.run_batch(e, c["kappa"], tg, hop, ext, descriptor=descriptor)
+    labels, ne = gg.relabel_first_appearance(e)
+    lut = {int(l): i for i, l in enumerate(labels)}
+    new_t = np.array([[lut.get(int(a), -1), lut.get(int(b), -1)] for a, b in tg], dtype=np.int32)
+    og = orc.OracleGraph(*gg.build_csr(len(labels), ne, c["kappa"]))
+    r = og.run_batch(new_t, hop=hop, descriptor=descriptor, flags=orc.F_NORM | (orc.F_EXTENDED if ext else 0))
+    assert r["cnt_compute"] == cnt_ref
+    assert np.array_equal(pi_ref.any(axis=1), r["pi"].any(axis=1))
+    assert rel_err(r["pi"], pi_ref) < 1e-11
+    assert np.array_equal(r["pi"][:3], r["pi"][10:13])                       # repeated targets: identical rows
