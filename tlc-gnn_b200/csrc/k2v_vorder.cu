@@ -29,7 +29,7 @@
 namespace tlc {
 namespace {
 
-__global__ void __launch_bounds__(512, 2) vorder_kernel(Params p, ChunkView c, int t0, int smem_ints, int bm_in_smem) {
+__global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, int t0, int smem_ints, int bm_in_smem) {
   extern __shared__ int32_t dyn[];
   __shared__ SortShared sh;
   const int t = t0 + blockIdx.x;

@@ -349,7 +349,17 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   if (edge_sorted) {
     cudaMemsetAsync(c.tfb, 1, (size_t)c.T, st);
   } else {
-    launch_vorder(p, c, 0, c.T, block, n_max, st);
+    {  // per sub-range like kernel 1b: the block table in shared memory is sized by the sub-range's largest vicinity
+      const bool fork = subs.size() > 1 && g->ev_fork != nullptr;
+      if (fork) cudaEventRecord(g->ev_fork, st);
+      for (size_t i = 0; i < subs.size(); i++) {
+        const SubRange& r = subs[i];
+        cudaStream_t s = st;
+        if (fork && i > 0 && i <= 3) { s = g->side[i - 1]; cudaStreamWaitEvent(s, g->ev_fork, 0); }
+        launch_vorder(p, c, r.t0, r.cnt, block, r.n_max, s);
+        if (s != st) { cudaEventRecord(g->ev_join[i - 1], s); cudaStreamWaitEvent(st, g->ev_join[i - 1], 0); }
+      }
+    }
     tm.mark(4);
     launch_sweep(p, c, 0, c.T, n_max, st);
   }
