@@ -361,7 +361,17 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
       }
     }
     tm.mark(4);
-    launch_sweep(p, c, 0, c.T, n_max, st);
+    {  // likewise kernel 3v: its shared-memory parents are sized by the sub-range's largest vicinity
+      const bool fork = subs.size() > 1 && g->ev_fork != nullptr;
+      if (fork) cudaEventRecord(g->ev_fork, st);
+      for (size_t i = 0; i < subs.size(); i++) {
+        const SubRange& r = subs[i];
+        cudaStream_t s = st;
+        if (fork && i > 0 && i <= 3) { s = g->side[i - 1]; cudaStreamWaitEvent(s, g->ev_fork, 0); }
+        launch_sweep(p, c, r.t0, r.cnt, r.n_max, s);
+        if (s != st) { cudaEventRecord(g->ev_join[i - 1], s); cudaStreamWaitEvent(st, g->ev_join[i - 1], 0); }
+      }
+    }
   }
   tm.mark(5);
   if (!c.dbm) {  // (graph-row route: no adjacency to derive edges from; a chunk with handed-back targets is redone)
