@@ -111,3 +111,27 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_kd_emitter_batching_logic():
+    """sg2dgm.kd._batches: consecutive batches, every target in exactly one, budget respected unless a single vicinity
+    alone exceeds it (pure host logic; the C-ABI call is stubbed)."""
+    import sg2dgm.kd as kd
+
+    class FakeGraph:
+        def __init__(self, n, m):
+            self.n, self.m = np.asarray(n, np.int32), np.asarray(m, np.int32)
+
+        def vicinity_sizes(self, tg, hop=2, mode=0):
+            return self.n[:len(tg)], self.m[:len(tg)], np.zeros(len(tg), np.uint8)
+
+    n = [10, 20, 5, 400, 7, 7, 7, 1000, 3]
+    m = [30, 60, 9, 900, 8, 8, 8, 5000, 2]
+    tg = np.zeros((len(n), 2), np.int32)
+    b = kd._batches(FakeGraph(n, m), tg, 2, 0, budget=200)
+    assert b[0][0] == 0 and b[-1][1] == len(n)
+    assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))             # consecutive, no gaps
+    cost = np.asarray(n) + np.asarray(m) + 1
+    for lo, hi in b:
+        assert hi > lo and (cost[lo:hi].sum() <= 200 or hi - lo == 1)          # an oversized vicinity travels alone
+    assert kd._batches(FakeGraph(n, m), tg, 2, 0, budget=10 ** 9) == [(0, len(n))]
