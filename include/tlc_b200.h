@@ -60,6 +60,11 @@ extern "C" {
 #define TLC_F_ASC_ONLY 256u /* tlc_vicinity_detail: ascending sweep only -- PD_up and [min,max]; no PD_down, no edge
                                lists / orders / Pos / Neg (those outputs are left untouched) */
 
+#define TLC_F_NO_SMALL 4096u /* never take the fused small-vicinity kernels (kernel S): every target through the staged
+                                pipeline.  Default: the batch calls (5 x 5 image, Ricci-distance filtration) first run kernel S,
+                                which finishes every vicinity of <= 256 vertices / <= 2048 edges in one launch per size class,
+                                and hand only the larger ones to the staged kernels.  Same results bit for bit */
+
 #define TLC_F_FILT_DEGREE 512u      /* PDGNN generators, filt='degree': filtration = induced degree / (max + 1e-10)
                                        Knowledge_Distillation/data_utils_NC.py:126-128 (no roots, no distances) */
 #define TLC_F_FILT_CENTRALITY 1024u /* filt='centrality': nx.degree_centrality (d * 1/(n-1)) / (max + 1e-10)   :118-121 */
@@ -96,6 +101,9 @@ typedef struct tlc_graph tlc_graph; /* opaque: CSR + curvature resident in HBM, 
 /* graph2pi.__init__ (riccidist2dgm.py:216-226): node ids are the reference's integer relabelling
  * (first appearance order); rowptr[N+1], col[nnz] ascending inside each row, kappa[nnz] = Ricci
  * curvature of the directed edge (weight = kappa + 1, :225).  All host pointers; copied to `device`.
+ * The CSR is validated (TLC_E_INVALID otherwise): rowptr monotone, col in [0, N), rows strictly ascending (no
+ * duplicate entries), no self-loops, every entry (x, y) mirrored by (y, x) with the same kappa, and kappa + 1 finite
+ * and > 0 (the precondition of the reference's Dijkstra).
  * arena_bytes = 0 picks a default (TLC_ARENA_GB env or 24 GiB, clamped to free memory). */
 int tlc_graph_create(int32_t N, int64_t nnz, const int32_t *rowptr, const int32_t *col, const double *kappa,
                      int device, uint64_t arena_bytes, tlc_graph **out);
@@ -148,6 +156,19 @@ typedef struct {
 } tlc_detail;
 int tlc_vicinity_detail(tlc_graph *g, const int32_t *targets, int64_t E, const tlc_params *p, tlc_detail *out);
 
+#define TLC_ST_NOT_SMALL 255 /* tlc_small_diagrams only: the vicinity exceeds kernel S (> 256 vertices or > 2048 edges) */
+
+/* Diagrams of a batch straight from the fused small-vicinity kernels (kernel S, k0_small.cu): for every target whose
+ * vicinity has <= 256 vertices and <= 2048 edges, the reference's PD_zero (+ PD_one with TLC_F_EXTENDED) in its own
+ * concatenation order (accelerated_PD.py:110, riccidist2dgm.py:323-328) -- kind, birth / death vertex (local ids),
+ * birth / death value -- at poff[t] .. poff[t] + npairs[t], plus the image row, status and vicinity size.  poff[E+1]
+ * are the caller's exclusive segment offsets; a segment must hold n + m + 2 pairs (tlc_vicinity_sizes).  Targets
+ * kernel S cannot take report TLC_ST_NOT_SMALL and no pairs (tlc_vicinity_detail serves those).  HOST buffers;
+ * any output pointer may be NULL.  5 x 5 image, Ricci-distance filtration only. */
+int tlc_small_diagrams(tlc_graph *g, const int32_t *targets, int64_t E, const tlc_params *p, const int64_t *poff,
+                       int32_t *npairs, int32_t *pkind, int32_t *pbv, int32_t *pdv, double *pbirth, double *pdeath,
+                       double *out_pi, uint8_t *out_status, int32_t *out_n, int32_t *out_m);
+
 /* Union_find(simplex_filter) + Accelerate_PD(Pos, Neg, simplex_filter) on ONE caller-supplied graph
  * (accelerated_PD.py:26,115; KD/accelerated_PD.py:25,120): n vertices with filtration fval[n], m edges
  * (a[i], b[i]) in the caller's dict order (that order is the tie-break).  flags: TLC_F_EXTENDED,
@@ -170,7 +191,9 @@ int tlc_pi_gather(int device, const double *dev_table, int64_t rows, int32_t r2,
                   int64_t start, int64_t n, float *dev_out_f32, void *stream);
 
 /* run this graph's kernels on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
- * graph's own stream).  Lets a host framework order the work with its own (e.g. NCCL) operations. */
+ * graph's own non-blocking stream -- to run on the legacy default stream pass cudaStreamLegacy, (void*)0x1).
+ * Lets a host framework order the work with its own (e.g. NCCL) operations: buffers handed to
+ * tlc_vicinity_pi_dev are written on this stream. */
 int tlc_graph_set_stream(tlc_graph *g, void *stream);
 
 /* introspection */
@@ -192,6 +215,9 @@ int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_
 int tlc_last_counts(tlc_graph *g, int64_t *out8);
 /* targets of the last call that took the graph-row route (TLC_F_DIRECT / TLC_F_NO_DIRECT) */
 int64_t tlc_last_direct(tlc_graph *g);
+/* kernel S in the last call: out[0..1] = device ms of the class A (warp per target) / class B (CTA per target) launch
+ * (TLC_STAGE_TIMING=1), out[2..3] = rows they finished, out[4] = rows handed on to the staged pipeline */
+int tlc_last_small(tlc_graph *g, double *out5);
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,25 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const double* __restr
   }
 }
 
+// targets of a sub-list, and the rows they came from (kernel S hands rows it cannot take to the staged pipeline)
+__global__ void gather_targets_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ list, int64_t k,
+                                      int32_t* __restrict__ sub, int64_t* __restrict__ idx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = list[i];
+    sub[2 * i] = targets[2 * r];
+    sub[2 * i + 1] = targets[2 * r + 1];
+    idx[i] = r;
+  }
+}
+
 }  // namespace
+
+void launch_gather_targets(const int32_t* targets, const int32_t* list, int64_t k, int32_t* sub, int64_t* idx, cudaStream_t st) {
+  if (k <= 0) return;
+  const int grid = (int)std::min<int64_t>((k + 255) / 256, 2048);
+  gather_targets_kernel<<<grid, 256, 0, st>>>(targets, list, k, sub, idx);
+  count_launch();
+}
 
 void launch_scatter_rows(const double* src_pi, const float* src_pi32, const uint8_t* src_st, const int64_t* idx, int64_t k,
                          int r2, double* dst_pi, float* dst_pi32, uint8_t* dst_st, int sm_count, cudaStream_t st) {

@@ -42,6 +42,17 @@ static int fail(int rc, const std::string& msg) {
                                   std::to_string(__LINE__));                                       \
   } while (0)
 
+// device allocation freed on every exit path (the CK macro returns early)
+struct DevBuf {
+  void* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  template <typename T_> T_* as() const { return static_cast<T_*>(p); }
+};
+
 static constexpr size_t ALIGN = 256;
 static size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
@@ -96,6 +107,22 @@ struct tlc_graph {
   int nchunks = 0;
   double alg_bytes = 0, alg_bytes_bfs = 0, alg_bytes_uf = 0;
   bool timing = false;
+  // kernel S (fused small-vicinity path): deferral lists, counters + statistics, their pinned host mirror
+  int32_t *sm_list_b = nullptr, *sm_list_c = nullptr;
+  int32_t* sm_sub = nullptr;       // [cap][2] targets handed on to the staged pipeline
+  int64_t* sm_idx = nullptr;       // [cap] their rows
+  double* sm_pi = nullptr;         // [cap][r2] staged results of those rows, scattered back
+  float* sm_pi32 = nullptr;
+  uint8_t* sm_st = nullptr;
+  int64_t sm_cap = 0, sm_sub_cap = 0;
+  char* sm_dev = nullptr;          // [int counters[2] | pad | SmallStats]
+  char* sm_host = nullptr;         // pinned mirror
+  int small_skip = 0;              // calls left for which the small path is not tried (it handled too few rows)
+  int small_hop = -1, small_mode = -1;
+  double small_ms[2] = {0, 0};
+  int64_t small_rows[3] = {0, 0, 0};  // last call: rows finished by class A / class B / handed to the staged pipeline
+  std::vector<cudaEvent_t> ev_pool;  // stage-timing events, reused from call to call
+  size_t ev_base = 0;                // first pool slot a (nested) call may use
   int sm_count = 0;
 };
 
@@ -282,29 +309,32 @@ static int size_class(int64_t m) { return block_for(m); }
 static int smem_class(int64_t n) { return n > 22000 ? 0 : (n > 16000 ? 1 : 2); }
 
 struct StageTimer {
+  // per-stage CUDA events (TLC_STAGE_TIMING=1).  The events come from a pool owned by the graph and are reused from call
+  // to call: no cudaEventCreate / cudaEventDestroy inside a timed call once the pool has grown to a call's needs.
   bool on;
   cudaStream_t st;
-  std::vector<cudaEvent_t> ev;
+  std::vector<cudaEvent_t>* pool;
+  size_t used, first;  // next free pool slot; first slot of the marks not collected yet
   std::vector<int> stage;
-  explicit StageTimer(bool on_, cudaStream_t s) : on(on_), st(s) {}
+  StageTimer(bool on_, cudaStream_t s, std::vector<cudaEvent_t>* pool_, size_t start) : on(on_), st(s), pool(pool_), used(start), first(start) {}
+  cudaEvent_t take() {
+    if (used == pool->size()) { cudaEvent_t e; cudaEventCreate(&e); pool->push_back(e); }
+    return (*pool)[used++];
+  }
   void mark(int stage_id) {  // marks the START of stage_id (or the end marker with id -1)
     if (!on) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, st);
-    ev.push_back(e);
+    cudaEventRecord(take(), st);
     stage.push_back(stage_id);
   }
-  void collect(double* ms8) {  // ms8: per-stage accumulators (10 slots)
+  void collect(double* ms8) {  // ms8: per-stage accumulators (10 slots); call after the stream is synchronised
     if (!on) return;
-    for (size_t i = 0; i + 1 < ev.size(); i++) {
+    for (size_t i = 0; i + 1 < stage.size(); i++) {
       if (stage[i] < 0) continue;
       float ms = 0;
-      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      cudaEventElapsedTime(&ms, (*pool)[first + i], (*pool)[first + i + 1]);
       ms8[stage[i]] += ms;
     }
-    for (auto e : ev) cudaEventDestroy(e);
-    ev.clear();
+    first = used;
     stage.clear();
   }
 };
@@ -403,10 +433,10 @@ static int check_params(const tlc_params* p) {
   return TLC_OK;
 }
 
-// the whole path over device-resident targets.  detail != NULL: single chunk in input order, every
+// the STAGED pipeline over device-resident targets.  detail != NULL: single chunk in input order, every
 // intermediate copied back to host.
-static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const tlc_params* up, double* d_pi,
-                        float* d_pi32, uint8_t* d_status, int64_t* cnt_compute, tlc_detail* detail) {
+static int run_staged(tlc_graph* g, const int32_t* d_targets, int64_t E, const tlc_params* up, double* d_pi,
+                      float* d_pi32, uint8_t* d_status, int64_t* cnt_compute, tlc_detail* detail) {
   int rc = check_params(up);
   if (rc) return rc;
   if (E < 0 || E >= ((int64_t)1 << 32)) return fail(TLC_E_INVALID, "E must be in [0, 2^32)");
@@ -427,9 +457,9 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   if ((rc = ensure_vicinity_scratch(g, p))) return rc;
   const char* tenv = getenv("TLC_STAGE_TIMING");
   g->timing = tenv && atoi(tenv) != 0;
-  StageTimer tm(g->timing, st);
+  StageTimer tm(g->timing, st, &g->ev_pool, g->ev_base);
   cudaEvent_t ev_total0 = nullptr, ev_total1 = nullptr;
-  if (g->timing) { cudaEventCreate(&ev_total0); cudaEventCreate(&ev_total1); cudaEventRecord(ev_total0, st); }
+  if (g->timing) { ev_total0 = tm.take(); ev_total1 = tm.take(); tm.first = tm.used; cudaEventRecord(ev_total0, st); }
 
   // ---- route: graph-row (no adjacency in HBM) or materialised, per call ----
   // the graph-row route serves calls that need the ascending sweep only; it reads D_S graph-row entries per root
@@ -456,8 +486,9 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     } else {
       const int64_t S = std::min<int64_t>(E, std::max<int64_t>(64, E / 64));
       const int64_t stride = E / S;
-      int32_t* d_sample = nullptr;
-      CK(cudaMalloc((void**)&d_sample, (size_t)S * 8));
+      DevBuf sample_buf;
+      CK(sample_buf.alloc((size_t)S * 8));
+      int32_t* d_sample = sample_buf.as<int32_t>();
       CK(cudaMemcpy2DAsync(d_sample, 8, d_targets, (size_t)stride * 8, 8, (size_t)S, cudaMemcpyDeviceToDevice, st));
       launch_vicinity_sizes(g->gv, p, d_sample, S, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->work_counter, st);
       std::vector<int32_t> sm((size_t)S), sds((size_t)S);
@@ -466,7 +497,6 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
       CK(cudaMemcpyAsync(sds.data(), g->d_ds, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(sst.data(), g->d_st, (size_t)S, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      cudaFree(d_sample);
       double a = 0, b = 0;
       for (int64_t i = 0; i < S; i++) if (sst[(size_t)i] == TLC_ST_OK) { a += sds[(size_t)i]; b += 2.0 * sm[(size_t)i]; }
       call_direct = b > 0 && a <= direct_ratio * b;
@@ -646,7 +676,8 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
         // kernel 3v handed targets back: their edge-sorted sweep needs the adjacency
         if (light) {  // no adjacency space was reserved: those targets are redone on the materialised route below
           std::vector<uint8_t> fbv((size_t)T);
-          CK(cudaMemcpy(fbv.data(), c.tfb, (size_t)T, cudaMemcpyDeviceToHost));
+          CK(cudaMemcpyAsync(fbv.data(), c.tfb, (size_t)T, cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
           for (int64_t k = 0; k < T; k++) if (fbv[(size_t)k]) redo.push_back(h_tidx[pos + k]);
         } else {
         // the chunk is redone on the materialised route (its space is reserved), image rows and statuses are rewritten
@@ -696,17 +727,23 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   if (!redo.empty()) {
     // the handed-back targets of a graph-row call, as their own call on the materialised route; rows scattered back
     const int64_t k = (int64_t)redo.size();
+    // (all copies on the call's stream -- a non-blocking stream is not ordered with the legacy stream a plain cudaMemcpy uses --
+    // and synchronised before the host vectors are touched or go away; the device buffers free themselves on every exit path)
     std::vector<int32_t> h_all((size_t)E * 2), h_sub((size_t)k * 2);
-    CK(cudaMemcpy(h_all.data(), d_targets, (size_t)E * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(h_all.data(), d_targets, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < k; i++) { h_sub[2 * i] = h_all[2 * redo[i]]; h_sub[2 * i + 1] = h_all[2 * redo[i] + 1]; }
-    int32_t* d_sub = nullptr; int64_t* d_idx = nullptr; double* s_pi = nullptr; float* s_pi32 = nullptr; uint8_t* s_st = nullptr;
-    CK(cudaMalloc((void**)&d_sub, (size_t)k * 8));
-    CK(cudaMalloc((void**)&d_idx, (size_t)k * 8));
-    CK(cudaMalloc((void**)&s_pi, (size_t)k * r2 * 8));
-    CK(cudaMalloc((void**)&s_pi32, (size_t)k * r2 * 4));
-    CK(cudaMalloc((void**)&s_st, (size_t)k));
-    CK(cudaMemcpy(d_sub, h_sub.data(), (size_t)k * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_idx, redo.data(), (size_t)k * 8, cudaMemcpyHostToDevice));
+    DevBuf b_sub, b_idx, b_pi, b_pi32, b_st;
+    CK(b_sub.alloc((size_t)k * 8));
+    CK(b_idx.alloc((size_t)k * 8));
+    CK(b_pi.alloc((size_t)k * r2 * 8));
+    CK(b_pi32.alloc((size_t)k * r2 * 4));
+    CK(b_st.alloc((size_t)k));
+    int32_t* d_sub = b_sub.as<int32_t>(); int64_t* d_idx = b_idx.as<int64_t>();
+    double* s_pi = b_pi.as<double>(); float* s_pi32 = b_pi32.as<float>(); uint8_t* s_st = b_st.as<uint8_t>();
+    CK(cudaMemcpyAsync(d_sub, h_sub.data(), (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_idx, redo.data(), (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
     // keep this call's statistics: the sub-call resets them
     const int64_t o_live = g->last_live, o_nv = g->last_nv, o_ne = g->last_ne, o_direct = g->last_direct;
     const int o_chunks = g->nchunks;
@@ -716,13 +753,15 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     for (int i = 0; i < 10; i++) o_ms[i] = g->stage_ms[i];
     tlc_params up2 = *up;
     up2.flags = (up2.flags | TLC_F_NO_DIRECT) & ~TLC_F_DIRECT;
-    rc = run_pipeline(g, d_sub, k, &up2, s_pi, s_pi32, s_st, nullptr, nullptr);
+    const size_t keep_base = g->ev_base;
+    g->ev_base = tm.used;  // the nested call's stage events live behind this call's
+    rc = run_staged(g, d_sub, k, &up2, s_pi, s_pi32, s_st, nullptr, nullptr);
+    g->ev_base = keep_base;
     if (rc == TLC_OK) {
       launch_scatter_rows(s_pi, d_pi32 ? s_pi32 : nullptr, d_status ? s_st : nullptr, d_idx, k, r2, d_pi, d_pi32, d_status,
                           g->sm_count, st);
       cudaStreamSynchronize(st);
     }
-    cudaFree(d_sub); cudaFree(d_idx); cudaFree(s_pi); cudaFree(s_pi32); cudaFree(s_st);
     if (rc) return rc;
     const int64_t sub_fb = g->last_fb;
     g->last_live = o_live; g->last_nv = o_nv; g->last_ne = o_ne; g->last_direct = o_direct - k; g->alg_bytes = o_bytes;
@@ -737,8 +776,6 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
     cudaEventElapsedTime(&ms, ev_total0, ev_total1);
     g->stage_ms[9] = ms;
     tm.collect(g->stage_ms);
-    cudaEventDestroy(ev_total0);
-    cudaEventDestroy(ev_total1);
   }
   // cnt_compute: targets whose image row was really computed (riccidist2dgm.py:354)
   if (cnt_compute || (detail && detail->status)) {
@@ -761,9 +798,152 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
   return TLC_OK;
 }
 
+static int ensure_small_buffers(tlc_graph* g, int64_t E) {
+  if (!g->sm_dev) {
+    CK(cudaMalloc((void**)&g->sm_dev, 256));
+    CK(cudaMallocHost((void**)&g->sm_host, 256));
+  }
+  if (E <= g->sm_cap) return TLC_OK;
+  if (g->sm_list_b) cudaFree(g->sm_list_b);
+  if (g->sm_list_c) cudaFree(g->sm_list_c);
+  g->sm_list_b = g->sm_list_c = nullptr; g->sm_cap = 0;
+  const int64_t cap = E + E / 8 + 1024;
+  CK(cudaMalloc((void**)&g->sm_list_b, (size_t)cap * 4));
+  CK(cudaMalloc((void**)&g->sm_list_c, (size_t)cap * 4));
+  g->sm_cap = cap;
+  return TLC_OK;
+}
+
+static int ensure_small_sub(tlc_graph* g, int64_t k, int r2) {
+  if (k <= g->sm_sub_cap) return TLC_OK;
+  cudaFree(g->sm_sub); cudaFree(g->sm_idx); cudaFree(g->sm_pi); cudaFree(g->sm_pi32); cudaFree(g->sm_st);
+  g->sm_sub = nullptr; g->sm_idx = nullptr; g->sm_pi = nullptr; g->sm_pi32 = nullptr; g->sm_st = nullptr; g->sm_sub_cap = 0;
+  const int64_t cap = k + k / 4 + 256;
+  CK(cudaMalloc((void**)&g->sm_sub, (size_t)cap * 8));
+  CK(cudaMalloc((void**)&g->sm_idx, (size_t)cap * 8));
+  CK(cudaMalloc((void**)&g->sm_pi, (size_t)cap * r2 * 8));
+  CK(cudaMalloc((void**)&g->sm_pi32, (size_t)cap * r2 * 4));
+  CK(cudaMalloc((void**)&g->sm_st, (size_t)cap));
+  g->sm_sub_cap = cap;
+  return TLC_OK;
+}
+
+static constexpr size_t SM_STATS_OFF = 16;  // SmallStats behind the two deferral counters in sm_dev / sm_host
+
+// which calls kernel S (k0_small.cu) can take: the batch call with a Ricci-distance filtration and a 5 x 5 image on a
+// graph whose ball cache exists; the route-forcing diagnostic flags keep their meaning (they name staged kernels)
+static bool small_applicable(const tlc_graph* g, const tlc_params* up, int64_t E, const tlc_detail* detail) {
+  if (detail || E <= 0 || E >= ((int64_t)1 << 31)) return false;
+  if (up->resolution != 5 || up->descriptor < 0 || up->descriptor > 2) return false;
+  if (up->flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING | TLC_F_EDGE_SORTED | TLC_F_DIRECT |
+                   TLC_F_NO_DIRECT | TLC_F_NO_SMALL | TLC_F_ASC_ONLY)) return false;
+  if (getenv("TLC_NO_SMALL")) return false;
+  return true;
+}
+
+// kernel S over the whole call, then the staged pipeline over the rows it handed on
+static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tlc_params* up, double* d_pi, float* d_pi32,
+                     uint8_t* d_status, int64_t* cnt_compute, bool* fell_through) {
+  *fell_through = false;
+  CK(cudaSetDevice(g->device));
+  Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
+  const int r2 = p.resolution * p.resolution;
+  cudaStream_t st = g->stream;
+  int rc;
+  if ((rc = ensure_call_buffers(g, E))) return rc;
+  if ((rc = ensure_vicinity_scratch(g, p))) return rc;
+  if (!g->ball_cache) { *fell_through = true; return TLC_OK; }
+  if ((rc = ensure_small_buffers(g, E))) return rc;
+  if (g->small_hop != p.hop || g->small_mode != p.mode) { g->small_hop = p.hop; g->small_mode = p.mode; g->small_skip = 0; }
+  if (g->small_skip > 0) { g->small_skip--; *fell_through = true; return TLC_OK; }
+  const char* tenv = getenv("TLC_STAGE_TIMING");
+  g->timing = tenv && atoi(tenv) != 0;
+  StageTimer tm(g->timing, st, &g->ev_pool, g->ev_base);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  if (g->timing) { ev0 = tm.take(); ev1 = tm.take(); ev2 = tm.take(); }
+  VicinityScratch vs = make_vs(g);
+  int* counters = reinterpret_cast<int*>(g->sm_dev);
+  SmallStats* d_stats = reinterpret_cast<SmallStats*>(g->sm_dev + SM_STATS_OFF);
+  launch_ball_cache(g->gv, p, d_targets, E, vs, st);
+  if (ev0) cudaEventRecord(ev0, st);
+  launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, counters, nullptr, nullptr,
+               nullptr, d_stats, g->sm_count, st, ev1);
+  if (ev2) cudaEventRecord(ev2, st);
+  CK(cudaMemcpyAsync(g->sm_host, g->sm_dev, SM_STATS_OFF + sizeof(SmallStats), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int nC = reinterpret_cast<const int*>(g->sm_host)[1];
+  const SmallStats hs = *reinterpret_cast<const SmallStats*>(g->sm_host + SM_STATS_OFF);
+  float msA = 0, msB = 0;
+  if (g->timing) { cudaEventElapsedTime(&msA, ev0, ev1); cudaEventElapsedTime(&msB, ev1, ev2); }
+  // a call whose vicinities are mostly too large: do not try again for a while (the size check alone costs a pass over
+  // two ball bitmaps per target)
+  if ((int64_t)nC * 4 > E * 3) g->small_skip = 32;
+  if (nC == E) { *fell_through = true; return TLC_OK; }  // nothing handled: the staged pipeline takes the whole call
+  double o_ms[10] = {0};
+  int64_t s_live = 0, s_nv = 0, s_ne = 0, s_fb = 0, s_general = 0, s_rowcheck = 0, s_blocks = 0, s_direct = 0;
+  int s_chunks = 0;
+  double s_bytes = 0;
+  if (nC > 0) {
+    if ((rc = ensure_small_sub(g, nC, r2))) return rc;
+    launch_gather_targets(d_targets, g->sm_list_c, nC, g->sm_sub, g->sm_idx, st);
+    tlc_params up2 = *up;
+    up2.flags |= TLC_F_NO_SMALL;
+    const size_t keep_base = g->ev_base;
+    g->ev_base = tm.used;
+    rc = run_staged(g, g->sm_sub, nC, &up2, g->sm_pi, g->sm_pi32, g->sm_st, nullptr, nullptr);
+    g->ev_base = keep_base;
+    if (rc) return rc;
+    launch_scatter_rows(g->sm_pi, d_pi32 ? g->sm_pi32 : nullptr, d_status ? g->sm_st : nullptr, g->sm_idx, nC, r2, d_pi, d_pi32,
+                        d_status, g->sm_count, st);
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 10; i++) o_ms[i] = g->stage_ms[i];
+    s_live = g->last_live; s_nv = g->last_nv; s_ne = g->last_ne; s_fb = g->last_fb; s_general = g->last_general;
+    s_rowcheck = g->last_rowcheck; s_blocks = g->last_blocks; s_direct = g->last_direct; s_chunks = g->nchunks; s_bytes = g->alg_bytes;
+  }
+  for (int i = 0; i < 10; i++) g->stage_ms[i] = o_ms[i];
+  g->stage_ms[9] += msA + msB;
+  g->small_ms[0] = msA; g->small_ms[1] = msB;
+  g->small_rows[0] = (int64_t)hs.handled[0]; g->small_rows[1] = (int64_t)hs.handled[1]; g->small_rows[2] = nC;
+  g->last_live = s_live + (int64_t)hs.live; g->last_nv = s_nv + (int64_t)hs.sum_n; g->last_ne = s_ne + (int64_t)hs.sum_m;
+  g->last_fb = s_fb; g->last_general = s_general; g->last_rowcheck = s_rowcheck; g->last_blocks = s_blocks; g->last_direct = s_direct;
+  g->nchunks = s_chunks;
+  g->alg_bytes = s_bytes + hs.bytes;
+  if (cnt_compute) {
+    *cnt_compute = 0;
+    if (d_status) {
+      if ((rc = ensure_pinned(g, (size_t)E + ALIGN))) return rc;
+      uint8_t* h_st = reinterpret_cast<uint8_t*>(g->h_pin);
+      CK(cudaMemcpyAsync(h_st, d_status, (size_t)E, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      int64_t cnt = 0;
+      for (int64_t i = 0; i < E; i++) cnt += h_st[i] <= TLC_ST_TRIVIAL;
+      *cnt_compute = cnt;
+    }
+  }
+  CK(cudaGetLastError());
+  return TLC_OK;
+}
+
+// the whole path over device-resident targets: kernel S where it applies, the staged pipeline for everything else
+static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const tlc_params* up, double* d_pi,
+                        float* d_pi32, uint8_t* d_status, int64_t* cnt_compute, tlc_detail* detail) {
+  int rc = check_params(up);
+  if (rc) return rc;
+  g->small_ms[0] = g->small_ms[1] = 0;
+  g->small_rows[0] = g->small_rows[1] = g->small_rows[2] = 0;
+  if (small_applicable(g, up, E, detail)) {
+    bool fell = false;
+    rc = run_small(g, d_targets, E, up, d_pi, d_pi32, d_status, cnt_compute, &fell);
+    if (rc || !fell) return rc;
+  }
+  return run_staged(g, d_targets, E, up, d_pi, d_pi32, d_status, cnt_compute, detail);
+}
+
 // =================================================================================================
 // C-ABI
 // =================================================================================================
+static int graph_upload(tlc_graph* g, int32_t N, int64_t nnz, const int32_t* rowptr, const int32_t* col, const double* kappa);
+
 extern "C" {
 
 const char* tlc_last_error(void) { return g_err.c_str(); }
@@ -774,6 +954,29 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
                      uint64_t arena_bytes, tlc_graph** out) {
   if (!out || !rowptr || (nnz > 0 && (!col || !kappa)) || N <= 0 || nnz < 0) return fail(TLC_E_INVALID, "bad graph arguments");
   if (rowptr[0] != 0 || rowptr[N] != nnz) return fail(TLC_E_INVALID, "rowptr[0] != 0 or rowptr[N] != nnz");
+  // The kernels index bitmaps / ball rows by col[] and bisect the rows: a malformed CSR would mean out-of-bounds device
+  // accesses, so the whole contract is checked here, once per graph (O(nnz log deg) on the host):
+  //   rowptr monotone; col in [0, N), strictly ascending inside a row (no duplicates), no self-loops; every (x, y) has its
+  //   mirror (y, x) with the same curvature (graph2pi.__init__ sets ricci_curv[(a,b)] = ricci_curv[(b,a)], riccidist2dgm.py:222-225);
+  //   weight kappa + 1 finite and > 0 (networkx's Dijkstra precondition; kernel 1b orders distances by their bit patterns)
+  for (int32_t x = 0; x < N; x++)
+    if (rowptr[x + 1] < rowptr[x]) return fail(TLC_E_INVALID, "rowptr is not monotone at node " + std::to_string(x));
+  for (int32_t x = 0; x < N; x++) {
+    for (int64_t e = rowptr[x]; e < rowptr[x + 1]; e++) {
+      const int32_t y = col[e];
+      if (y < 0 || y >= N) return fail(TLC_E_INVALID, "col out of range in row " + std::to_string(x));
+      if (y == x) return fail(TLC_E_INVALID, "self-loop at node " + std::to_string(x));
+      if (e > rowptr[x] && col[e - 1] >= y) return fail(TLC_E_INVALID, "row " + std::to_string(x) + " is not strictly ascending");
+      const double w = kappa[e] + 1.0;
+      if (!(w > 0.0) || !std::isfinite(w))
+        return fail(TLC_E_INVALID, "kappa + 1 must be finite and > 0 (edge " + std::to_string(x) + "-" + std::to_string(y) + ")");
+      const int32_t* lo = col + rowptr[y];
+      const int32_t* hi = col + rowptr[y + 1];
+      const int32_t* it = std::lower_bound(lo, hi, x);
+      if (it == hi || *it != x) return fail(TLC_E_INVALID, "graph is not symmetric: (" + std::to_string(x) + "," + std::to_string(y) + ") has no mirror entry");
+      if (kappa[it - col] != kappa[e]) return fail(TLC_E_INVALID, "curvature of (" + std::to_string(x) + "," + std::to_string(y) + ") differs from its mirror entry");
+    }
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
   if (device < 0 || device >= ndev) return fail(TLC_E_INVALID, "device index out of range");
@@ -781,6 +984,18 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
   tlc_graph* g = new tlc_graph();
   g->device = device;
   g->arena_req = (size_t)arena_bytes;
+  const int rc = graph_upload(g, N, nnz, rowptr, col, kappa);
+  if (rc != TLC_OK) { const std::string keep = g_err; tlc_graph_destroy(g); g_err = keep; return rc; }  // nothing leaks on a failed create
+  *out = g;
+  return TLC_OK;
+}
+
+}  // extern "C"
+
+// device side of tlc_graph_create: every allocation is stored in *g as soon as it exists, so the caller can free a
+// partially built graph with tlc_graph_destroy
+static int graph_upload(tlc_graph* g, int32_t N, int64_t nnz, const int32_t* rowptr, const int32_t* col, const double* kappa) {
+  const int device = g->device;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   g->sm_count = prop.multiProcessorCount;
@@ -793,17 +1008,24 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
       CK(cudaEventCreateWithFlags(&g->ev_join[i], cudaEventDisableTiming));
     }
   }
-  int32_t *d_rowptr = nullptr, *d_col = nullptr;
-  double* d_kappa = nullptr;
-  CK(cudaMalloc((void**)&d_rowptr, (size_t)(N + 1) * 4));
-  CK(cudaMalloc((void**)&d_col, std::max<size_t>((size_t)nnz * 4, 16)));
-  CK(cudaMalloc((void**)&d_kappa, std::max<size_t>((size_t)nnz * 8, 16)));
-  CK(cudaMemcpy(d_rowptr, rowptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice));
+  g->gv = GraphView{N, nnz, nullptr, nullptr, nullptr, nullptr};
+  CK(cudaMalloc((void**)&g->gv.rowptr, (size_t)(N + 1) * 4));
+  CK(cudaMalloc((void**)&g->gv.col, std::max<size_t>((size_t)nnz * 4, 16)));
+  CK(cudaMalloc((void**)&g->gv.kappa, std::max<size_t>((size_t)nnz * 8, 16)));
+  CK(cudaMemcpy((void*)g->gv.rowptr, rowptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice));
   if (nnz) {
-    CK(cudaMemcpy(d_col, col, (size_t)nnz * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_kappa, kappa, (size_t)nnz * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((void*)g->gv.col, col, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((void*)g->gv.kappa, kappa, (size_t)nnz * 8, cudaMemcpyHostToDevice));
   }
-  g->gv = GraphView{N, nnz, d_rowptr, d_col, d_kappa};
+  {
+    // interleaved row records for kernel 1b's graph-row route: {id, 0, weight}; the weight is this IEEE double add
+    struct Rec { uint32_t id, pad; double w; };
+    static_assert(sizeof(Rec) == 16, "row record must be 16 bytes");
+    std::vector<Rec> rec((size_t)nnz);
+    for (int64_t e = 0; e < nnz; e++) rec[(size_t)e] = Rec{(uint32_t)col[e], 0u, kappa[e] + 1.0};
+    CK(cudaMalloc((void**)&g->gv.rec, std::max<size_t>((size_t)nnz * 16, 16)));
+    if (nnz) CK(cudaMemcpy((void*)g->gv.rec, rec.data(), (size_t)nnz * 16, cudaMemcpyHostToDevice));
+  }
   {
     // per node: smallest weight kappa + 1 of its row as a float rounded DOWN (settling margin of the graph-row route)
     std::vector<float> mw((size_t)N, 3.0e38f);
@@ -819,14 +1041,15 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
   }
 
   CK(cudaMalloc((void**)&g->work_counter, 64));
-  *out = g;
   return TLC_OK;
 }
+
+extern "C" {
 
 int tlc_graph_destroy(tlc_graph* g) {
   if (!g) return TLC_OK;
   cudaSetDevice(g->device);
-  cudaFree((void*)g->gv.rowptr); cudaFree((void*)g->gv.col); cudaFree((void*)g->gv.kappa);
+  cudaFree((void*)g->gv.rowptr); cudaFree((void*)g->gv.col); cudaFree((void*)g->gv.kappa); cudaFree((void*)g->gv.rec);
   cudaFree(g->arena); cudaFree(g->bitmaps); cudaFree(g->queue); cudaFree(g->work_counter);
   cudaFree(g->ball_cache); cudaFree(g->ball_acc); cudaFree(g->ball_state); cudaFree(g->ball_list);
   cudaFree(g->d_n); cudaFree(g->d_m); cudaFree(g->d_ds); cudaFree(g->d_st); cudaFree(g->d_bytes);
@@ -835,6 +1058,10 @@ int tlc_graph_destroy(tlc_graph* g) {
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   for (int i = 0; i < 3; i++) { if (g->side[i]) cudaStreamDestroy(g->side[i]); if (g->ev_join[i]) cudaEventDestroy(g->ev_join[i]); }
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  cudaFree(g->sm_list_b); cudaFree(g->sm_list_c); cudaFree(g->sm_sub); cudaFree(g->sm_idx); cudaFree(g->sm_pi);
+  cudaFree(g->sm_pi32); cudaFree(g->sm_st); cudaFree(g->sm_dev);
+  if (g->sm_host) cudaFreeHost(g->sm_host);
+  for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   delete g;
   return TLC_OK;
 }
@@ -843,11 +1070,13 @@ int tlc_vicinity_pi_dev(tlc_graph* g, const int32_t* dev_targets, int64_t E, con
                         float* dev_out_pi_f32, uint8_t* dev_out_status, int64_t* cnt_compute) {
   if (!g || (E > 0 && (!dev_targets || !dev_out_pi))) return fail(TLC_E_INVALID, "NULL argument");
   uint8_t* st = dev_out_status;
-  uint8_t* tmp = nullptr;
-  if (!st && cnt_compute && E > 0) { CK(cudaSetDevice(g->device)); CK(cudaMalloc((void**)&tmp, (size_t)E)); st = tmp; }
-  const int rc = run_pipeline(g, dev_targets, E, p, dev_out_pi, dev_out_pi_f32, st, cnt_compute, nullptr);
-  if (tmp) cudaFree(tmp);
-  return rc;
+  if (!st && cnt_compute && E > 0) {  // the count needs the statuses: the graph's grow-only staging, no cudaMalloc per call
+    CK(cudaSetDevice(g->device));
+    const int rc0 = ensure_io_buffers(g, E, 0);
+    if (rc0) return rc0;
+    st = g->io_st;
+  }
+  return run_pipeline(g, dev_targets, E, p, dev_out_pi, dev_out_pi_f32, st, cnt_compute, nullptr);
 }
 
 int tlc_vicinity_pi(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_params* p, double* out_pi,
@@ -884,8 +1113,8 @@ int tlc_vicinity_sizes(tlc_graph* g, const int32_t* targets, int64_t E, const tl
   Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
   if ((rc = ensure_call_buffers(g, E))) return rc;
   if ((rc = ensure_vicinity_scratch(g, p))) return rc;
-  int32_t* d_t = nullptr;
-  CK(cudaMalloc((void**)&d_t, (size_t)E * 8));
+  if ((rc = ensure_io_buffers(g, E, 0))) return rc;  // grow-only device staging: no cudaMalloc / cudaFree per call
+  int32_t* d_t = g->io_t;
   CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
   VicinityScratch vs = make_vs(g);
   launch_ball_cache(g->gv, p, d_t, E, vs, g->stream);
@@ -894,7 +1123,6 @@ int tlc_vicinity_sizes(tlc_graph* g, const int32_t* targets, int64_t E, const tl
   if (out_m) CK(cudaMemcpyAsync(out_m, g->d_m, (size_t)E * 4, cudaMemcpyDeviceToHost, g->stream));
   if (out_status) CK(cudaMemcpyAsync(out_status, g->d_st, (size_t)E, cudaMemcpyDeviceToHost, g->stream));
   CK(cudaStreamSynchronize(g->stream));
-  cudaFree(d_t);
   CK(cudaGetLastError());
   return TLC_OK;
 }
@@ -906,12 +1134,10 @@ int tlc_vicinity_detail(tlc_graph* g, const int32_t* targets, int64_t E, const t
   if (E == 0) return TLC_OK;
   CK(cudaSetDevice(g->device));
   const int r2 = p->resolution * p->resolution;
-  int32_t* d_t = nullptr;
-  double* d_pi = nullptr;
-  uint8_t* d_st = nullptr;
-  CK(cudaMalloc((void**)&d_t, (size_t)E * 8));
-  CK(cudaMalloc((void**)&d_pi, (size_t)E * r2 * 8));
-  CK(cudaMalloc((void**)&d_st, (size_t)E));
+  if ((rc = ensure_io_buffers(g, E, r2))) return rc;  // grow-only device staging shared with tlc_vicinity_pi
+  int32_t* d_t = g->io_t;
+  double* d_pi = g->io_pi;
+  uint8_t* d_st = g->io_st;
   CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
   int64_t cnt = 0;
   g->detail_chunk.T = 0;
@@ -930,8 +1156,62 @@ int tlc_vicinity_detail(tlc_graph* g, const int32_t* targets, int64_t E, const t
         cudaStreamSynchronize(g->stream) != cudaSuccess)
       rc = fail(TLC_E_CUDA, "copy back failed");
   }
-  cudaFree(d_t); cudaFree(d_pi); cudaFree(d_st);
   return rc;
+}
+
+int tlc_small_diagrams(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_params* up, const int64_t* poff,
+                       int32_t* npairs, int32_t* pkind, int32_t* pbv, int32_t* pdv, double* pbirth, double* pdeath,
+                       double* out_pi, uint8_t* out_status, int32_t* out_n, int32_t* out_m) {
+  if (!g || (E > 0 && (!targets || !poff))) return fail(TLC_E_INVALID, "NULL argument");
+  int rc = check_params(up);
+  if (rc) return rc;
+  if (E == 0) return TLC_OK;
+  if (E >= ((int64_t)1 << 31)) return fail(TLC_E_INVALID, "E must be < 2^31");
+  if (up->resolution != 5 || up->descriptor < 0 || up->descriptor > 2 ||
+      (up->flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)))
+    return fail(TLC_E_INVALID, "kernel S serves the Ricci-distance filtrations with a 5 x 5 image");
+  CK(cudaSetDevice(g->device));
+  Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
+  if ((rc = ensure_call_buffers(g, E))) return rc;
+  if ((rc = ensure_vicinity_scratch(g, p))) return rc;
+  if (!g->ball_cache) return fail(TLC_E_NOMEM, "no ball cache for this graph (TLC_BALL_CACHE_GB)");
+  if ((rc = ensure_small_buffers(g, E))) return rc;
+  if ((rc = ensure_io_buffers(g, E, 25))) return rc;
+  const int64_t P = poff[E];
+  DevBuf b_poff, b_np, b_kind, b_bv, b_dv, b_birth, b_death;
+  CK(b_poff.alloc((size_t)(E + 1) * 8)); CK(b_np.alloc((size_t)E * 4)); CK(b_kind.alloc((size_t)P + 16));
+  CK(b_bv.alloc((size_t)P * 4 + 16)); CK(b_dv.alloc((size_t)P * 4 + 16)); CK(b_birth.alloc((size_t)P * 8 + 16)); CK(b_death.alloc((size_t)P * 8 + 16));
+  cudaStream_t st = g->stream;
+  CK(cudaMemcpyAsync(g->io_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(b_poff.p, poff, (size_t)(E + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(b_np.p, 0, (size_t)E * 4, st));
+  CK(cudaMemsetAsync(g->io_st, 255, (size_t)E, st));  // rows kernel S does not take keep TLC_ST_NOT_SMALL
+  CK(cudaMemsetAsync(g->io_pi, 0, (size_t)E * 25 * 8, st));
+  CK(cudaMemsetAsync(g->d_n, 0, (size_t)E * 4, st));
+  CK(cudaMemsetAsync(g->d_m, 0, (size_t)E * 4, st));
+  SmallDiag dg{b_poff.as<int64_t>(), b_np.as<int32_t>(), b_kind.as<uint8_t>(), b_bv.as<int32_t>(), b_dv.as<int32_t>(),
+               b_birth.as<double>(), b_death.as<double>()};
+  VicinityScratch vs = make_vs(g);
+  launch_ball_cache(g->gv, p, g->io_t, E, vs, st);
+  launch_small(g->gv, p, g->io_t, E, vs, g->io_pi, nullptr, g->io_st, g->sm_list_b, g->sm_list_c,
+               reinterpret_cast<int*>(g->sm_dev), g->d_n, g->d_m, &dg, nullptr, g->sm_count, st, nullptr);
+  std::vector<uint8_t> k8((size_t)P + 1);
+  if (npairs) CK(cudaMemcpyAsync(npairs, b_np.p, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+  if (P > 0) {
+    CK(cudaMemcpyAsync(k8.data(), b_kind.p, (size_t)P, cudaMemcpyDeviceToHost, st));
+    if (pbv) CK(cudaMemcpyAsync(pbv, b_bv.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    if (pdv) CK(cudaMemcpyAsync(pdv, b_dv.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    if (pbirth) CK(cudaMemcpyAsync(pbirth, b_birth.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    if (pdeath) CK(cudaMemcpyAsync(pdeath, b_death.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (out_pi) CK(cudaMemcpyAsync(out_pi, g->io_pi, (size_t)E * 25 * 8, cudaMemcpyDeviceToHost, st));
+  if (out_status) CK(cudaMemcpyAsync(out_status, g->io_st, (size_t)E, cudaMemcpyDeviceToHost, st));
+  if (out_n) CK(cudaMemcpyAsync(out_n, g->d_n, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+  if (out_m) CK(cudaMemcpyAsync(out_m, g->d_m, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (pkind) for (int64_t i = 0; i < P; i++) pkind[i] = k8[(size_t)i];
+  return TLC_OK;
 }
 
 int tlc_union_find(int device, int32_t n, int32_t m, const double* fval, const int32_t* a, const int32_t* b, uint32_t flags,
@@ -1029,8 +1309,15 @@ int tlc_pi_gather(int device, const double* dev_table, int64_t rows, int32_t r2,
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
   if (device < 0 || device >= ndev) return fail(TLC_E_INVALID, "device index out of range");
   CK(cudaSetDevice(device));
-  static thread_local int* d_bad[64] = {nullptr};
-  static thread_local int sms[64] = {0};
+  // per host thread and device: the out-of-range flag and the SM count; released when the thread exits
+  struct GatherScratch {
+    int* d_bad[64] = {nullptr};
+    int sms[64] = {0};
+    ~GatherScratch() { for (int i = 0; i < 64; i++) if (d_bad[i]) cudaFree(d_bad[i]); }
+  };
+  static thread_local GatherScratch gs;
+  int** d_bad = gs.d_bad;
+  int* sms = gs.sms;
   if (device >= 64) return fail(TLC_E_INVALID, "device index out of range");
   if (!d_bad[device]) {
     CK(cudaMalloc((void**)&d_bad[device], sizeof(int)));
@@ -1063,6 +1350,13 @@ int tlc_last_counts(tlc_graph* g, int64_t* out5) {  // out5: 8 slots
 }
 
 int64_t tlc_last_direct(tlc_graph* g) { return g ? g->last_direct : 0; }
+
+int tlc_last_small(tlc_graph* g, double* out5) {
+  if (!g || !out5) return TLC_E_INVALID;
+  out5[0] = g->small_ms[0]; out5[1] = g->small_ms[1];
+  out5[2] = (double)g->small_rows[0]; out5[3] = (double)g->small_rows[1]; out5[4] = (double)g->small_rows[2];
+  return TLC_OK;
+}
 
 int tlc_last_stage_ms(tlc_graph* g, double* out10) {
   if (!g || !out10) return 0;

@@ -16,6 +16,9 @@ struct GraphView {
   const int32_t* rowptr;  // [N+1]
   const int32_t* col;     // [nnz] ascending per row
   const double* kappa;    // [nnz]
+  // [nnz] interleaved row records {u32 neighbour id, u32 0, f64 weight = kappa + 1}: ONE 128-bit load per row entry on
+  // the graph-row route of kernel 1b (the weight is the host's IEEE double add, bit-identical to __dadd_rn(kappa, 1.0))
+  const uint4* rec;
 };
 
 // All device pointers of one chunk of targets.  Vertex-indexed arrays are addressed at voff[t],
@@ -203,6 +206,26 @@ void launch_gather_rows(const double* table, int64_t rows, int r2, const int64_t
 
 void launch_scatter_rows(const double* src_pi, const float* src_pi32, const uint8_t* src_st, const int64_t* idx, int64_t k,
                          int r2, double* dst_pi, float* dst_pi32, uint8_t* dst_st, int sm_count, cudaStream_t st);
+
+// kernel S (k0_small.cu): the whole path for small vicinities in one launch per size class
+struct SmallDiag {  // optional diagram output: pairs of row t at poff[t] (capacity n + m + 2 per row)
+  const int64_t* poff;
+  int32_t* np;
+  uint8_t* kind;
+  int32_t *bv, *dv;
+  double *birth, *death;
+};
+struct SmallStats {  // device accumulators of one call
+  unsigned long long handled[2];  // rows finished by class A / class B (any status)
+  unsigned long long live, sum_n, sum_m;  // over the rows with status <= TRIVIAL
+  double bytes;                   // their compulsory bytes B_e
+};
+void launch_small(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
+                  double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int* counters,
+                  int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count, cudaStream_t st,
+                  cudaEvent_t ev_mid);
+// rows of a sub-list: sub[i] = targets[list[i]], idx[i] = list[i]
+void launch_gather_targets(const int32_t* targets, const int32_t* list, int64_t k, int32_t* sub, int64_t* idx, cudaStream_t st);
 
 int64_t launch_count();
 void count_launch();

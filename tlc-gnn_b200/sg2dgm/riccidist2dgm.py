@@ -4,6 +4,7 @@
 whole batch (the reference maps a GIL-bound thread pool over edges, :367-370).  The legacy dionysus
 half of the reference file (graph2dgm, sg2pimg, get_pimg) is out of scope.
 """
+import sys
 import time
 
 import numpy as np
@@ -16,15 +17,25 @@ __all__ = ["graph2pi", "filtration"]
 _DESCRIPTORS = ("min", "max", "sum")
 
 
+def default_plain_sum():
+    """True when float sum() of the running interpreter adds left to right (CPython <= 3.11), False when it is
+    Neumaier-compensated (CPython >= 3.12)."""
+    return sys.version_info < (3, 12)
+
+
 class graph2pi():
-    def __init__(self, g, ricci_curv, device=0, plain_sum=False):
+    def __init__(self, g, ricci_curv, device=0, plain_sum=None):
         """g: networkx-like graph (needs .nodes() and .edges()); ricci_curv: [[n1, n2, kappa], ...]
         (both directions, loaddatas.py:117-121).  Nodes are relabelled to integers in g.nodes() order
         exactly as nx.convert_node_labels_to_integers does (riccidist2dgm.py:217-220).
-        plain_sum: add the path weights of build_fv (:30,35) left to right, as sum() of CPython <= 3.11 does (the
-        reference pins 3.7); default: the Neumaier-compensated sum() of CPython >= 3.12.  The two only
-        differ in the last bits, and only for weights that are not exactly representable sums."""
-        self.plain_sum = bool(plain_sum)
+        plain_sum: how build_fv's `sum([...])` of the path weights (:30,35) is evaluated -- it is the ONE place where the
+        reference's float64 results depend on the interpreter.  True: left to right, as sum() of CPython <= 3.11 does
+        (the reference pins CPython 3.7: PersistenceImager.cpython-37m, requirements.txt).  False: the Neumaier-
+        compensated sum() of CPython >= 3.12.  Default (None): whatever sum() of the RUNNING interpreter does, so the
+        drop-in reproduces the reference executed in the caller's own environment; pass True to reproduce tables cached
+        by the reference under its pinned 3.7.  The two differ in the last bits only, and only for curvatures whose
+        path sums are not exactly representable."""
+        self.plain_sum = default_plain_sum() if plain_sum is None else bool(plain_sum)
         nodes = list(g.nodes())
         self.dict_node = {old: new for new, old in enumerate(nodes)}
         self.old_label = nodes
@@ -34,7 +45,10 @@ class graph2pi():
         edges = edges[edges[:, 0] != edges[:, 1]]
         lo = np.minimum(edges[:, 0], edges[:, 1])
         hi = np.maximum(edges[:, 0], edges[:, 1])
-        key = lo * max(N, 1) + hi
+        # one entry per UNDIRECTED edge: a DiGraph listing both (a,b) and (b,a), or a MultiGraph, must not yield duplicate
+        # CSR entries (nx.Graph semantics of the reference's subgraph views; tlc_graph_create rejects duplicate row entries)
+        key = np.unique(lo * max(N, 1) + hi)
+        lo, hi = key // max(N, 1), key % max(N, 1)
         # curvature per undirected edge; a later entry overwrites an earlier one (dict semantics, :222-226).
         # Edges without an entry have no 'weight' attribute: networkx then uses weight 1 for Dijkstra but
         # ricci_curv[...] raises KeyError -> dist = 100; such graphs are outside the contract (kappa given
@@ -67,10 +81,10 @@ class graph2pi():
             self._int_labels = (lab[o], o.astype(np.int32))
 
     @classmethod
-    def from_csr(cls, rowptr, col, kappa, device=0):
+    def from_csr(cls, rowptr, col, kappa, device=0, plain_sum=None):
         """graph already in integer ids 0..N-1 (CSR, ascending rows): skips the networkx ingestion."""
         self = cls.__new__(cls)
-        self.plain_sum = False
+        self.plain_sum = default_plain_sum() if plain_sum is None else bool(plain_sum)
         self.csr = (rowptr, col, kappa)
         self._graph = api.VicinityGraph(rowptr, col, kappa, device=device)
         self.N = self._graph.N

@@ -11,6 +11,25 @@ import numpy as np
 from . import _lib as L
 
 
+_CUDA_STREAM_LEGACY = 0x1  # cudaStreamLegacy (driver_types.h): an explicit handle of the legacy default stream
+
+
+def _dev_ptr(t, dtype_name, shape, device_index, what):
+    """data pointer of a torch CUDA tensor that crosses the C-ABI: dtype, shape, contiguity and device are checked here,
+    because the library can only see a raw address."""
+    if t is None:
+        return None
+    if str(t.dtype) != "torch." + dtype_name:
+        raise TypeError("%s must be %s, got %s" % (what, dtype_name, t.dtype))
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (what, tuple(shape), tuple(t.shape)))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % what)
+    if t.device.type != "cuda" or (t.device.index is not None and t.device.index != device_index):
+        raise ValueError("%s must live on cuda:%d, got %s" % (what, device_index, t.device))
+    return t.data_ptr()
+
+
 def make_params(hop=2, mode=L.MODE_EDGE, descriptor="sum", resolution=5, flags=L.F_NORM, img_mask=None):
     d = L.DESC.get(descriptor, -1) if isinstance(descriptor, str) else int(descriptor)
     if img_mask is None:
@@ -70,11 +89,13 @@ class VicinityGraph:
         torch CUDA tensors; only their data pointers cross the C-ABI."""
         E = int(targets_dev.shape[0])
         p = make_params(hop, mode, descriptor, resolution, flags, img_mask)
+        r2 = int(resolution) * int(resolution)
         cnt = C.c_int64(0)
         L.check(L.lib().tlc_vicinity_pi_dev(
-            self._h, targets_dev.data_ptr(), E, C.byref(p), out_pi.data_ptr(),
-            out_pi_f32.data_ptr() if out_pi_f32 is not None else None,
-            out_status.data_ptr() if out_status is not None else None,
+            self._h, _dev_ptr(targets_dev, "int32", (E, 2), self.device, "targets_dev"), E, C.byref(p),
+            _dev_ptr(out_pi, "float64", (E, r2), self.device, "out_pi"),
+            _dev_ptr(out_pi_f32, "float32", (E, r2), self.device, "out_pi_f32"),
+            _dev_ptr(out_status, "uint8", (E,), self.device, "out_status"),
             C.byref(cnt) if want_count else None))
         return int(cnt.value)
 
@@ -134,6 +155,39 @@ class VicinityGraph:
         out["neg"] = a["neg"][vo:vo + a["nneg"][i]]
         return out
 
+    def small_diagrams(self, targets, hop=2, mode=L.MODE_EDGE, descriptor="sum", flags=L.F_NORM, img_mask=None):
+        """diagrams straight from the fused small-vicinity kernels (kernel S): a list with one dict per target
+        (status, n, m, img, pkind, pbv, pdv, pbirth, pdeath); targets kernel S cannot take have status ST_NOT_SMALL."""
+        t = np.ascontiguousarray(targets, dtype=np.int32).reshape(-1, 2)
+        E = t.shape[0]
+        n, m, _ = self.vicinity_sizes(t, hop, mode)
+        cap = n.astype(np.int64) + m.astype(np.int64) + 2
+        poff = np.zeros(E + 1, np.int64)
+        np.cumsum(cap, out=poff[1:])
+        P = int(poff[-1])
+        p = make_params(hop, mode, descriptor, 5, flags, img_mask)
+        npairs = np.zeros(E, np.int32)
+        pkind = np.zeros(P + 1, np.int32); pbv = np.zeros(P + 1, np.int32); pdv = np.zeros(P + 1, np.int32)
+        pbirth = np.zeros(P + 1); pdeath = np.zeros(P + 1)
+        pi = np.zeros((E, 25)); st = np.zeros(E, np.uint8)
+        on = np.zeros(E, np.int32); om = np.zeros(E, np.int32)
+        L.check(L.lib().tlc_small_diagrams(self._h, t.ctypes.data, E, C.byref(p), poff.ctypes.data, npairs.ctypes.data,
+                                           pkind.ctypes.data, pbv.ctypes.data, pdv.ctypes.data, pbirth.ctypes.data,
+                                           pdeath.ctypes.data, pi.ctypes.data, st.ctypes.data, on.ctypes.data, om.ctypes.data))
+        out = []
+        for i in range(E):
+            a, b = int(poff[i]), int(poff[i]) + int(npairs[i])
+            out.append(dict(status=int(st[i]), n=int(on[i]), m=int(om[i]), img=pi[i], pkind=pkind[a:b], pbv=pbv[a:b],
+                            pdv=pdv[a:b], pbirth=pbirth[a:b], pdeath=pdeath[a:b]))
+        return out
+
+    def last_small(self):
+        """kernel S in the last call: device ms of its two launches (TLC_STAGE_TIMING=1), rows finished per class, rows
+        handed on to the staged pipeline."""
+        out = np.zeros(5)
+        L.lib().tlc_last_small(self._h, out.ctypes.data)
+        return dict(ms_a=float(out[0]), ms_b=float(out[1]), rows_a=int(out[2]), rows_b=int(out[3]), rows_staged=int(out[4]))
+
     def last_stage_ms(self):
         out = np.zeros(10)
         nch = L.lib().tlc_last_stage_ms(self._h, out.ctypes.data)
@@ -141,8 +195,15 @@ class VicinityGraph:
         return dict(zip(names, out.tolist())), int(nch)
 
     def set_stream(self, cuda_stream_ptr):
-        """run on a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream (None: own stream)."""
-        L.check(L.lib().tlc_graph_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+        """run on a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream.
+        None restores the graph's own (non-blocking) stream.  0 -- what torch reports for its default stream -- selects the
+        LEGACY default stream (cudaStreamLegacy), i.e. the stream the caller's default-stream work is ordered with; it is
+        not silently replaced by the library's own stream."""
+        if cuda_stream_ptr is None:
+            ptr = None
+        else:
+            ptr = C.c_void_p(int(cuda_stream_ptr) if int(cuda_stream_ptr) != 0 else _CUDA_STREAM_LEGACY)
+        L.check(L.lib().tlc_graph_set_stream(self._h, ptr))
 
     def last_counts(self):
         out = np.zeros(8, np.int64)

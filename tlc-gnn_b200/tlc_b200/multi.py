@@ -123,15 +123,28 @@ def cuda_local_fn(graph, device, hop=2, descriptor="sum", resolution=5, flags=1,
     """the product's per-rank compute: one C-ABI call on this rank's shard, rows stay in HBM."""
     import torch
 
+    bufs = {}
+
     def fn(tshard):
         k = tshard.shape[0]
         r2 = resolution * resolution
+        # The library writes its outputs on the GRAPH's stream; the tensors here come from torch's caching allocator
+        # and are consumed (pad copy, all-gather) on torch's CURRENT stream.  Both must be the same stream, or a buffer
+        # could be recycled and overwritten while an earlier batch's copy is still pending: the graph is therefore bound
+        # to torch's current stream for the call.
+        graph.set_stream(torch.cuda.current_stream(device).cuda_stream)
         tg = tshard if torch.is_tensor(tshard) else torch.from_numpy(np.ascontiguousarray(tshard)).to(device)
-        pi64 = torch.empty((max(k, 1), r2), dtype=torch.float64, device=device)
-        pi32 = torch.empty((max(k, 1), r2), dtype=torch.float32, device=device)
-        st = torch.empty((max(k, 1),), dtype=torch.uint8, device=device)
+        if tg.dtype != torch.int32 or not tg.is_contiguous():
+            tg = tg.to(torch.int32).contiguous()
+        if bufs.get("cap", -1) < k:  # output staging reused from batch to batch (grow-only): no allocator traffic per call
+            cap = max(k, 1)
+            bufs["pi64"] = torch.empty((cap, r2), dtype=torch.float64, device=device)
+            bufs["pi32"] = torch.empty((cap, r2), dtype=torch.float32, device=device)
+            bufs["st"] = torch.empty((cap,), dtype=torch.uint8, device=device)
+            bufs["cap"] = cap
+        pi64, pi32, st = bufs["pi64"][:k], bufs["pi32"][:k], bufs["st"][:k]
         if k:
             graph.vicinity_pi_dev(tg, pi64, pi32, st, hop=hop, mode=mode, descriptor=descriptor,
                                   resolution=resolution, flags=flags)
-        return pi32[:k], st[:k]
+        return pi32, st
     return fn
