@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--negatives", type=int, default=0, help="append an equal number of seeded non-adjacent pairs (collab config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--secondary", type=int, default=int(os.environ.get("TLC_BENCH_SECONDARY", "1")),
+                    help="1: also measure the other BASELINE.json configurations (a few steps each) into the `secondary` object")
     return ap.parse_args()
 
 
@@ -107,6 +109,8 @@ def config_dict(args, world):
             "targets_per_gpu_per_step": args.batch, "global_targets_per_step": args.batch * world,
             "kappa": "U(-0.9,0.9) on a 1/1024 grid", "extended_flag": bool(args.extended),
             "l2": "new targets every step; per-step working set >> L2 (no flush needed)",
+            "ball_cache": "warm: the k-hop ball bitmap of a node is expanded once per graph (13.7 k balls serve all 245,861 "
+                          "targets) and the warm-up steps fill it; the timed steps reuse it, as every call after the first does",
             "parallelism": "targets sharded over %d GPU(s), CSR replicated, NCCL all-gather of fp32 images" % world}
 
 
@@ -233,7 +237,8 @@ def run_reference(args):
     value = float(np.mean([b["value"] for b in res]))
     secs = float(np.mean([b["seconds"] for b in res]))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * args.batch * world / value, "sample_ms": 1e3 * secs,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": config_dict(args, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": res[-1]["cores"], "kind": "port",
@@ -241,6 +246,15 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def stage_ms_of(g):
+    """per-stage device ms of the last call: the staged kernels plus kernel S (the fused small-vicinity kernels)"""
+    ms, _ = g.last_stage_ms()
+    sm = g.last_small()
+    ms["small"] = sm["ms_a"] + sm["ms_b"] + sm["ms_c"]
+    ms["small_a"], ms["small_b"], ms["small_c"] = sm["ms_a"], sm["ms_b"], sm["ms_c"]
+    return ms
 
 
 # algorithmic bytes per target of each stage kernel (DESIGN.md section 4), from the vicinity's n, m and the
@@ -252,7 +266,8 @@ def stage_alg_bytes(sum_n, sum_m, be_total, r2, live):
             "filtration": 2.0 * adj + 40.0 * sum_n,                  # every row read once per root + d1, d2, fval, tree
             "vorder": 48.0 * sum_n,                                  # sort keys/payload, rank tables, block table
             "sweep": 12.0 * sum_n,                                   # block table + rank order (+ rows only off the fast path)
-            "image": 4.0 * r2 * live}
+            "image": 4.0 * r2 * live,
+            "small": be_total}               # kernel S is the whole path: the compulsory bytes B_e of its targets
 
 
 def measure_handoff(dev, peak_gbs):
@@ -283,6 +298,110 @@ def measure_handoff(dev, peak_gbs):
     return {"kernel": "gather_rows (tlc_pi_gather)", "rows": int(idx.numel()), "ms": 1e3 * t, "rows_per_s": idx.numel() / t,
             "achieved_gbs": nbytes / 1e9 / t, "frac_of_hbm_peak": nbytes / 1e9 / t / peak_gbs,
             "note": "L2 flushed between repeats (256 MB write); time includes the call's own host sync"}
+
+
+SECONDARY = [  # (key, BASELINE.json config it belongs to, bench arguments)
+    ("C1_cora_hop2", "configs[0]", dict(workload="cora", hop=2, extended=0, mode="edge", negatives=0, batch=5278)),
+    ("C1_cora_hop2_ext", "configs[0], extended_flag=True (the reference's shipped setting)", dict(workload="cora", hop=2, extended=1, mode="edge", negatives=0, batch=5278)),
+    ("C2_pubmed_hop2", "configs[1]", dict(workload="pubmed", hop=2, extended=0, mode="edge", negatives=0, batch=8192)),
+    ("C2_pubmed_hop2_ext", "configs[1], extended_flag=True", dict(workload="pubmed", hop=2, extended=1, mode="edge", negatives=0, batch=8192)),
+    ("C3_computers_hop1_ext", "configs[2] at the reference's own hop for this dataset (baselines/TLCGNN.py:102), extended_flag=True",
+     dict(workload="computers", hop=1, extended=1, mode="edge", negatives=0, batch=8192)),
+    ("C3_computers_hop2_ext", "configs[2], extended_flag=True", dict(workload="computers", hop=2, extended=1, mode="edge", negatives=0, batch=256)),
+    ("C4_ppi24_node_ext", "configs[3]", dict(workload="ppi", hop=2, extended=1, mode="node", negatives=0, batch=4096)),
+    ("C5_collab_neg_hop2", "configs[4] (one GPU's share)", dict(workload="collab", hop=2, extended=0, mode="edge", negatives=1, batch=16384)),
+]
+
+
+def run_secondary(dev, local, peak, cache, steps=3, warmup=2, cpu_seconds=2.5, spot=64):
+    """the other BASELINE.json configurations in the same run, each a short measurement (a few steps) with the same
+    rules as the headline: device-timed value (inputs resident), e2e through the reference-facing call (host in / host
+    out), the CPU port on a bounded sample, the dominant kernel with its roofline fraction, and an oracle spot check."""
+    import torch
+    from tlc_b200 import _lib as L
+    from tlc_b200 import api
+    import sg2dgm.riccidist2dgm as mirror
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    out = {}
+    for key, what, kw in SECONDARY:
+        a = argparse.Namespace(**kw)
+        try:
+            wkey = (a.workload, a.mode, a.negatives)
+            if wkey not in cache:
+                cache.clear()  # (one workload resident at a time)
+                cache[wkey] = make_workload(a.workload, a.mode, a.negatives)
+            c, labels, ne, csr, perm = cache[wkey]
+            g = api.VicinityGraph(*csr, device=local)
+            stream = torch.cuda.Stream(dev)
+            flags, cmode = path_flags(a, L)
+            B, r2 = a.batch, 25
+            out_pi = torch.zeros((B, r2), dtype=torch.float64, device=dev)
+            out_f32 = torch.zeros((B, r2), dtype=torch.float32, device=dev)
+            out_st = torch.zeros((B,), dtype=torch.uint8, device=dev)
+            batches = [torch.from_numpy(batch_targets(ne, perm, s0, 0, 1, B)).to(dev) for s0 in range(warmup + steps)]
+            stage_acc, alg_bytes, sum_n, sum_m, live = {}, 0.0, 0, 0, 0
+            with torch.cuda.stream(stream):
+                g.set_stream(stream.cuda_stream)
+                for s0 in range(warmup):
+                    g.vicinity_pi_dev(batches[s0], out_pi, out_f32, out_st, hop=a.hop, mode=cmode, flags=flags)
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for s0 in range(warmup, warmup + steps):
+                    g.vicinity_pi_dev(batches[s0], out_pi, out_f32, out_st, hop=a.hop, mode=cmode, flags=flags)
+                    for k, v in stage_ms_of(g).items():
+                        stage_acc[k] = stage_acc.get(k, 0.0) + v
+                    alg_bytes += g.last_algorithmic_bytes()
+                    cn = g.last_counts()
+                    sum_n += cn["sum_n"]; sum_m += cn["sum_m"]; live += cn["live"]
+                ev1.record()
+                torch.cuda.synchronize()
+            value = B * steps / max(ev0.elapsed_time(ev1) / 1e3, 1e-9)
+            sm = g.last_small()
+            g.set_stream(None)
+            g.close()
+            # e2e: the reference-facing call, host buffers
+            gm = mirror.graph2pi.from_csr(*csr, device=local)
+            e2e_b = [batch_targets(ne, perm, 500 + s0, 0, 1, B) for s0 in range(steps + 1)]
+
+            def call(tg):
+                if a.mode == "node":
+                    return gm._graph.vicinity_pi(tg, hop=a.hop, mode=cmode, flags=flags)
+                gm.get_pimg_for_all_edges(tg, cores=16, hop=a.hop, norm=True, extended_flag=bool(a.extended), resolution=5, descriptor="sum")
+                return gm.pi_sg, gm.status, gm.cnt_compute
+            call(e2e_b[0])
+            t0 = time.perf_counter()
+            for s0 in range(steps):
+                res = call(e2e_b[1 + s0])
+            e2e = B * steps / (time.perf_counter() - t0)
+            # oracle spot check on the last e2e batch
+            og = orc.OracleGraph(*csr)
+            oflags, omode = path_flags(a, orc)
+            tg = e2e_b[steps][:spot]
+            ref = og.run_batch(tg, hop=a.hop, mode=omode, flags=oflags, nthreads=orc.max_threads())
+            pi_s, st_s = np.asarray(res[0])[:spot], np.asarray(res[1])[:spot]
+            den = np.where(ref["pi"] != 0, np.abs(ref["pi"]), 1.0)
+            err = float(np.max(np.abs(pi_s - ref["pi"]) / den)) if len(tg) else 0.0
+            ok = bool(np.array_equal(st_s, ref["status"]) and err < 1e-5)
+            gm._graph.close()
+            cpu = cpu_baseline(csr, ne, perm, a, cpu_seconds)
+            stages = {k: v for k, v in stage_acc.items() if k != "total" and not k.startswith("small_")}
+            dom = max(stages, key=stages.get) if stages else "n/a"
+            sab = stage_alg_bytes(float(sum_n), float(sum_m), alg_bytes, r2, float(live))
+            dom_ms = stages.get(dom, 0.0)
+            achieved = (sab.get(dom, alg_bytes) / 1e9) / max(dom_ms / 1e3, 1e-12)
+            out[key] = {"config": what, "targets_per_step": B, "steps": steps, "value": value, "e2e": e2e, "unit": UNIT,
+                        "cpu_port": {"value": cpu["value"], "cores": cpu["cores"], "sample": cpu["sample"]},
+                        "value_over_port": value / max(cpu["value"], 1e-9), "e2e_over_port": e2e / max(cpu["value"], 1e-9),
+                        "dominant_kernel": dom, "dominant_kernel_ms_per_step": dom_ms / steps,
+                        "roofline_frac": achieved / peak, "achieved_gbs": achieved,
+                        "stage_ms_per_step": {k: round(v / steps, 4) for k, v in stage_acc.items() if v > 0},
+                        "kernel_S_rows_last_step": {"class_a": sm["rows_a"], "class_b": sm["rows_b"], "class_c": sm["rows_c"], "staged": sm["rows_staged"]},
+                        "oracle_spot_check": {"targets": int(len(tg)), "status_equal_and_img_rel_err_lt_1e-5": ok, "max_rel_err": err}}
+        except Exception as ex:  # a secondary line never fails the headline
+            out[key] = {"config": what, "error": repr(ex)[:300]}
+    return out
 
 
 def run_cuda(args):
@@ -355,8 +474,7 @@ def run_cuda(args):
     t_wall0 = time.perf_counter()
     for s in range(args.warmup, args.warmup + args.steps):
         run(batches[s])
-        ms, _ = g.last_stage_ms()
-        for k, v in ms.items():
+        for k, v in stage_ms_of(g).items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
         alg_bytes += g.last_algorithmic_bytes()
         cnts = g.last_counts()
@@ -367,6 +485,7 @@ def run_cuda(args):
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     launches = api.launch_count() - launches0
+    ks_last = g.last_small()
     # device time of the K steps (CUDA events on the launching stream), max over ranks
     dev_ms = float(ev0.elapsed_time(ev1))
     elapsed = max(dev_ms / 1e3, 1e-9)
@@ -395,7 +514,7 @@ def run_cuda(args):
         t0 = time.perf_counter()
         for s in range(args.steps):
             e2e_call(e2e_batches[1 + s])
-            for k, v in gm._graph.last_stage_ms()[0].items():
+            for k, v in stage_ms_of(gm._graph).items():
                 e2e_stage[k] = e2e_stage.get(k, 0.0) + v
         te_local = time.perf_counter() - t0
         h2d, d2h = int(B * 8), int(B * (r2 * 8 + 1))
@@ -425,7 +544,7 @@ def run_cuda(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         # dominant kernel = the stage with the largest share of device time
-        stages = {k: v for k, v in stage_acc.items() if k != "total"}
+        stages = {k: v for k, v in stage_acc.items() if k != "total" and not k.startswith("small_")}
         dom = max(stages, key=stages.get) if stages else "n/a"
         dom_ms = stages.get(dom, 0.0)
         sab = stage_alg_bytes(float(sum_n), float(sum_m), alg_bytes, r2, float(live))
@@ -461,15 +580,19 @@ def run_cuda(args):
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(csr, ne, perm, args, args.cpu_seconds)
             cpu.pop("seconds", None)
+        secondary = None
+        if world == 1 and args.secondary:
+            g.close()
+            secondary = run_secondary(dev, local, peak, {(args.workload, args.mode, args.negatives): (c, labels, ne, csr, perm)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(args, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "stage_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()}},
-                "handed_back_per_step": handed_back / args.steps,
+                "handed_back_per_step": handed_back / args.steps, "kernel_S_last_step": ks_last,
                 "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "handoff": handoff}
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "handoff": handoff, "secondary": secondary}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

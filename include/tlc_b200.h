@@ -62,7 +62,7 @@ extern "C" {
 
 #define TLC_F_NO_SMALL 4096u /* never take the fused small-vicinity kernels (kernel S): every target through the staged
                                 pipeline.  Default: the batch calls (5 x 5 image, Ricci-distance filtration) first run kernel S,
-                                which finishes every vicinity of <= 256 vertices / <= 2048 edges in one launch per size class,
+                                which finishes every vicinity of <= 1024 vertices / <= 4096 edges in one launch per size class,
                                 and hand only the larger ones to the staged kernels.  Same results bit for bit */
 
 #define TLC_F_FILT_DEGREE 512u      /* PDGNN generators, filt='degree': filtration = induced degree / (max + 1e-10)
@@ -156,10 +156,10 @@ typedef struct {
 } tlc_detail;
 int tlc_vicinity_detail(tlc_graph *g, const int32_t *targets, int64_t E, const tlc_params *p, tlc_detail *out);
 
-#define TLC_ST_NOT_SMALL 255 /* tlc_small_diagrams only: the vicinity exceeds kernel S (> 256 vertices or > 2048 edges) */
+#define TLC_ST_NOT_SMALL 255 /* tlc_small_diagrams only: the vicinity exceeds kernel S (> 1024 vertices or > 4096 edges) */
 
 /* Diagrams of a batch straight from the fused small-vicinity kernels (kernel S, k0_small.cu): for every target whose
- * vicinity has <= 256 vertices and <= 2048 edges, the reference's PD_zero (+ PD_one with TLC_F_EXTENDED) in its own
+ * vicinity has <= 1024 vertices and <= 4096 edges, the reference's PD_zero (+ PD_one with TLC_F_EXTENDED) in its own
  * concatenation order (accelerated_PD.py:110, riccidist2dgm.py:323-328) -- kind, birth / death vertex (local ids),
  * birth / death value -- at poff[t] .. poff[t] + npairs[t], plus the image row, status and vicinity size.  poff[E+1]
  * are the caller's exclusive segment offsets; a segment must hold n + m + 2 pairs (tlc_vicinity_sizes).  Targets
@@ -190,6 +190,25 @@ int tlc_pimg_transform(int device, const double *dgm, int64_t K, int32_t resolut
 int tlc_pi_gather(int device, const double *dev_table, int64_t rows, int32_t r2, const int64_t *dev_index,
                   int64_t start, int64_t n, float *dev_out_f32, void *stream);
 
+/* ---- multi-GPU: the exchange of the image rows as PEER STORES (BASELINE.json north_star kernel 5) ----
+ * The target list is sharded over the ranks of one node (one process per GPU, the CSR replicated); every rank needs the
+ * whole table float32[rows][r2 + 1] afterwards (r2 image floats + the status as a float).  Instead of padding the shards
+ * and calling an all-gather, every rank owns such a table and maps the tables of its peers through CUDA IPC; after the
+ * shard's rows are computed, ONE kernel stores each row at its FINAL index into the table of every rank (remote ones over
+ * NVLink / NVSwitch) and signals an arrival counter in each table; a one-thread kernel on the same stream then waits
+ * until all ranks have arrived.  No host synchronisation, no NCCL, no un-permute pass.
+ *   tlc_table_create : allocate this rank's table (zeroed); dev_rows receives the device address of row 0, handle64 the
+ *                      64-byte CUDA IPC handle the host framework passes to the other ranks (any transport)
+ *   tlc_table_attach : the handles of ALL ranks, ordered by rank ([nranks][64]); maps the peers' tables
+ *   tlc_vicinity_pi_exchange : this rank's shard dev_targets[E][2] with the final row of each target dev_row_index[E]
+ *                      (device buffers): tlc_vicinity_pi_dev + the exchange, asynchronous on the graph's stream; every
+ *                      rank of the node must call it once per step (a rank with an empty shard passes E = 0)
+ * Work queued behind the call on the graph's stream sees the complete table.  At most 16 ranks. */
+int tlc_table_create(tlc_graph *g, int64_t rows, int32_t r2, void **dev_rows, unsigned char *handle64);
+int tlc_table_attach(tlc_graph *g, int32_t nranks, int32_t my_rank, const unsigned char *handles64);
+int tlc_vicinity_pi_exchange(tlc_graph *g, const int32_t *dev_targets, const int64_t *dev_row_index, int64_t E,
+                             const tlc_params *p, int64_t *cnt_compute);
+
 /* run this graph's kernels on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
  * graph's own non-blocking stream -- to run on the legacy default stream pass cudaStreamLegacy, (void*)0x1).
  * Lets a host framework order the work with its own (e.g. NCCL) operations: buffers handed to
@@ -215,9 +234,10 @@ int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_
 int tlc_last_counts(tlc_graph *g, int64_t *out8);
 /* targets of the last call that took the graph-row route (TLC_F_DIRECT / TLC_F_NO_DIRECT) */
 int64_t tlc_last_direct(tlc_graph *g);
-/* kernel S in the last call: out[0..1] = device ms of the class A (warp per target) / class B (CTA per target) launch
- * (TLC_STAGE_TIMING=1), out[2..3] = rows they finished, out[4] = rows handed on to the staged pipeline */
-int tlc_last_small(tlc_graph *g, double *out5);
+/* kernel S in the last call: out[0..2] = device ms of the class A (warp per target, n <= 64) / class B (128-thread CTA,
+ * n <= 256) / class C (256-thread CTA, n <= 1024) launch (TLC_STAGE_TIMING=1), out[3..5] = rows they finished,
+ * out[6] = rows handed on to the staged pipeline */
+int tlc_last_small(tlc_graph *g, double *out7);
 
 #ifdef __cplusplus
 }

@@ -179,3 +179,89 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def spec_validity(d, B=32):
+    """speculative batches of B positive edges against the frozen tree; an edge is VALID when no vertex of its frozen cycle had
+    its parent pointer rewritten by an earlier edge of the batch (conservative check), else it is recomputed in order."""
+    n, m = d["n"], d["m"]
+    elo, ehi = d["elo"], d["ehi"]
+    arank = np.empty(m, np.int64)
+    arank[d["ord_asc"]] = np.arange(m)
+    neg, pos = d["neg"], d["pos"]
+    par = np.full(n, -1)
+    pr = np.full(n, -1)
+    root = elo[neg[0]]
+    par[root] = root
+    nb = [[] for _ in range(n)]
+    for e in neg:
+        nb[elo[e]].append((ehi[e], e))
+        nb[ehi[e]].append((elo[e], e))
+    q = [root]
+    for x in q:
+        for y, e in nb[x]:
+            if par[y] < 0:
+                par[y] = x
+                pr[y] = arank[e]
+                q.append(y)
+
+    def walk(p0, p1):
+        s0 = []
+        x = p0
+        seen = {}
+        while True:
+            seen[x] = len(s0)
+            s0.append(x)
+            if par[x] == x:
+                break
+            x = par[x]
+        y = p1
+        s1 = []
+        while y not in seen:
+            s1.append(y)
+            y = par[y]
+        return s0[:seen[y]], s1, y, len(s0)
+
+    npos = len(pos)
+    valid = true_ok = 0
+    cyc = []
+    root_len = []
+    for k0 in range(0, npos, B):
+        hi = min(npos, k0 + B)
+        frozen = []
+        for j in range(k0, hi):
+            pe = pos[j]
+            a0, a1, lca, L0 = walk(elo[pe], ehi[pe])
+            frozen.append((set(a0) | set(a1) | {lca}, set(pr[x] for x in a0) | set(pr[x] for x in a1)))
+            root_len.append(L0)
+        touched = set()
+        removed = set()
+        for j in range(k0, hi):
+            vs, rk = frozen[j - k0]
+            if not (vs & touched):
+                valid += 1
+            if not (rk & removed):
+                true_ok += 1
+            pe = pos[j]
+            p0, p1 = elo[pe], ehi[pe]
+            a0, a1, lca, L0 = walk(p0, p1)
+            cyc.append(len(a0) + len(a1))
+            best, bc, in0 = -1, -1, 0
+            for x in a0:
+                if pr[x] > best:
+                    best, bc, in0 = pr[x], x, 1
+            for x in a1:
+                if pr[x] > best:
+                    best, bc, in0 = pr[x], x, 0
+            removed.add(best)
+            node, nodec, rc = (p0, p1, arank[pe]) if in0 else (p1, p0, arank[pe])
+            while True:
+                tp, tr = par[node], pr[node]
+                par[node] = nodec
+                pr[node] = rc
+                touched.add(node)
+                if node == bc:
+                    break
+                nodec, rc, node = node, tr, tp
+    return dict(npos=npos, valid_frac=valid / max(npos, 1), true_ok_frac=true_ok / max(npos, 1), cyc_mean=float(np.mean(cyc)) if cyc else 0,
+                cyc_p95=float(np.percentile(cyc, 95)) if cyc else 0, cyc_max=max(cyc) if cyc else 0, root_path_mean=float(np.mean(root_len)) if root_len else 0)

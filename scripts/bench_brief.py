@@ -3,5 +3,5 @@
 import json, sys
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 st = d["roofline"]["stage_ms_per_step"]
-print("%s value %.0f e2e %.0f | %s" % (sys.argv[1] if len(sys.argv) > 1 else "", d["value"], d["e2e"]["value"],
+print("%s value %.0f e2e %.0f | %s | %s" % (sys.argv[1] if len(sys.argv) > 1 else "", d["value"], d["e2e"]["value"], {k: v for k, v in d.get("kernel_S_last_step", {}).items() if k.startswith("rows")},
                                         " ".join("%s %.2f" % (k, v) for k, v in st.items() if v > 0.05)))

@@ -6,7 +6,7 @@ tag=$1; shift
 mkdir -p gpurun_out
 run() {  # name, bench args...
   local name=$1; shift
-  timeout 240 python bench.py --steps 10 --warmup 3 "$@" > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err < /dev/null
+  timeout 240 python bench.py --steps 10 --warmup 3 --secondary 0 "$@" > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err < /dev/null
   python scripts/bench_brief.py "$name" < gpurun_out/${tag}_${name}.json 2>/dev/null || { echo "$name FAILED"; tail -3 gpurun_out/${tag}_${name}.err; }
 }
 for cfg in "$@"; do

@@ -19,6 +19,8 @@
 // after the largest, for the staged pipeline).  Results are bit-identical to the staged kernels: same canonical order,
 // same IEEE operation order (tests/test_gpu_small.py compares pairs and images with the oracle).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "tlc_common.cuh"
@@ -111,6 +113,12 @@ struct Team {
   }
 };
 
+#ifdef SMALL_PROFILE
+#define SPROF(slot) do { if (tid == 0 && a.prof) { const long long now_ = clock64(); atomicAdd(&a.prof[a.cls * 16 + (slot)], (unsigned long long)(now_ - tprof)); tprof = now_; } } while (0)
+#else
+#define SPROF(slot) do { } while (0)
+#endif
+
 struct SmallArgs {
   GraphView g;
   Params p;
@@ -135,7 +143,8 @@ struct SmallArgs {
   int want_desc;            // run the descending sweep although no loops are wanted (diagram output)
   SmallStats* stats;        // device accumulators (handled rows, sum n, sum m, algorithmic bytes) or nullptr
   const unsigned long long* ball_acc;  // [N][2] per ball: expanded degree sum, rowptr pairs read (byte accounting)
-  int cls;                  // 0: class A, 1: class B
+  int cls;                  // 0: class A, 1: class B, 2: class C
+  unsigned long long* prof; // -DSMALL_PROFILE builds: clock64 ticks per class and stage [3][16]
 };
 
 template <int NC, int AC>
@@ -153,7 +162,8 @@ struct SmallMem {
   static constexpr size_t o_ast = o_vert + (size_t)NC * 4;           // i32[NC + 1]  adjacency row starts
   static constexpr size_t o_gra = o_ast + (size_t)(NC + 1) * 4;      // i32[NC]      graph row starts      | later tpe (parent entry)
   static constexpr size_t o_gpre = o_gra + (size_t)NC * 4;           // i32[NC + 1]  prefix of graph degrees
-  static constexpr size_t o_ark = o_gpre + (size_t)(NC + 1) * 4;     // u16[MC]      rank of every edge in the ascending sweep
+  static constexpr size_t o_pm = o_gpre + (size_t)(NC + 1) * 4;      // i32[NC]      loops: (largest rank below the vertex on its climb) << 10 | child end
+  static constexpr size_t o_ark = o_pm + (size_t)NC * 4;             // u16[MC]      rank of every edge in the ascending sweep
   static constexpr size_t o_neg = o_ark + (size_t)MC * 2;            // u16[NC]      Neg edges in sweep order
   static constexpr size_t o_tpr = o_neg + (size_t)NC * 2;            // u16[NC]      loops: rank of the parent edge
   static constexpr size_t o_stp = o_tpr + (size_t)NC * 2;            // u16[NC]      loops: visit stamp
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
   using LID = typename M::LID;
   constexpr int MC = M::MC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int32_t xchg_all[48];
+  __shared__ __align__(16) int32_t xchg_all[48];
   constexpr int TEAMS = NT == 32 ? 4 : 1;  // teams per CTA
   const int team_in_cta = NT == 32 ? (threadIdx.x >> 5) : 0;
   Team<NT> tm{NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x, xchg_all};
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
   int32_t* gra = reinterpret_cast<int32_t*>(base + M::o_gra);
   int32_t* tpe = gra;  // (graph row starts are dead once the adjacency exists)
   int32_t* gpre = reinterpret_cast<int32_t*>(base + M::o_gpre);
+  int32_t* pmx = reinterpret_cast<int32_t*>(base + M::o_pm);
   uint16_t* ark = reinterpret_cast<uint16_t*>(base + M::o_ark);
   uint16_t* negl = reinterpret_cast<uint16_t*>(base + M::o_neg);
   uint16_t* tpr = reinterpret_cast<uint16_t*>(base + M::o_tpr);
@@ -275,6 +286,9 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
     double* out = a.out_pi + row * 25;
     float* out32 = a.out_pi32 ? a.out_pi32 + row * 25 : nullptr;
     uint8_t status = TLC_ST_OK;
+#ifdef SMALL_PROFILE
+    long long tprof = clock64();
+#endif
     int n = 0, m = 0, np = 0;
     int gpre_total = 0;  // sum of the members' graph degrees (D_S)
     const int64_t dpo = a.poff ? a.poff[row] : 0;
@@ -310,6 +324,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)row;
       continue;
     }
+    SPROF(0);
     int lu = -1, lv = -1;
     if (status == TLC_ST_OK) {
       tm.sync();
@@ -326,7 +341,17 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       }
       if (tid == 0) { gpre[0] = 0; ast[0] = 0; }
       tm.sync();
-      if (tid == 0) { int run = 0; for (int i = 1; i <= n; i++) { run += gpre[i]; gpre[i] = run; } }  // (n <= NC: a short serial scan)
+      {  // inclusive scan of the degrees in gpre[1..n]
+        int run = 0;
+        for (int b0 = 1; b0 <= n; b0 += NT) {
+          const int i = b0 + tid;
+          const int vdeg = i <= n ? gpre[i] : 0;
+          int tot;
+          const int ex = tm.exscan(vdeg, tot);
+          if (i <= n) gpre[i] = run + ex + vdeg;
+          run += tot;
+        }
+      }
       tm.sync();
       const int D = gpre[n];
       gpre_total = D;
@@ -364,7 +389,17 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       }
       m = ecur;
       tm.sync();
-      if (tid == 0) { int run = 0; for (int i = 1; i <= n; i++) { run += ast[i]; ast[i] = run; } }
+      {  // inclusive scan of the kept entries per row in ast[1..n]
+        int run = 0;
+        for (int b0 = 1; b0 <= n; b0 += NT) {
+          const int i = b0 + tid;
+          const int vdeg = i <= n ? ast[i] : 0;
+          int tot;
+          const int ex = tm.exscan(vdeg, tot);
+          if (i <= n) ast[i] = run + ex + vdeg;
+          run += tot;
+        }
+      }
       // local roots
       {
         int lo = 0, hi = n;
@@ -380,6 +415,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       tm.sync();
       if ((node_mode || forced) && m == 0) status = TLC_ST_EMPTY;  // `return None, None`  data_utils_NC.py:103-104, data_utils_LP.py:117-118
     }
+    SPROF(1);
     const bool live0 = status == TLC_ST_OK;  // the staged pipeline's "live" targets: a valid, non-empty vicinity (byte accounting)
     const int A2 = status == TLC_ST_OK ? ast[n] : 0;  // directed entries = 2m
     const bool roots_in = lu >= 0 && lv >= 0;
@@ -479,6 +515,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       tm.sync();
     }
 
+    SPROF(2);
     int npb = 0;  // pairs waiting in the buffer
     if (tid < 25) img[tid] = 0.0;
     tm.sync();
@@ -488,8 +525,15 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       // min_value / max_value: first vertex (ascending id) attaining them   :35-38
       int minv = 0, maxv = 0;
       {
-        double fmn = fv[0], fmx = fv[0];
-        for (int x = 1; x < n; x++) { const double f = fv[x]; if (f < fmn) { fmn = f; minv = x; } if (f > fmx) { fmx = f; maxv = x; } }
+        double lmx = -1e300, lmn = -1e300;  // (min through max of the negated values)
+        for (int x = tid; x < n; x += NT) { const double f = fv[x]; lmx = fmax(lmx, f); lmn = fmax(lmn, -f); }
+        const double fmx = tm.maxd(lmx), fmn = -tm.maxd(lmn);
+        if (tid == 0) { ast[0] = 0x7fffffff; gpre[0] = 0x7fffffff; }  // (both arrays are dead by now)
+        tm.sync();
+        for (int x = tid; x < n; x += NT) { const double f = fv[x]; if (f == fmn) atomicMin(&ast[0], x); if (f == fmx) atomicMin(&gpre[0], x); }
+        tm.sync();
+        minv = ast[0]; maxv = gpre[0];
+        tm.sync();
       }
       int P2 = 32;
       while (P2 < m) P2 <<= 1;
@@ -523,6 +567,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
             tm.sync();
           }
         }
+        SPROF(3 + 2 * sweep);
         if (sweep == 0 && do_desc && ext) { for (int k = tid; k < m; k += NT) ark[sidx[k]] = (uint16_t)k; }
         for (int x = tid; x < n; x += NT) par[x] = (LID)x;
         tm.sync();
@@ -596,6 +641,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
           np = xchg_all[40]; npb = xchg_all[41]; merges = xchg_all[42]; nneg = xchg_all[43]; npos = xchg_all[44];
           __syncthreads();
         }
+        SPROF(4 + 2 * sweep);
         if (sweep == 0) merges_asc = merges;
         // essential pair of the sweep   :110
         if (tid == 0) {
@@ -633,6 +679,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
             tm.sync();
             if (!tm.any(ch)) break;
           }
+          SPROF(7);
           // sequential sweep over the positive edges (sidx[0..npos) in sweep order) on the team's first lane; whenever the
           // pair buffer fills, the lane stops, the whole team rasterises the buffer, and the sweep resumes
           int k = 0, st_i = status;
@@ -642,13 +689,34 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
                 const int pe = sidx[k];
                 const int p0 = elo[pe], p1 = ehi[pe];
                 int rc = ark[pe];
-                // path_0: p0 -> root, stamped   :131-144
-                for (int x = p0;;) { stp[x] = (uint16_t)k; const int px = (int)tpa[x]; if (px == x) break; x = px; }
-                int lca = p1;  // :145-151
-                while (stp[lca] != (uint16_t)k) lca = (int)tpa[lca];
-                int best = -1, bc = -1, in0 = 0;
-                for (int x = p0; x != lca; x = (int)tpa[x]) { const int rk = tpr[x]; if (rk > best) { best = rk; bc = x; in0 = 1; } }
-                for (int x = p1; x != lca; x = (int)tpa[x]) { const int rk = tpr[x]; if (rk > best) { best = rk; bc = x; in0 = 0; } }
+                // Loop = path_0 (p0 -> root) xor path_1 (p1 -> root) = (p0 -> lca) + (p1 -> lca)   :131-151.  The two climbs
+                // alternate, each stamping its own mark, until one steps on the other's mark: ~2 x the cycle length
+                // instead of the whole root path (the Neg trees of sparse vicinities are deep)
+                const uint16_t mk0 = (uint16_t)(2 * k), mk1 = (uint16_t)(2 * k + 1);
+                // every stamped vertex also keeps the largest parent-edge rank met below it on its side's climb (packed with
+                // that edge's child end), so the cycle's maximum is known the moment the climbs meet -- no second walk
+                int best0 = -1, best1 = -1;
+                {
+                  int x0 = p0, x1 = p1;
+                  stp[x0] = mk0; pmx[x0] = -1;
+                  stp[x1] = mk1; pmx[x1] = -1;  // (p0 != p1)
+                  for (;;) {
+                    const int q0 = (int)tpa[x0];
+                    if (q0 != x0) {
+                      best0 = max(best0, ((int)tpr[x0] << 10) | x0);
+                      if (stp[q0] == mk1) { best1 = pmx[q0]; break; }
+                      stp[q0] = mk0; pmx[q0] = best0; x0 = q0;
+                    }
+                    const int q1 = (int)tpa[x1];
+                    if (q1 != x1) {
+                      best1 = max(best1, ((int)tpr[x1] << 10) | x1);
+                      if (stp[q1] == mk0) { best0 = pmx[q1]; break; }
+                      stp[q1] = mk1; pmx[q1] = best1; x1 = q1;
+                    }
+                  }
+                }
+                const int in0 = best0 > best1 ? 1 : 0;       // (ranks are distinct)
+                const int bc = (in0 ? best0 : best1) & 1023;  // child end of the cycle's largest edge
                 const int by = (int)tpa[bc];  // large_edge = (bc, by)   :155-159
                 const int la = min(bc, by), lb = max(bc, by);
                 const int lvv = fv[la] >= fv[lb] ? la : lb;   // large_value = max(old[large_edge])
@@ -677,6 +745,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       }
     }
     tm.sync();
+    SPROF(8);
 
     // ---------------- 7. image + outputs ----------------
     // (status, np, npb are uniform over the team here: every single-lane section ends with a broadcast)
@@ -688,6 +757,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       out[tid] = val;
       if (out32) out32[tid] = (float)val;
     }
+    SPROF(9);
     if (tid == 0) {
       if (a.out_status) a.out_status[row] = status;
       if (a.out_n) a.out_n[row] = n;
@@ -724,14 +794,28 @@ static void launch_class(const SmallArgs& a, int grid, cudaStream_t st) {
 
 }  // namespace
 
-// class A: a warp per target (n <= 64, <= 256 induced edges); class B: a 128-thread CTA per target (n <= 256, <= 2048 edges).
-// counters[0] / counters[1]: rows deferred from A to B (list_b) / from B to the staged pipeline (list_c); zeroed here.
+// class A: a warp per target (n <= 64, <= 256 induced edges); class B: a 128-thread CTA per target (n <= 256, <= 2048 edges);
+// class C: a 256-thread CTA per target (n <= 1024, <= 4096 edges).
+// counters[0] / [1] / [2]: rows deferred from A to B (list_b) / from B to C (list_c) / from C to the staged pipeline (list_b
+// again: class B has consumed it by then); zeroed here.
 void launch_small(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
                   double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int* counters,
                   int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count, cudaStream_t st,
-                  cudaEvent_t ev_mid) {
+                  cudaEvent_t ev_mid, cudaEvent_t ev_mid2) {
   SmallArgs a{};
   a.stats = stats; a.ball_acc = vs.ball_acc;
+#ifdef SMALL_PROFILE
+  static unsigned long long* d_prof = nullptr;
+  if (!d_prof) { cudaMalloc((void**)&d_prof, 48 * 8); cudaMemset(d_prof, 0, 48 * 8); }
+  a.prof = d_prof;
+  if (getenv("SMALL_PROFILE_DUMP")) {
+    unsigned long long h[48];
+    cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost);
+    static const char* nm[10] = {"vicinity", "adjacency", "filtration", "sort_asc", "sweep_asc", "sort_desc", "sweep_desc", "tree_root", "loops", "image"};
+    for (int c = 0; c < 3; c++) { fprintf(stderr, "[small profile] class %c:", 'A' + c); for (int i = 0; i < 10; i++) fprintf(stderr, " %s %.1fM", nm[i], h[c * 16 + i] / 1e6); fprintf(stderr, "\n"); }
+    cudaMemset(d_prof, 0, 48 * 8);
+  }
+#endif
   a.g = g; a.p = p; a.targets = targets; a.E = E;
   a.ball_cache = vs.ball_cache; a.W = (g.N + 31) / 32;
   a.out_pi = out_pi; a.out_pi32 = out_pi32; a.out_status = out_status;
@@ -740,7 +824,7 @@ void launch_small(const GraphView& g, const Params& p, const int32_t* targets, i
     a.poff = diag->poff; a.dnp = diag->np; a.dkind = diag->kind; a.dbv = diag->bv; a.ddv = diag->dv;
     a.dbirth = diag->birth; a.ddeath = diag->death; a.want_desc = 1;
   }
-  cudaMemsetAsync(counters, 0, 2 * sizeof(int), st);
+  cudaMemsetAsync(counters, 0, 3 * sizeof(int), st);
   if (stats) cudaMemsetAsync(stats, 0, sizeof(SmallStats), st);
   // class A over every target
   a.list = nullptr; a.list_count = nullptr; a.defer_list = list_b; a.defer_count = counters;
@@ -756,6 +840,14 @@ void launch_small(const GraphView& g, const Params& p, const int32_t* targets, i
   {
     const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count * 3);
     launch_class<128, 256, 4096>(a, std::max(grid, 1), st);
+  }
+  if (ev_mid2) cudaEventRecord(ev_mid2, st);
+  // class C over the rows class B deferred; what it cannot take either goes back into list_b for the staged pipeline
+  a.cls = 2;
+  a.list = list_c; a.list_count = counters + 1; a.defer_list = list_b; a.defer_count = counters + 2;
+  {
+    const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count);
+    launch_class<256, 1024, 8192>(a, std::max(grid, 1), st);
   }
 }
 

@@ -41,6 +41,20 @@ __device__ __forceinline__ bool set_bit(uint32_t* bm, int32_t y) {  // returns t
   return (atomicOr(&bm[y >> 5], bit) & bit) == 0;
 }
 
+// a warp walks the CSR row [a, b) of col[]: the 16-byte aligned body with coalesced 128-bit loads (four neighbour ids per
+// lane and load, LDG.E.128), the unaligned head and the tail with 32-bit loads.  f(y) is called once per entry.
+template <typename F>
+__device__ __forceinline__ void warp_row_v4(const int32_t* __restrict__ col, int32_t a, int32_t b, int lane, F f) {
+  const int32_t a4 = min(b, (a + 3) & ~3);           // first 4-aligned index (cudaMalloc'ed col[] is 256-byte aligned)
+  const int32_t b4 = a4 + ((b - a4) & ~3);           // end of the whole int4 groups
+  if (a + lane < a4) f(col[a + lane]);               // head: < 4 entries
+  for (int32_t e = a4 + 4 * lane; e < b4; e += 128) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(col + e));
+    f(v.x); f(v.y); f(v.z); f(v.w);
+  }
+  if (b4 + lane < b) f(col[b4 + lane]);              // tail: < 4 entries
+}
+
 // closed ball of radius hop around root into bm (bm zeroed by the caller).
 // nodes_u = [root] + [x for _, x in nx.bfs_edges(G, root, depth_limit=hop)]   riccidist2dgm.py:311-312
 __device__ void ball(const GraphView& g, int32_t root, int hop, uint32_t* bm, int32_t* q0, int32_t* q1,
@@ -51,8 +65,9 @@ __device__ void ball(const GraphView& g, int32_t root, int hop, uint32_t* bm, in
   if (hop <= 0) return;
   const int32_t r0 = g.rowptr[root], r1 = g.rowptr[root + 1];
   if (tid == 0) { sh.dacc += (unsigned long long)(r1 - r0); sh.xacc += 1; }
-  // depth 1: the CSR row of the root, 128-bit loads where the row is aligned
-  for (int32_t e = r0 + tid; e < r1; e += nt) set_bit(bm, g.col[e]);
+  // depth 1: the CSR row of the root, every warp a 128-entry slice of it (128-bit loads)
+  for (int32_t s0 = r0 + wid * 128; s0 < r1; s0 += nw * 128)
+    warp_row_v4(g.col, s0, min(s0 + 128, r1), lane, [&](int32_t y) { set_bit(bm, y); });
   __syncthreads();
   if (hop == 1) return;
   // depth 2: one warp per depth-1 vertex, lanes stride its row (coalesced)
@@ -63,10 +78,7 @@ __device__ void ball(const GraphView& g, int32_t root, int hop, uint32_t* bm, in
     const int32_t x = g.col[i];
     const int32_t a = g.rowptr[x], b = g.rowptr[x + 1];
     if (lane == 0) { atomicAdd(&sh.dacc, (unsigned long long)(b - a)); atomicAdd(&sh.xacc, 1ull); }
-    for (int32_t e = a + lane; e < b; e += 32) {
-      const int32_t y = g.col[e];
-      if (set_bit(bm, y) && push) q0[atomicAdd(&sh.qcnt[0], 1)] = y;
-    }
+    warp_row_v4(g.col, a, b, lane, [&](int32_t y) { if (set_bit(bm, y) && push) q0[atomicAdd(&sh.qcnt[0], 1)] = y; });
   }
   __syncthreads();
   // depth >= 3: explicit frontier queues (HBM slabs); newly set bits form the next frontier
@@ -83,10 +95,7 @@ __device__ void ball(const GraphView& g, int32_t root, int hop, uint32_t* bm, in
       const int32_t x = cur[i];
       const int32_t a = g.rowptr[x], b = g.rowptr[x + 1];
       if (lane == 0) { atomicAdd(&sh.dacc, (unsigned long long)(b - a)); atomicAdd(&sh.xacc, 1ull); }
-      for (int32_t e = a + lane; e < b; e += 32) {
-        const int32_t y = g.col[e];
-        if (set_bit(bm, y) && push2) nxt[atomicAdd(&sh.qcnt[ci ^ 1], 1)] = y;
-      }
+      warp_row_v4(g.col, a, b, lane, [&](int32_t y) { if (set_bit(bm, y) && push2) nxt[atomicAdd(&sh.qcnt[ci ^ 1], 1)] = y; });
     }
     __syncthreads();
     int32_t* t = cur; cur = nxt; nxt = t;

@@ -61,65 +61,38 @@ __device__ __forceinline__ double pysum_get(const PySum& p, bool plain) {
 #ifndef FILT_RU
 #define FILT_RU 4
 #endif
+// Two variants of the relaxation loop that were built and MEASURED on B200 (round 2, Computers-shaped 2-hop, 4096 targets
+// per step, kernel time of this kernel) -- both issue fewer instructions per row entry and both are
+// slower than the plain form, so they are off by default:
+//   FILT_REC   = 1: one LDG.128 of an interleaved {id, 0, kappa + 1} row record instead of LDG.32 + LDG.64 + a float64 add
+//                   (14.70 ms vs 14.59 ms: a third more bytes through the L2 for one instruction less)
+//   FILT_SPLIT = 1: decide by d[y] > d[x] whether an entry is a relaxation or a parent candidate, one float64 add per entry
+//                   instead of two (15.18 ms: the add can no longer issue before d[y] arrives -- the loop is latency-bound)
+#ifndef FILT_REC
+#define FILT_REC 0
+#endif
+#ifndef FILT_SPLIT
+#define FILT_SPLIT 0
+#endif
 constexpr int QCAP = FILT_QCAP;  // vertices settled per phase at most
-// one settled vertex of the phase: first entry of its row in the phase's concatenation (exclusive degree prefix), row
-// start in the adjacency / the graph's CSR, bit pattern of its (final) distance -- ONE 128-bit shared-memory read per row
-struct __align__(16) RowInfo {
-  int32_t pre;
-  int32_t rs;
-  unsigned long long dx;
-};
 struct FiltShared {
-  RowInfo row[QCAP + 1];
-  // the phase's settled vertices: id, smallest adjacency position of a tree-parent candidate
-  int32_t qx[QCAP], qbest[QCAP];
   double redd[32];
+  // the phase's settled vertices: id, first entry in the concatenated rows (exclusive degree prefix),
+  // row start in the adjacency, smallest adjacency position of a tree-parent candidate
+  int32_t qx[QCAP], qpre[QCAP + 1], qrs[QCAP], qbest[QCAP];
   int32_t wsum[33];
   // double-buffered by phase parity: vertices settled in the phase / smallest tentative distance for the next one
   int qn[2];
   unsigned long long nmin[2];
 };
 
-// ---- shared memory through explicit 32-bit window addresses ----
-// The hot loop indexes three runtime-placed arrays of the dynamic shared memory (distances, states, graph id -> local id).
-// Through generic pointers the compiler re-derives their window addresses at every use (64 registers per thread leave no
-// room to keep them: ~15 % of the kernel's instructions in the ncu source view); as plain 32-bit shared addresses they
-// are one register each and every access is a single LDS / STS / ATOMS.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
-  uint32_t v;
-  asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void atoms_min_u64(uint32_t a, unsigned long long v) {
-  asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
-}
-__device__ __forceinline__ void atoms_min_s32(uint32_t a, int v) { asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
 // exclusive scan of data[0..cnt) in shared memory, two barriers; returns the total.  All threads call.
-template <int STRIDE = 1>
 __device__ inline int block_scan_shfl(int32_t* data, int cnt, int32_t* wsum) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
   const int per = (cnt + nt - 1) / nt;
   const int lo = min(tid * per, cnt), hi = min(lo + per, cnt);
   int s = 0;
-  for (int i = lo; i < hi; i++) s += data[i * STRIDE];
+  for (int i = lo; i < hi; i++) s += data[i];
   int inc = s;
   for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
   if (lane == 31) wsum[wid] = inc;
@@ -133,7 +106,7 @@ __device__ inline int block_scan_shfl(int32_t* data, int cnt, int32_t* wsum) {
   }
   __syncthreads();
   int run = wsum[wid] + inc - s;
-  for (int i = lo; i < hi; i++) { const int v = data[i * STRIDE]; data[i * STRIDE] = run; run += v; }
+  for (int i = lo; i < hi; i++) { const int v = data[i]; data[i] = run; run += v; }
   return wsum[32];
 }
 
@@ -147,7 +120,7 @@ struct DirectArgs {
 
 template <bool DIRECT, bool SMEM>
 __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c, int t0, int cap, int bpv, DirectArgs da) {
-  extern __shared__ __align__(16) unsigned long long dyn64[];
+  extern __shared__ unsigned long long dyn64[];
   __shared__ FiltShared sh;
   const int t = t0 + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
@@ -177,7 +150,7 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
       bm[W + w] = __popc(x);
     }
     __syncthreads();
-    n = block_scan_shfl<1>(reinterpret_cast<int32_t*>(bm + W), W, sh.wsum);
+    n = block_scan_shfl(reinterpret_cast<int32_t*>(bm + W), W, sh.wsum);
     __syncthreads();
     uint32_t* gb = c.dbm + (size_t)t * 2 * W;  // kernels 2v / 3v map graph ids through it
     for (int w = tid; w < 2 * W; w += nt) gb[w] = bm[w];
@@ -225,7 +198,9 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
   // rows: induced adjacency segment of the target, or (graph-row route) the graph's CSR itself
   const uint32_t* __restrict__ anb = DIRECT ? reinterpret_cast<const uint32_t*>(da.g.col) : c.anb + ao;
   const double* __restrict__ aw = DIRECT ? da.g.kappa : c.aw + ao;
+#if FILT_REC
   const uint4* __restrict__ grec = da.g.rec;  // graph-row route: interleaved {id, 0, kappa + 1} row records
+#endif
   double* d1 = c.d1 + vo;
   double* d2 = c.d2 + vo;
   double* fval = c.fval + vo;
@@ -268,9 +243,6 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
     double* tpw = reinterpret_cast<double*>(c.v64b + vo);
     const float* __restrict__ aminw = c.aminw + vo;
     constexpr uint8_t FAR = 0, TENT = 1, DONE = 2;
-    const uint32_t a_row = smem_addr(&sh.row[0]), a_qbest = smem_addr(&sh.qbest[0]);
-    const uint32_t a_dist = SMEM ? smem_addr(dist) : 0u, a_state = SMEM ? smem_addr(state) : 0u;
-    const uint32_t a_lid = use_lid ? smem_addr(slid) : 0u;
     for (int r = 0; r < (two ? 2 : 1); r++) {
       const int root = r == 0 ? lu : lv;
       const int cnt_this_root = (count_m && r == 0) ? 1 : 0;
@@ -311,9 +283,8 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
             if (take && pos < QCAP) {
               state[x] = DONE;
               sh.qx[pos] = x;
-              sh.row[pos].pre = adeg[x];
-              sh.row[pos].rs = astart[x];
-              sh.row[pos].dx = d;  // final from here on
+              sh.qpre[pos] = adeg[x];
+              sh.qrs[pos] = astart[x];
               sh.qbest[pos] = 0x7fffffff;
               d = INF_BITS;
             }
@@ -325,8 +296,8 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
         __syncthreads();
         const int qn = min(sh.qn[cur], QCAP);
         if (tid == 0) { sh.nmin[cur] = INF_BITS; sh.qn[cur ^ 1] = 0; }  // (read by everyone before the barrier above)
-        const int total = block_scan_shfl<4>(&sh.row[0].pre, qn, sh.wsum);  // row[i].pre = first entry of row i in the phase's concatenation
-        if (tid == 0) sh.row[qn].pre = total;
+        const int total = block_scan_shfl(sh.qpre, qn, sh.wsum);  // qpre[i] = first entry of row i in the phase's concatenation
+        if (tid == 0) sh.qpre[qn] = total;
         __syncthreads();
         unsigned long long umin = INF_BITS;  // smallest distance this thread writes
         // ---- relax the settled rows, every warp an equal share of the concatenated entries (coalesced);
@@ -336,13 +307,12 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
           const int e1 = min((wid + 1) * span, total);
           int e = wid * span + lane;
           if (e < e1) {
-            int lo = 0, hi = qn;  // row i: largest i with row[i].pre <= e
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)lds_u32(a_row + 16u * mid) <= e) lo = mid; else hi = mid; }
-            int i = lo, nxt = (int)lds_u32(a_row + 16u * (i + 1));
-            while (e >= nxt) { i++; nxt = (int)lds_u32(a_row + 16u * (i + 1)); }  // (rows of degree 0)
-            uint4 ri4 = lds_v4(a_row + 16u * i);
-            int off = (int)ri4.y - (int)ri4.x;
-            unsigned long long dxb = ((unsigned long long)ri4.w << 32) | ri4.z;
+            int lo = 0, hi = qn;  // row i: largest i with qpre[i] <= e
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.qpre[mid] <= e) lo = mid; else hi = mid; }
+            int i = lo, nxt = sh.qpre[i + 1];
+            while (e >= nxt) { i++; nxt = sh.qpre[i + 1]; }  // (rows of degree 0)
+            int off = sh.qrs[i] - sh.qpre[i];
+            unsigned long long dxb = dist[sh.qx[i]];
             // RU entries per lane and step: the row bookkeeping runs ahead in shared memory, then all loads of
             // the step are issued before the first use
             constexpr int RU = FILT_RU;
@@ -354,50 +324,67 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
                 const int ek = e + 32 * k;
                 if (ek < e1) {
                   if (ek >= nxt) {
-                    do { i++; nxt = (int)lds_u32(a_row + 16u * (i + 1)); } while (ek >= nxt);
-                    ri4 = lds_v4(a_row + 16u * i);
-                    off = (int)ri4.y - (int)ri4.x;
-                    dxb = ((unsigned long long)ri4.w << 32) | ri4.z;
+                    do { i++; nxt = sh.qpre[i + 1]; } while (ek >= nxt);
+                    off = sh.qrs[i] - sh.qpre[i];
+                    dxb = dist[sh.qx[i]];
                   }
                   ai[k] = off + ek; ri[k] = i; dx[k] = dxb;
                 } else ai[k] = -1;
               }
-              uint32_t yy[RU];
+              int yy[RU];
               double ww[RU];
 #pragma unroll
               for (int k = 0; k < RU; k++) if (ai[k] >= 0) {
-                if (DIRECT) {  // {id, 0, kappa + 1}: one 128-bit load per row entry   riccidist2dgm.py:225
+#if FILT_REC
+                if (DIRECT) {  // {id, 0, kappa + 1}: ONE 128-bit load per row entry, the weight ready-made   riccidist2dgm.py:225
                   const uint4 r = __ldg(grec + ai[k]);
-                  yy[k] = r.x; ww[k] = __hiloint2double((int)r.w, (int)r.z);
-                } else { yy[k] = anb[ai[k]]; ww[k] = aw[ai[k]]; }
+                  yy[k] = (int)r.x; ww[k] = __hiloint2double((int)r.w, (int)r.z);
+                } else
+#endif
+                { yy[k] = (int)anb[ai[k]]; ww[k] = aw[ai[k]]; }
               }
 #pragma unroll
               for (int k = 0; k < RU; k++) {
                 if (ai[k] < 0) continue;
-                int y = (int)yy[k];
+                int y = yy[k];
                 if (DIRECT) {
-                  if (use_lid) { const int l = (int)lds_u16(a_lid + 2u * (uint32_t)y); y = l == 0xffff ? -1 : l; }
+                  if (use_lid) { const int l = (int)slid[y]; y = l == 0xffff ? -1 : l; }
                   else y = bitmap_rank(bm, W, y);
                   if (y < 0) continue;  // the neighbour is outside the vicinity
                   mcnt += cnt_this_root;
                 }
+#if FILT_REC
                 const double w = ww[k];
-                unsigned long long dyb;
-                if (SMEM) dyb = lds_u64(a_dist + 8u * (uint32_t)y); else dyb = dist[y];
+#else
+                const double w = DIRECT ? __dadd_rn(ww[k], 1.0) : ww[k];  // weight = kappa + 1   riccidist2dgm.py:225
+#endif
+                const unsigned long long dyb = dist[y];
+#if FILT_SPLIT
                 if (dyb > dx[k]) {
-                  // y is not final yet (farther than x): relax.  (fl(d[y] + w) == d[x] is impossible here, w > 0)
+                  // y lies farther than x: relax.  (fl(d[y] + w) == d[x] is impossible here, w > 0)
                   const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dx[k]), w));
                   if (tb < dyb) {
-                    if (SMEM) { atoms_min_u64(a_dist + 8u * (uint32_t)y, tb); sts_u8(a_state + (uint32_t)y, TENT); }
-                    else { atomicMin(&dist[y], tb); state[y] = TENT; }
-                    // (y is FAR or TENT: a settled vertex's distance is final and cannot be improved)
+                    atomicMin(&dist[y], tb);
+                    state[y] = TENT;  // (y is FAR or TENT: a settled vertex's distance is final and cannot be improved)
                     umin = tb < umin ? tb : umin;
                   }
                 } else if ((unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dx[k]) {
                   // d[y] <= d[x]: fl(d[x] + w) >= d[x] >= d[y], nothing to relax; y is a parent of the row's vertex iff
                   // fl(d[y] + w) == d[x] (d[y] is final whenever this can hold)
-                  atoms_min_s32(a_qbest + 4u * (uint32_t)ri[k], ai[k]);
+                  atomicMin(&sh.qbest[ri[k]], ai[k]);
                 }
+#else
+                const unsigned long long tb = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dx[k]), w));
+                if (tb < dyb) {
+                  atomicMin(&dist[y], tb);
+                  state[y] = TENT;  // (y is FAR or TENT: a settled vertex's distance is final and cannot be improved)
+                  umin = tb < umin ? tb : umin;
+                } else if ((unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dx[k]) {
+                  // (an unreached y carries +inf: inf + w never equals the finite d[x])
+                  // y a parent of the row's vertex (d[y] is final whenever this can hold; it cannot when d[x] + w < d[y])
+                  atomicMin(&sh.qbest[ri[k]], ai[k]);
+                }
+#endif
               }
             }
           }
@@ -408,12 +395,9 @@ __global__ void __launch_bounds__(1024) filtration_kernel(Params p, ChunkView c,
         for (int i = tid; i < qn; i += nt) {
           const int x = sh.qx[i], a = sh.qbest[i];
           if (x != root && a != 0x7fffffff) {
-            if (DIRECT) {
-              const uint4 rr = __ldg(grec + a);
-              tpar[x] = bitmap_rank(bm, W, (int)rr.x);
-              tpw[x] = __hiloint2double((int)rr.w, (int)rr.z);
-            } else { tpar[x] = (int)anb[a]; tpw[x] = aw[a]; }
+            tpar[x] = DIRECT ? bitmap_rank(bm, W, (int)anb[a]) : (int)anb[a];
             (r == 0 ? hint0 : hint)[x] = tpar[x];
+            tpw[x] = DIRECT ? __dadd_rn(aw[a], 1.0) : aw[a];  // (== the record's weight: the same IEEE add, done on the host)
           }
         }
         __syncthreads();  // the next phase overwrites the queue
@@ -556,23 +540,22 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
   // dist (8) + minw (2) + state (1) bytes per vertex in shared memory when the sub-range's largest vicinity fits;
   // graph-row route: + the vicinity bitmap and its word-prefix ranks
   size_t bmb = DIRECT ? (size_t)2 * da.W * 4 : 0;
-  // 227 KB per CTA: ~25 KB of static queues (FiltShared), the rest for the per-vertex state
-  constexpr size_t BUDGET = 232448 - sizeof(FiltShared) - 512;  // dynamic shared memory next to the static queues
-  if (DIRECT && block < 128) block = 128;  // the prologue walks the bitmap a warp per word
+  constexpr size_t BUDGET = 208 * 1024;  // dynamic shared memory next to the 17 KB of static queues (227 KB per CTA)
   int cap = (int)((n_max + 7) / 8 * 8);
   int bpv = 11;
-  if ((size_t)cap * 11 + bmb > BUDGET - 18 * 1024) bpv = 9;      // very large vicinity: lean state (margins stay in the arena)
-  if ((size_t)cap * bpv + bmb > BUDGET) cap = 0;                 // larger still: per-vertex state in the arena
+  if ((size_t)cap * 11 + bmb > 190 * 1024) bpv = 9;            // very large vicinity: lean state (margins stay in the arena)
+  if ((size_t)cap * bpv + bmb > BUDGET) cap = 0;               // larger still: per-vertex state in the arena
   DirectArgs da2 = da;
   if (DIRECT) {  // the graph id -> local id table, when it fits next to the per-vertex state
     const size_t lidb = ((size_t)da.g.N + 1) / 2 * 4;
-    da2.lid_table = (n_max < 65535 && cap > 0 && (size_t)cap * bpv + bmb + lidb <= BUDGET) ? 1 : 0;
+    da2.lid_table = (n_max < 65535 && cap > 0 && (size_t)cap * bpv + bmb + lidb <= 190 * 1024) ? 1 : 0;
     if (getenv("TLC_NO_LID")) da2.lid_table = 0;  // (tuning experiments)
     if (da2.lid_table) bmb += lidb;
   }
   const size_t bytes = (size_t)cap * bpv + bmb;
+  if (DIRECT && block < 128) block = 128;  // the prologue walks the bitmap a warp per word
   // one resident CTA per SM (large vicinities): give it 32 warps, the relaxation is latency-bound
-  if (bytes + sizeof(FiltShared) > 113 * 1024 && block >= 512) block = 1024;
+  if (bytes + sizeof(FiltShared) > 110 * 1024 && block >= 512) block = 1024;
   if (const char* env = getenv("TLC_FILT_BLOCK")) block = atoi(env);  // (tuning experiments)
   auto go = [&](auto kern) {
     cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -59,7 +59,60 @@ __global__ void gather_targets_kernel(const int32_t* __restrict__ targets, const
   }
 }
 
+// ---- multi-GPU exchange without a library collective (fused variant) ----
+// Every rank owns a table [header | float32 rows[rows][r2 + 1]] in its HBM (25 image floats + the status as the last
+// float); the tables of the peers are mapped through CUDA IPC.  This kernel stores the rows a rank has just computed AT
+// THEIR FINAL INDEX into the table of EVERY rank -- peer stores over NVLink / NVSwitch for the remote ones -- so there
+// is no padding copy, no all-gather and no un-permute pass.  The last block then publishes completion: a system-scope
+// fence followed by one atomic increment of the arrival counter in every table's header.
+__global__ void __launch_bounds__(256) peer_scatter_kernel(const float* __restrict__ src_pi32, const uint8_t* __restrict__ src_st,
+                                                           const int64_t* __restrict__ row_index, int64_t k, int r2,
+                                                           PeerTables pt, unsigned int* ticket) {
+  const int w = r2 + 1;
+  const int64_t total = k * w;
+  for (int t = 0; t < pt.n; t++) {
+    float* dst = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(pt.table[t]) + PEER_HEADER_BYTES);
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = e / w;
+      const int j = (int)(e - i * w);
+      const int64_t r = row_index[i];
+      dst[r * w + j] = j < r2 ? src_pi32[i * r2 + j] : (float)src_st[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(ticket, 1u);
+    if (done == gridDim.x - 1) {  // every block's stores are fenced: signal all tables (this rank's own included)
+      *ticket = 0;
+      __threadfence_system();
+      for (int t = 0; t < pt.n; t++) atomicAdd_system(reinterpret_cast<unsigned int*>(pt.table[t]), 1u);
+    }
+  }
+}
+
+// wait until `target` arrivals were counted in this rank's own table header (one per rank and exchange step)
+__global__ void peer_wait_kernel(const unsigned int* flag, unsigned int target) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    while (*reinterpret_cast<const volatile unsigned int*>(flag) < target) __nanosleep(200);
+    __threadfence_system();
+  }
+}
+
 }  // namespace
+
+void launch_peer_scatter(const float* src_pi32, const uint8_t* src_st, const int64_t* row_index, int64_t k, int r2,
+                         const PeerTables& pt, unsigned int* ticket, int sm_count, cudaStream_t st) {
+  const int64_t want = std::max<int64_t>((k * (r2 + 1) + 255) / 256, 1);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count * 4);
+  peer_scatter_kernel<<<grid, 256, 0, st>>>(src_pi32, src_st, row_index, k, r2, pt, ticket);
+  count_launch();
+}
+
+void launch_peer_wait(const unsigned int* flag, unsigned int target, cudaStream_t st) {
+  peer_wait_kernel<<<1, 32, 0, st>>>(flag, target);
+  count_launch();
+}
 
 void launch_gather_targets(const int32_t* targets, const int32_t* list, int64_t k, int32_t* sub, int64_t* idx, cudaStream_t st) {
   if (k <= 0) return;

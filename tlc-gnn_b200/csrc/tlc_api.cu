@@ -119,8 +119,20 @@ struct tlc_graph {
   char* sm_host = nullptr;         // pinned mirror
   int small_skip = 0;              // calls left for which the small path is not tried (it handled too few rows)
   int small_hop = -1, small_mode = -1;
-  double small_ms[2] = {0, 0};
-  int64_t small_rows[3] = {0, 0, 0};  // last call: rows finished by class A / class B / handed to the staged pipeline
+  double small_ms[3] = {0, 0, 0};
+  int64_t small_rows[4] = {0, 0, 0, 0};  // last call: rows finished by class A / B / C / handed to the staged pipeline
+  // multi-GPU exchange by peer stores: this rank's table, the mapped tables of all ranks, exchange epoch
+  void* peer_own = nullptr;
+  int64_t peer_rows = 0;
+  int peer_r2 = 0;
+  PeerTables peers{};
+  std::vector<void*> peer_opened;   // tables mapped with cudaIpcOpenMemHandle
+  unsigned int peer_epoch = 0;
+  unsigned int* peer_ticket = nullptr;
+  float* px_pi32 = nullptr;         // [cap][r2] staging of the shard's rows
+  double* px_pi = nullptr;
+  uint8_t* px_st = nullptr;
+  int64_t px_cap = 0;
   std::vector<cudaEvent_t> ev_pool;  // stage-timing events, reused from call to call
   size_t ev_base = 0;                // first pool slot a (nested) call may use
   int sm_count = 0;
@@ -828,7 +840,7 @@ static int ensure_small_sub(tlc_graph* g, int64_t k, int r2) {
   return TLC_OK;
 }
 
-static constexpr size_t SM_STATS_OFF = 16;  // SmallStats behind the two deferral counters in sm_dev / sm_host
+static constexpr size_t SM_STATS_OFF = 16;  // SmallStats behind the three deferral counters in sm_dev / sm_host
 
 // which calls kernel S (k0_small.cu) can take: the batch call with a Ricci-distance filtration and a 5 x 5 image on a
 // graph whose ball cache exists; the route-forcing diagnostic flags keep their meaning (they name staged kernels)
@@ -859,22 +871,22 @@ static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tl
   const char* tenv = getenv("TLC_STAGE_TIMING");
   g->timing = tenv && atoi(tenv) != 0;
   StageTimer tm(g->timing, st, &g->ev_pool, g->ev_base);
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-  if (g->timing) { ev0 = tm.take(); ev1 = tm.take(); ev2 = tm.take(); }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev1b = nullptr, ev2 = nullptr;
+  if (g->timing) { ev0 = tm.take(); ev1 = tm.take(); ev1b = tm.take(); ev2 = tm.take(); }
   VicinityScratch vs = make_vs(g);
   int* counters = reinterpret_cast<int*>(g->sm_dev);
   SmallStats* d_stats = reinterpret_cast<SmallStats*>(g->sm_dev + SM_STATS_OFF);
   launch_ball_cache(g->gv, p, d_targets, E, vs, st);
   if (ev0) cudaEventRecord(ev0, st);
   launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, counters, nullptr, nullptr,
-               nullptr, d_stats, g->sm_count, st, ev1);
+               nullptr, d_stats, g->sm_count, st, ev1, ev1b);
   if (ev2) cudaEventRecord(ev2, st);
   CK(cudaMemcpyAsync(g->sm_host, g->sm_dev, SM_STATS_OFF + sizeof(SmallStats), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const int nC = reinterpret_cast<const int*>(g->sm_host)[1];
+  const int nC = reinterpret_cast<const int*>(g->sm_host)[2];  // rows no class could take (listed in sm_list_b)
   const SmallStats hs = *reinterpret_cast<const SmallStats*>(g->sm_host + SM_STATS_OFF);
-  float msA = 0, msB = 0;
-  if (g->timing) { cudaEventElapsedTime(&msA, ev0, ev1); cudaEventElapsedTime(&msB, ev1, ev2); }
+  float msA = 0, msB = 0, msC = 0;
+  if (g->timing) { cudaEventElapsedTime(&msA, ev0, ev1); cudaEventElapsedTime(&msB, ev1, ev1b); cudaEventElapsedTime(&msC, ev1b, ev2); }
   // a call whose vicinities are mostly too large: do not try again for a while (the size check alone costs a pass over
   // two ball bitmaps per target)
   if ((int64_t)nC * 4 > E * 3) g->small_skip = 32;
@@ -885,7 +897,7 @@ static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tl
   double s_bytes = 0;
   if (nC > 0) {
     if ((rc = ensure_small_sub(g, nC, r2))) return rc;
-    launch_gather_targets(d_targets, g->sm_list_c, nC, g->sm_sub, g->sm_idx, st);
+    launch_gather_targets(d_targets, g->sm_list_b, nC, g->sm_sub, g->sm_idx, st);
     tlc_params up2 = *up;
     up2.flags |= TLC_F_NO_SMALL;
     const size_t keep_base = g->ev_base;
@@ -901,9 +913,10 @@ static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tl
     s_rowcheck = g->last_rowcheck; s_blocks = g->last_blocks; s_direct = g->last_direct; s_chunks = g->nchunks; s_bytes = g->alg_bytes;
   }
   for (int i = 0; i < 10; i++) g->stage_ms[i] = o_ms[i];
-  g->stage_ms[9] += msA + msB;
-  g->small_ms[0] = msA; g->small_ms[1] = msB;
-  g->small_rows[0] = (int64_t)hs.handled[0]; g->small_rows[1] = (int64_t)hs.handled[1]; g->small_rows[2] = nC;
+  g->stage_ms[9] += msA + msB + msC;
+  g->small_ms[0] = msA; g->small_ms[1] = msB; g->small_ms[2] = msC;
+  g->small_rows[0] = (int64_t)hs.handled[0]; g->small_rows[1] = (int64_t)hs.handled[1]; g->small_rows[2] = (int64_t)hs.handled[2];
+  g->small_rows[3] = nC;
   g->last_live = s_live + (int64_t)hs.live; g->last_nv = s_nv + (int64_t)hs.sum_n; g->last_ne = s_ne + (int64_t)hs.sum_m;
   g->last_fb = s_fb; g->last_general = s_general; g->last_rowcheck = s_rowcheck; g->last_blocks = s_blocks; g->last_direct = s_direct;
   g->nchunks = s_chunks;
@@ -929,8 +942,8 @@ static int run_pipeline(tlc_graph* g, const int32_t* d_targets, int64_t E, const
                         float* d_pi32, uint8_t* d_status, int64_t* cnt_compute, tlc_detail* detail) {
   int rc = check_params(up);
   if (rc) return rc;
-  g->small_ms[0] = g->small_ms[1] = 0;
-  g->small_rows[0] = g->small_rows[1] = g->small_rows[2] = 0;
+  g->small_ms[0] = g->small_ms[1] = g->small_ms[2] = 0;
+  g->small_rows[0] = g->small_rows[1] = g->small_rows[2] = g->small_rows[3] = 0;
   if (small_applicable(g, up, E, detail)) {
     bool fell = false;
     rc = run_small(g, d_targets, E, up, d_pi, d_pi32, d_status, cnt_compute, &fell);
@@ -1061,6 +1074,8 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaFree(g->sm_list_b); cudaFree(g->sm_list_c); cudaFree(g->sm_sub); cudaFree(g->sm_idx); cudaFree(g->sm_pi);
   cudaFree(g->sm_pi32); cudaFree(g->sm_st); cudaFree(g->sm_dev);
   if (g->sm_host) cudaFreeHost(g->sm_host);
+  for (void* q : g->peer_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(g->peer_own); cudaFree(g->peer_ticket); cudaFree(g->px_pi32); cudaFree(g->px_pi); cudaFree(g->px_st);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   delete g;
   return TLC_OK;
@@ -1194,7 +1209,7 @@ int tlc_small_diagrams(tlc_graph* g, const int32_t* targets, int64_t E, const tl
   VicinityScratch vs = make_vs(g);
   launch_ball_cache(g->gv, p, g->io_t, E, vs, st);
   launch_small(g->gv, p, g->io_t, E, vs, g->io_pi, nullptr, g->io_st, g->sm_list_b, g->sm_list_c,
-               reinterpret_cast<int*>(g->sm_dev), g->d_n, g->d_m, &dg, nullptr, g->sm_count, st, nullptr);
+               reinterpret_cast<int*>(g->sm_dev), g->d_n, g->d_m, &dg, nullptr, g->sm_count, st, nullptr, nullptr);
   std::vector<uint8_t> k8((size_t)P + 1);
   if (npairs) CK(cudaMemcpyAsync(npairs, b_np.p, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
   if (P > 0) {
@@ -1336,6 +1351,74 @@ int tlc_pi_gather(int device, const double* dev_table, int64_t rows, int32_t r2,
   return TLC_OK;
 }
 
+// ---- multi-GPU exchange by peer stores ----
+int tlc_table_create(tlc_graph* g, int64_t rows, int32_t r2, void** dev_rows, unsigned char* handle64) {
+  if (!g || rows <= 0 || r2 < 1 || !handle64) return fail(TLC_E_INVALID, "bad arguments");
+  CK(cudaSetDevice(g->device));
+  if (g->peer_own) return fail(TLC_E_INVALID, "this graph already owns an exchange table");
+  const size_t bytes = PEER_HEADER_BYTES + (size_t)rows * (size_t)(r2 + 1) * sizeof(float);
+  CK(cudaMalloc(&g->peer_own, bytes));
+  CK(cudaMemset(g->peer_own, 0, bytes));
+  if (!g->peer_ticket) { CK(cudaMalloc((void**)&g->peer_ticket, 64)); CK(cudaMemset(g->peer_ticket, 0, 64)); }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, g->peer_own));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  memcpy(handle64, &h, 64);
+  g->peer_rows = rows; g->peer_r2 = r2; g->peer_epoch = 0;
+  g->peers.n = 0;
+  if (dev_rows) *dev_rows = reinterpret_cast<unsigned char*>(g->peer_own) + PEER_HEADER_BYTES;
+  return TLC_OK;
+}
+
+int tlc_table_attach(tlc_graph* g, int32_t nranks, int32_t my_rank, const unsigned char* handles64) {
+  if (!g || !g->peer_own || nranks < 1 || nranks > PEER_MAX || my_rank < 0 || my_rank >= nranks || !handles64)
+    return fail(TLC_E_INVALID, "bad arguments (create the table first; at most 16 ranks)");
+  CK(cudaSetDevice(g->device));
+  for (void* q : g->peer_opened) cudaIpcCloseMemHandle(q);
+  g->peer_opened.clear();
+  g->peers.n = nranks;
+  for (int r = 0; r < nranks; r++) {
+    if (r == my_rank) { g->peers.table[r] = g->peer_own; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles64 + (size_t)r * 64, 64);
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    g->peer_opened.push_back(q);
+    g->peers.table[r] = q;
+  }
+  return TLC_OK;
+}
+
+int tlc_vicinity_pi_exchange(tlc_graph* g, const int32_t* dev_targets, const int64_t* dev_row_index, int64_t E,
+                             const tlc_params* p, int64_t* cnt_compute) {
+  if (!g || (E > 0 && (!dev_targets || !dev_row_index))) return fail(TLC_E_INVALID, "NULL argument");
+  if (!g->peer_own || g->peers.n < 1) return fail(TLC_E_INVALID, "no exchange table attached (tlc_table_create / tlc_table_attach)");
+  int rc = check_params(p);
+  if (rc) return rc;
+  const int r2 = p->resolution * p->resolution;
+  if (r2 != g->peer_r2) return fail(TLC_E_INVALID, "resolution differs from the exchange table's");
+  CK(cudaSetDevice(g->device));
+  if (E > g->px_cap) {
+    cudaFree(g->px_pi32); cudaFree(g->px_pi); cudaFree(g->px_st);
+    g->px_pi32 = nullptr; g->px_pi = nullptr; g->px_st = nullptr; g->px_cap = 0;
+    const int64_t cap = E + E / 8 + 256;
+    CK(cudaMalloc((void**)&g->px_pi32, (size_t)cap * r2 * 4));
+    CK(cudaMalloc((void**)&g->px_pi, (size_t)cap * r2 * 8));
+    CK(cudaMalloc((void**)&g->px_st, (size_t)cap));
+    g->px_cap = cap;
+  }
+  if (E > 0) {
+    rc = run_pipeline(g, dev_targets, E, p, g->px_pi, g->px_pi32, g->px_st, cnt_compute, nullptr);
+    if (rc) return rc;
+  } else if (cnt_compute) *cnt_compute = 0;
+  // store this rank's rows into every rank's table at their final index, then wait for everyone's arrival
+  launch_peer_scatter(g->px_pi32, g->px_st, dev_row_index, E, r2, g->peers, g->peer_ticket, g->sm_count, g->stream);
+  g->peer_epoch++;
+  launch_peer_wait(reinterpret_cast<const unsigned int*>(g->peer_own), g->peer_epoch * (unsigned int)g->peers.n, g->stream);
+  CK(cudaGetLastError());
+  return TLC_OK;
+}
+
 int tlc_graph_set_stream(tlc_graph* g, void* stream) {
   if (!g) return fail(TLC_E_INVALID, "NULL graph");
   g->stream = stream ? (cudaStream_t)stream : g->own_stream;
@@ -1351,10 +1434,10 @@ int tlc_last_counts(tlc_graph* g, int64_t* out5) {  // out5: 8 slots
 
 int64_t tlc_last_direct(tlc_graph* g) { return g ? g->last_direct : 0; }
 
-int tlc_last_small(tlc_graph* g, double* out5) {
-  if (!g || !out5) return TLC_E_INVALID;
-  out5[0] = g->small_ms[0]; out5[1] = g->small_ms[1];
-  out5[2] = (double)g->small_rows[0]; out5[3] = (double)g->small_rows[1]; out5[4] = (double)g->small_rows[2];
+int tlc_last_small(tlc_graph* g, double* out7) {
+  if (!g || !out7) return TLC_E_INVALID;
+  for (int i = 0; i < 3; i++) out7[i] = g->small_ms[i];
+  for (int i = 0; i < 4; i++) out7[3 + i] = (double)g->small_rows[i];
   return TLC_OK;
 }
 

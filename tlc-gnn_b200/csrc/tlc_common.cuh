@@ -216,16 +216,27 @@ struct SmallDiag {  // optional diagram output: pairs of row t at poff[t] (capac
   double *birth, *death;
 };
 struct SmallStats {  // device accumulators of one call
-  unsigned long long handled[2];  // rows finished by class A / class B (any status)
+  unsigned long long handled[3];  // rows finished by class A / B / C (any status)
   unsigned long long live, sum_n, sum_m;  // over the rows with status <= TRIVIAL
   double bytes;                   // their compulsory bytes B_e
 };
 void launch_small(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
                   double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int* counters,
                   int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count, cudaStream_t st,
-                  cudaEvent_t ev_mid);
+                  cudaEvent_t ev_mid, cudaEvent_t ev_mid2);
 // rows of a sub-list: sub[i] = targets[list[i]], idx[i] = list[i]
 void launch_gather_targets(const int32_t* targets, const int32_t* list, int64_t k, int32_t* sub, int64_t* idx, cudaStream_t st);
+
+// multi-GPU exchange by peer stores (k5_gather.cu): the tables of all ranks, this rank's own included
+constexpr int PEER_MAX = 16;
+constexpr size_t PEER_HEADER_BYTES = 256;  // [u32 arrival counter | pad] in front of the float32 rows
+struct PeerTables {
+  int n;
+  void* table[PEER_MAX];
+};
+void launch_peer_scatter(const float* src_pi32, const uint8_t* src_st, const int64_t* row_index, int64_t k, int r2,
+                         const PeerTables& pt, unsigned int* ticket, int sm_count, cudaStream_t st);
+void launch_peer_wait(const unsigned int* flag, unsigned int target, cudaStream_t st);
 
 int64_t launch_count();
 void count_launch();

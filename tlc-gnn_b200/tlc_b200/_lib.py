@@ -24,7 +24,8 @@ ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NOD
 EXPORTS = ["tlc_graph_create", "tlc_graph_destroy", "tlc_vicinity_pi", "tlc_vicinity_pi_dev", "tlc_vicinity_sizes",
            "tlc_vicinity_detail", "tlc_union_find", "tlc_pimg_transform", "tlc_last_error", "tlc_version",
            "tlc_launch_count", "tlc_last_stage_ms", "tlc_last_algorithmic_bytes", "tlc_graph_set_stream",
-           "tlc_last_counts", "tlc_last_direct", "tlc_pi_gather", "tlc_last_small", "tlc_small_diagrams"]
+           "tlc_last_counts", "tlc_last_direct", "tlc_pi_gather", "tlc_last_small", "tlc_small_diagrams",
+           "tlc_table_create", "tlc_table_attach", "tlc_vicinity_pi_exchange"]
 
 
 class Params(C.Structure):
@@ -97,6 +98,12 @@ def lib():
     L.tlc_last_direct.argtypes = [vp]
     L.tlc_last_small.restype = C.c_int
     L.tlc_last_small.argtypes = [vp, vp]
+    L.tlc_table_create.restype = C.c_int
+    L.tlc_table_create.argtypes = [vp, i64, i32, C.POINTER(vp), vp]
+    L.tlc_table_attach.restype = C.c_int
+    L.tlc_table_attach.argtypes = [vp, i32, i32, vp]
+    L.tlc_vicinity_pi_exchange.restype = C.c_int
+    L.tlc_vicinity_pi_exchange.argtypes = [vp, vp, vp, i64, C.POINTER(Params), C.POINTER(i64)]
     L.tlc_small_diagrams.restype = C.c_int
     L.tlc_small_diagrams.argtypes = [vp, vp, i64, C.POINTER(Params), vp] + [vp] * 10
     _lib = L

@@ -184,9 +184,10 @@ class VicinityGraph:
     def last_small(self):
         """kernel S in the last call: device ms of its two launches (TLC_STAGE_TIMING=1), rows finished per class, rows
         handed on to the staged pipeline."""
-        out = np.zeros(5)
+        out = np.zeros(7)
         L.lib().tlc_last_small(self._h, out.ctypes.data)
-        return dict(ms_a=float(out[0]), ms_b=float(out[1]), rows_a=int(out[2]), rows_b=int(out[3]), rows_staged=int(out[4]))
+        return dict(ms_a=float(out[0]), ms_b=float(out[1]), ms_c=float(out[2]), rows_a=int(out[3]), rows_b=int(out[4]),
+                    rows_c=int(out[5]), rows_staged=int(out[6]))
 
     def last_stage_ms(self):
         out = np.zeros(10)
