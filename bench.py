@@ -49,6 +49,11 @@ def parse():
     ap.add_argument("--negatives", type=int, default=0, help="append an equal number of seeded non-adjacent pairs (collab config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--scaling", default=os.environ.get("TLC_BENCH_SCALING", "weak"), choices=["weak", "strong"],
+                    help="weak: --batch targets per GPU and step (default); strong: --batch targets per step in total, split over the GPUs")
+    ap.add_argument("--exchange", default=os.environ.get("TLC_EXCHANGE", "peer"), choices=["peer", "nccl"],
+                    help="N > 1: peer = rows stored straight into every rank's table over NVLink (tlc_vicinity_pi_exchange); "
+                         "nccl = pad + NCCL all-gather + un-permute (torch.distributed)")
     ap.add_argument("--secondary", type=int, default=int(os.environ.get("TLC_BENCH_SECONDARY", "1")),
                     help="1: also measure the other BASELINE.json configurations (a few steps each) into the `secondary` object")
     return ap.parse_args()
@@ -106,12 +111,14 @@ def config_dict(args, world):
                         "norm=True, 5x5 image, extended_flag=%s" % (args.workload, N, M, args.hop, kind,
                                                                     " + equal negatives" if args.negatives else "",
                                                                     bool(args.extended)),
-            "targets_per_gpu_per_step": args.batch, "global_targets_per_step": args.batch * world,
+            "targets_per_gpu_per_step": args.batch if getattr(args, "scaling", "weak") == "weak" else args.batch / world,
+            "global_targets_per_step": args.batch * world if getattr(args, "scaling", "weak") == "weak" else args.batch,
             "kappa": "U(-0.9,0.9) on a 1/1024 grid", "extended_flag": bool(args.extended),
             "l2": "new targets every step; per-step working set >> L2 (no flush needed)",
             "ball_cache": "warm: the k-hop ball bitmap of a node is expanded once per graph (13.7 k balls serve all 245,861 "
                           "targets) and the warm-up steps fill it; the timed steps reuse it, as every call after the first does",
-            "parallelism": "targets sharded over %d GPU(s), CSR replicated, NCCL all-gather of fp32 images" % world}
+            "parallelism": "targets sharded over %d GPU(s), CSR replicated; N > 1: every rank stores its fp32 image rows "
+                           "straight into every rank's table (peer stores over NVLink) or, --exchange nccl, NCCL all-gather" % world}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -435,9 +442,26 @@ def run_cuda(args):
     out_pi = torch.zeros((B, r2), dtype=torch.float64, device=dev)
     out_f32 = torch.zeros((B, r2), dtype=torch.float32, device=dev)
     out_st = torch.zeros((B,), dtype=torch.uint8, device=dev)
-    sv = multi.ShardedVicinity(csr[0], multi.cuda_local_fn(g, dev, hop=args.hop, flags=flags, mode=cmode), dev) if world > 1 else None
+    strong = args.scaling == "strong"
+    G = B if strong else B * world   # targets per step over all ranks
+    sv, exchange, exchange_note = None, None, None
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "peer":
+            try:
+                sv = multi.PeerShardedVicinity(g, csr[0], dev, max_rows=G, hop=args.hop, flags=flags, mode=cmode)
+            except Exception as ex:  # (e.g. CUDA IPC not permitted between the ranks' containers): say so, use NCCL
+                exchange, exchange_note = "nccl", "peer-store exchange unavailable: %s" % (repr(ex)[:160])
+            ok = torch.tensor([1 if exchange == "peer" else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+            if int(ok.item()) == 0 and exchange == "peer":
+                exchange, exchange_note, sv = "nccl", "peer-store exchange unavailable on another rank", None
+        if exchange == "nccl":
+            sv = multi.ShardedVicinity(csr[0], multi.cuda_local_fn(g, dev, hop=args.hop, flags=flags, mode=cmode), dev)
 
-    def global_targets(s):  # the step's targets of ALL ranks (weak scaling: world * B per step)
+    def global_targets(s):  # the step's targets of ALL ranks (weak: world * B per step; strong: B per step in total)
+        if strong:
+            return batch_targets(ne, perm, s, 0, 1, B)
         return np.concatenate([batch_targets(ne, perm, s, r, world, B) for r in range(world)])
 
     def step(s):  # inputs resident in HBM before the timed region
@@ -493,7 +517,7 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_max = float(t.item())
-    value = world * B * args.steps / elapsed_max
+    value = G * args.steps / elapsed_max
 
     # ---- e2e through the reference-facing API (host in, host out) ----
     import sg2dgm.riccidist2dgm as mirror
@@ -526,14 +550,17 @@ def run_cuda(args):
         t0 = time.perf_counter()
         for s in range(args.steps):
             pi_all, st_all = sv.compute(e2e_lists[1 + s])
-            pi_host = pi_all.cpu()
+            if rank == 0:  # the caller's table on the host (one copy of it: rank 0; every rank holds it in HBM)
+                pi_host = pi_all.cpu()
+            else:
+                torch.cuda.current_stream().synchronize()
         torch.cuda.synchronize()
         te_local = time.perf_counter() - t0
-        h2d, d2h = int(B * 8), int(world * B * r2 * 4)
+        h2d, d2h = int(G // world * 8), int(G * r2 * 4)
     te = torch.tensor([te_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(te.item())
+    e2e_value = G * args.steps / float(te.item())
 
     if rank == 0:
         peaks = {}
@@ -586,8 +613,8 @@ def run_cuda(args):
             secondary = run_secondary(dev, local, peak, {(args.workload, args.mode, args.negatives): (c, labels, ne, csr, perm)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config_dict(args, world),
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(args, world), "exchange": exchange, "exchange_note": exchange_note,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "stage_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()}},
                 "handed_back_per_step": handed_back / args.steps, "kernel_S_last_step": ks_last,

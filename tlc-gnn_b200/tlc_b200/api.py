@@ -181,6 +181,31 @@ class VicinityGraph:
                             pdv=pdv[a:b], pbirth=pbirth[a:b], pdeath=pdeath[a:b]))
         return out
 
+    # ---- multi-GPU exchange by peer stores (include/tlc_b200.h: tlc_table_*) ----
+    def table_create(self, rows, resolution=5):
+        """this rank's exchange table float32[rows][res^2 + 1]: -> (device address of row 0, 64-byte CUDA IPC handle)"""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        L.check(L.lib().tlc_table_create(self._h, int(rows), int(resolution) * int(resolution), C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def table_attach(self, handles, my_rank):
+        """handles: the 64-byte IPC handles of ALL ranks, ordered by rank"""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        L.check(L.lib().tlc_table_attach(self._h, len(handles), int(my_rank), buf))
+
+    def vicinity_pi_exchange(self, targets_dev, row_index_dev, hop=2, mode=L.MODE_EDGE, descriptor="sum", resolution=5,
+                             flags=L.F_NORM, img_mask=None):
+        """this rank's shard (torch CUDA tensors int32[k,2], int64[k]) through the path, every row stored at its final
+        index into the exchange table of every rank; asynchronous on the graph's stream"""
+        k = int(targets_dev.shape[0])
+        p = make_params(hop, mode, descriptor, resolution, flags, img_mask)
+        L.check(L.lib().tlc_vicinity_pi_exchange(
+            self._h, _dev_ptr(targets_dev, "int32", (k, 2), self.device, "targets_dev") if k else None,
+            _dev_ptr(row_index_dev, "int64", (k,), self.device, "row_index_dev") if k else None, k, C.byref(p), None))
+
     def last_small(self):
         """kernel S in the last call: device ms of its two launches (TLC_STAGE_TIMING=1), rows finished per class, rows
         handed on to the staged pipeline."""
