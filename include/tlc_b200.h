@@ -65,6 +65,13 @@ extern "C" {
                                 which finishes every vicinity of <= 1024 vertices / <= 4096 edges in one launch per size class,
                                 and hand only the larger ones to the staged kernels.  Same results bit for bit */
 
+#define TLC_F_NO_TABLE 8192u /* graph-row route: never use the per-root shortest-path tables (kernel 1t), always run kernel 1b's
+                                Dijkstra per target.  Default: on graphs of <= 16384 nodes whose tables fit the budget
+                                (20 N^2 bytes <= TLC_SSSP_CACHE_GB, default 8) the distances, tree parents and path sums of a
+                                root over the WHOLE graph are computed once; a vicinity vertex whose tree branch stays inside
+                                the vicinity takes its values from the table, the others are relaxed over their own rows.
+                                Same results bit for bit */
+
 #define TLC_F_FILT_DEGREE 512u      /* PDGNN generators, filt='degree': filtration = induced degree / (max + 1e-10)
                                        Knowledge_Distillation/data_utils_NC.py:126-128 (no roots, no distances) */
 #define TLC_F_FILT_CENTRALITY 1024u /* filt='centrality': nx.degree_centrality (d * 1/(n-1)) / (max + 1e-10)   :118-121 */
@@ -169,6 +176,16 @@ int tlc_small_diagrams(tlc_graph *g, const int32_t *targets, int64_t E, const tl
                        int32_t *npairs, int32_t *pkind, int32_t *pbv, int32_t *pdv, double *pbirth, double *pdeath,
                        double *out_pi, uint8_t *out_status, int32_t *out_n, int32_t *out_m);
 
+/* compute_ricci_curvature (loaddatas.py:105-123): OllivierRicci(G, alpha, method="Sinkhorn").compute_ricci_curvature() on the
+ * unweighted graph given as a symmetric CSR (ascending rows, no self-loops) -- the step BEFORE the path, whose output is
+ * the `kappa` of tlc_graph_create.  out_kappa[nnz] receives the curvature of every directed entry (both directions of an
+ * edge carry the same value, :117-121); out_iters[nnz] (may be NULL) the Sinkhorn iterations spent.  HOST buffers; runs
+ * kernel 6 (k6_ricci.cu) on `device`.  The reference's arithmetic for this step lives in GraphRicciCurvature + POT, neither
+ * vendored nor pinned by the reference: their published algorithm is restated (nbr_topk = 3000, reg = 0.1, <= 1000
+ * iterations, stop at 1e-9) -- parity unpinned, see oracle/ricci_oracle.py. */
+int tlc_ollivier_ricci(int device, int32_t N, int64_t nnz, const int32_t *rowptr, const int32_t *col, double alpha,
+                       double *out_kappa, int32_t *out_iters);
+
 /* Union_find(simplex_filter) + Accelerate_PD(Pos, Neg, simplex_filter) on ONE caller-supplied graph
  * (accelerated_PD.py:26,115; KD/accelerated_PD.py:25,120): n vertices with filtration fval[n], m edges
  * (a[i], b[i]) in the caller's dict order (that order is the tie-break).  flags: TLC_F_EXTENDED,
@@ -234,6 +251,10 @@ int tlc_last_algorithmic_bytes(tlc_graph *g, double *bytes_total, double *bytes_
 int tlc_last_counts(tlc_graph *g, int64_t *out8);
 /* targets of the last call that took the graph-row route (TLC_F_DIRECT / TLC_F_NO_DIRECT) */
 int64_t tlc_last_direct(tlc_graph *g);
+/* targets of the last call whose filtration came from the per-root shortest-path tables (kernel 1t; TLC_F_NO_TABLE).  For
+ * those targets of a BATCH call the induced edges are not counted (no kernel reads all their rows any more): they are
+ * missing from tlc_last_counts' sum m and from the 16 m term of tlc_last_algorithmic_bytes; tlc_vicinity_sizes counts them. */
+int64_t tlc_last_table(tlc_graph *g);
 /* kernel S in the last call: out[0..2] = device ms of the class A (warp per target, n <= 64) / class B (128-thread CTA,
  * n <= 256) / class C (256-thread CTA, n <= 1024) launch (TLC_STAGE_TIMING=1), out[3..5] = rows they finished,
  * out[6] = rows handed on to the staged pipeline */

@@ -39,7 +39,8 @@ def test_binding_constants_match_header():
                  ("TLC_ST_OK", L.ST_OK), ("TLC_ST_NO_TREE_EDGES", L.ST_NO_TREE_EDGES), ("TLC_DESC_SUM", L.DESC["sum"]),
                  ("TLC_MODE_EDGE_FORCED", L.MODE_EDGE_FORCED), ("TLC_F_NO_DIRECT", L.F_NO_DIRECT), ("TLC_F_DIRECT", L.F_DIRECT),
                  ("TLC_F_ASC_ONLY", L.F_ASC_ONLY), ("TLC_F_FILT_DEGREE", L.F_FILT_DEGREE),
-                 ("TLC_F_FILT_CENTRALITY", L.F_FILT_CENTRALITY), ("TLC_F_FILT_CLUSTERING", L.F_FILT_CLUSTERING)]:
+                 ("TLC_F_FILT_CENTRALITY", L.F_FILT_CENTRALITY), ("TLC_F_FILT_CLUSTERING", L.F_FILT_CLUSTERING),
+                 ("TLC_F_NO_SMALL", L.F_NO_SMALL), ("TLC_F_NO_TABLE", L.F_NO_TABLE), ("TLC_ST_NOT_SMALL", L.ST_NOT_SMALL)]:
         assert int(macros[k]) == v, k
     assert C.sizeof(L.Params) == 24
 
@@ -59,6 +60,30 @@ def test_call_level_errors_without_gpu():
     import torch
     if not torch.cuda.is_available():   # no device: a well-formed call reports TLC_E_NODEVICE instead of crashing
         assert lib.tlc_graph_create(2, 2, rp.ctypes.data, col.ctypes.data, kap.ctypes.data, 0, 0, C.byref(h)) == -4
+
+
+def test_graph_create_validates_the_csr():
+    """a malformed CSR would mean out-of-bounds device accesses: every precondition is checked on the host, before any
+    CUDA call (so this runs without a GPU), and reported through rc / tlc_last_error"""
+    lib = L.lib()
+    h = C.c_void_p()
+
+    def create(rp, col, kap):
+        rp = np.asarray(rp, np.int32); col = np.asarray(col, np.int32); kap = np.asarray(kap, np.float64)
+        rc = lib.tlc_graph_create(len(rp) - 1, len(col), rp.ctypes.data, col.ctypes.data, kap.ctypes.data, 0, 0, C.byref(h))
+        return rc, lib.tlc_last_error().decode()
+
+    # path 0 - 1 - 2, well formed except for the one defect under test
+    rc, msg = create([0, 3, 1, 4], [1, 0, 2, 1], [0, 0, 0, 0]);            assert rc == -1 and "monotone" in msg
+    rc, msg = create([0, 1, 3, 4], [1, 0, 7, 1], [0, 0, 0, 0]);            assert rc == -1 and "out of range" in msg
+    rc, msg = create([0, 1, 3, 4], [0, 0, 2, 1], [0, 0, 0, 0]);            assert rc == -1 and "self-loop" in msg
+    rc, msg = create([0, 1, 3, 4], [1, 2, 0, 1], [0, 0, 0, 0]);            assert rc == -1 and "ascending" in msg
+    rc, msg = create([0, 2, 4, 4], [1, 1, 0, 0], [0, 0, 0, 0]);            assert rc == -1 and "ascending" in msg   # duplicate entry
+    rc, msg = create([0, 1, 2, 3], [1, 2, 1], [0, 0, 0]);                  assert rc == -1 and "symmetric" in msg
+    rc, msg = create([0, 1, 3, 4], [1, 0, 2, 1], [0.5, 0.25, 0, 0]);       assert rc == -1 and "mirror" in msg      # kappa(0,1) != kappa(1,0)
+    rc, msg = create([0, 1, 3, 4], [1, 0, 2, 1], [-1.0, -1.0, 0, 0]);      assert rc == -1 and "kappa + 1" in msg   # weight 0
+    rc, msg = create([0, 1, 3, 4], [1, 0, 2, 1], [0, 0, np.nan, np.nan]);  assert rc == -1 and "kappa + 1" in msg
+    rc, msg = create([0, 1, 3, 4], [1, 0, 2, 1], [0, 0, np.inf, np.inf]);  assert rc == -1 and "kappa + 1" in msg
 
 
 def test_csr_ingestion_matches_reference_numbering():

@@ -236,21 +236,29 @@ def test_graph_row_route_random(name, scale, hop, cont):
     tg = ne[rng.choice(len(ne), 48, replace=False)].astype(np.int32)
     neg = rng.integers(0, len(labels), size=(16, 2)).astype(np.int32)
     tg = np.concatenate([tg, neg, np.array([[-1, 3], [0, 0]], np.int32)])
-    compare_asc(g, og, tg, hop, "sum", L.F_NORM | L.F_DIRECT, orc.F_NORM)
+    compare_asc(g, og, tg, hop, "sum", L.F_NORM | L.F_DIRECT, orc.F_NORM)                  # kernel 1t (shortest-path tables)
+    compare_asc(g, og, tg, hop, "sum", L.F_NORM | L.F_DIRECT | L.F_NO_TABLE, orc.F_NORM)   # kernel 1b on the graph rows
     o = og.run_batch(tg, hop=hop, flags=orc.F_NORM)
-    for fl in (L.F_DIRECT, 0, L.F_NO_DIRECT):  # forced, density-routed (mixed chunks), materialised
+    # forced with / without the tables, default routing (kernel S first), staged + density-routed, materialised
+    for fl in (L.F_DIRECT | L.F_NO_TABLE, L.F_DIRECT, 0, L.F_NO_SMALL, L.F_NO_DIRECT):
         pi, status, cnt = g.vicinity_pi(tg, hop=hop, flags=L.F_NORM | fl)
         assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
         assert rel_err(pi, o["pi"]) < IMG_TOL
         cn = g.last_counts()
-        if fl == L.F_DIRECT:
+        if fl == (L.F_DIRECT | L.F_NO_TABLE):
             pi_d, cn_d = pi, cn
             # (a target kernel 3v hands back needs the adjacency: the whole call is then redone on the materialised route)
             assert cn["graph_row_route"] > 0 or cn["handed_back"] > 0
+            assert cn["table_route"] == 0
         else:
             assert np.array_equal(pi, pi_d)
-            # the edge totals agree whether kernel 1's counting pass or kernel 1b (graph-row batch call) counted them
-            assert (cn["sum_n"], cn["sum_m"], cn["live"]) == (cn_d["sum_n"], cn_d["sum_m"], cn_d["live"])
+            if fl == L.F_DIRECT:
+                assert cn["table_route"] > 0 or cn["handed_back"] > 0
+            if cn["table_route"] == 0:
+                # the edge totals agree whether kernel 1's counting pass, kernel 1b (graph-row batch call) or kernel S counted them
+                assert (cn["sum_n"], cn["sum_m"], cn["live"]) == (cn_d["sum_n"], cn_d["sum_m"], cn_d["live"])
+            else:
+                assert (cn["sum_n"], cn["live"]) == (cn_d["sum_n"], cn_d["live"])
     assert abs(g.last_algorithmic_bytes()) > 0
     g.close()
 

@@ -1,0 +1,499 @@
+// k1t_sssp_table.cu -- kernel 1t: the node filtration from a per-ROOT shortest-path table of the whole graph.
+//
+// build_fv (riccidist2dgm.py:20-61) needs, for a target (u, v), the shortest-path distances from u and from v INSIDE the
+// vicinity S.  Kernel 1b runs one Dijkstra per root and target.  On graphs small enough to afford O(N^2) entries the
+// same values come from a table that is built ONCE per graph and root r over the WHOLE graph G:
+//     D_r[x] = least fixpoint of d[y] = min_x fl(d[x] + w(x, y)) on G          (what Dijkstra returns, fl(+) monotone)
+//     P_r[x] = smallest id y with fl(D_r[y] + w(y, x)) == D_r[x]               (the tree rule of kernel 1b / the oracle)
+//     Q_r[x] = python-order sum of the weights along x -> P_r[x] -> ... -> r   (:30,35)
+// For a vicinity S containing r call x VALID when its whole tree branch x -> ... -> r lies in S.  Then, exactly:
+//   * d_S[x] == D_r[x]: d_S >= D_r (fewer edges), and along the branch d_S[x] <= fl(d_S[p] + w) = fl(D_r[p] + w) = D_r[x];
+//   * the tree parent inside S is P_r[x]: every candidate y in S (fl(d_S[y] + w) == d_S[x]) is a candidate in G as well
+//     (D_r[y] <= d_S[y] and D_r[x] is minimal), and P_r[x], the smallest candidate of G, lies in S with d_S = D_r;
+//   * hence the path and its python-order sum are Q_r[x].
+// The other vertices of S (their branch leaves S: 10-20 % on the Computers-shaped 2-hop vicinities, 0.3 % on the largest)
+// get their distance from the same fixpoint restricted to them, the valid vertices acting as settled sources: rounds of
+// "pull" relaxations over THEIR graph rows only, then the tree rule and the path walk (through computed parents, then
+// through the table once the walk reaches a valid vertex).  Results are bit-identical to kernel 1b (tests: the parity
+// suite runs both; TLC_F_NO_TABLE selects kernel 1b).
+//
+// Rows read per target drop from 2 x D_S (every row of the vicinity, once per root) to the rows of the invalid
+// vertices; the table rows of u and v (D, Q, P: 20 N bytes each) are streamed instead.
+#include <cstdlib>
+
+#include "tlc_common.cuh"
+
+namespace tlc {
+namespace {
+
+constexpr unsigned long long T_INF = 0x7ff0000000000000ull;
+
+struct PySumT {  // CPython's float sum(): first item exact, then Neumaier (3.12+) or plain adds
+  double s, c;
+  int k;
+};
+__device__ __forceinline__ void pyt_add(PySumT& p, double x, bool plain) {
+  if (p.k == 0) { p.s = x; p.k = 1; return; }
+  if (plain) { p.s = __dadd_rn(p.s, x); return; }
+  const double t = __dadd_rn(p.s, x);
+  if (fabs(p.s) >= fabs(x)) p.c = __dadd_rn(p.c, __dadd_rn(__dadd_rn(p.s, -t), x));
+  else p.c = __dadd_rn(p.c, __dadd_rn(__dadd_rn(x, -t), p.s));
+  p.s = t;
+}
+__device__ __forceinline__ double pyt_get(const PySumT& p, bool plain) {
+  if (p.k == 0) return 0.0;
+  if (!plain && p.c != 0.0 && isfinite(p.c)) return __dadd_rn(p.s, p.c);
+  return p.s;
+}
+
+__device__ __forceinline__ unsigned long long shfl_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }
+  return v;
+}
+
+__device__ inline int scan_words(int32_t* data, int cnt, int32_t* wsum) {  // exclusive scan in shared memory, returns the total
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
+  const int per = (cnt + nt - 1) / nt;
+  const int lo = min(tid * per, cnt), hi = min(lo + per, cnt);
+  int s = 0;
+  for (int i = lo; i < hi; i++) s += data[i];
+  int inc = s;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const int wv = lane < nw ? wsum[lane] : 0;
+    int winc = wv;
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += v; }
+    if (lane < nw) wsum[lane] = winc - wv;
+    if (lane == 31) wsum[32] = winc;
+  }
+  __syncthreads();
+  int run = wsum[wid] + inc - s;
+  for (int i = lo; i < hi; i++) { const int v = data[i]; data[i] = run; run += v; }
+  return wsum[32];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// table build: one CTA per root, whole graph, distances + parents in shared memory
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void sssp_mark_kernel(const int32_t* __restrict__ targets, int64_t E, int node_mode, GraphView g, SsspTables tb) {
+  const int64_t total = 2 * E;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (node_mode && (i & 1)) continue;
+    const int32_t x = targets[i];
+    if (x < 0 || x >= g.N || g.rowptr[x + 1] == g.rowptr[x]) continue;
+    if (tb.state[x] == 0 && atomicCAS(&tb.state[x], 0, 1) == 0) tb.list[atomicAdd(tb.count, 1)] = x;
+  }
+}
+
+constexpr int BQ = 2048;  // vertices settled per phase at most
+struct BuildShared {
+  int32_t q[BQ];
+  int32_t qn, qhead;
+  unsigned long long dmin;
+  int32_t any;
+};
+
+__global__ void __launch_bounds__(1024) sssp_build_kernel(GraphView g, SsspTables tb, const float* __restrict__ gminw,
+                                                          double* __restrict__ pw_scratch, int plain) {
+  extern __shared__ __align__(16) unsigned long long bsm[];
+  __shared__ BuildShared sh;
+  const int N = g.N;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  unsigned long long* dist = bsm;                                   // [N]
+  int32_t* par = reinterpret_cast<int32_t*>(bsm + N);               // [N]
+  uint8_t* state = reinterpret_cast<uint8_t*>(par + N);             // [N]  0 far, 1 tentative, 2 done
+  double* pw = pw_scratch + (size_t)blockIdx.x * N;                 // weight of the parent edge (global scratch of this CTA)
+  const int cnt = *tb.count;
+  for (int idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
+    const int32_t root = tb.list[idx];
+    __syncthreads();
+    for (int x = tid; x < N; x += nt) { dist[x] = T_INF; state[x] = 0; par[x] = -1; }
+    __syncthreads();
+    if (tid == 0) { dist[root] = 0ull; state[root] = 1; }
+    __syncthreads();
+    for (int phase = 0; phase < 2 * N + 2; phase++) {
+      // smallest tentative distance
+      if (tid == 0) { sh.dmin = T_INF; sh.qn = 0; sh.qhead = 0; }
+      __syncthreads();
+      unsigned long long lm = T_INF;
+      for (int x = tid; x < N; x += nt) if (state[x] == 1) { const unsigned long long d = dist[x]; lm = d < lm ? d : lm; }
+      lm = shfl_min_u64(lm);
+      if (lane == 0 && lm != T_INF) atomicMin(&sh.dmin, lm);
+      __syncthreads();
+      const unsigned long long dminb = sh.dmin;
+      if (dminb == T_INF) break;
+      const double dmin = __longlong_as_double((long long)dminb);
+      // settle every tentative x with d[x] <= fl(dmin + minw[x])   (Crauser et al.'s IN criterion, exact by monotonicity of fl)
+      for (int x = tid; x < N; x += nt) {
+        if (state[x] != 1) continue;
+        if (__longlong_as_double((long long)dist[x]) <= __dadd_rn(dmin, (double)gminw[x])) {
+          const int pos = atomicAdd(&sh.qn, 1);
+          if (pos < BQ) { state[x] = 2; sh.q[pos] = x; }
+        }
+      }
+      __syncthreads();
+      const int qn = min(sh.qn, BQ);
+      // relax the settled rows: a warp per row, rows handed out by a shared counter
+      for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&sh.qhead, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= qn) break;
+        const int x = sh.q[i];
+        const double dx = __longlong_as_double((long long)dist[x]);
+        const int a = g.rowptr[x], b = g.rowptr[x + 1];
+        for (int e = a + lane; e < b; e += 32) {
+          const int y = g.col[e];
+          const unsigned long long tbv = (unsigned long long)__double_as_longlong(__dadd_rn(dx, __dadd_rn(g.kappa[e], 1.0)));
+          if (tbv < dist[y]) { atomicMin(&dist[y], tbv); if (state[y] == 0) state[y] = 1; }
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    // tree rule: parent[x] = smallest id y with fl(d[y] + w) == d[x] (rows ascend: the first matching position)
+    for (int x = wid; x < N; x += nw) {
+      const unsigned long long dxb = dist[x];
+      if (x == root || dxb == T_INF) continue;
+      const int a = g.rowptr[x], b = g.rowptr[x + 1];
+      for (int e0 = a; e0 < b; e0 += 32) {
+        const int e = e0 + lane;
+        bool hit = false;
+        double w = 0.0;
+        int y = 0;
+        if (e < b) {
+          y = g.col[e];
+          w = __dadd_rn(g.kappa[e], 1.0);
+          const unsigned long long dyb = dist[y];
+          hit = dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dxb;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+          if (lane == __ffs(bal) - 1) { par[x] = y; pw[x] = w; }
+          break;
+        }
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // outputs: D (bit pattern as double), P, Q (python-order path sum; 100 where the root does not reach x: riccidist2dgm.py:31-32)
+    double* Drow = tb.D + (size_t)root * N;
+    double* Qrow = tb.Q + (size_t)root * N;
+    int32_t* Prow = tb.P + (size_t)root * N;
+    for (int x = tid; x < N; x += nt) {
+      const unsigned long long dxb = dist[x];
+      Drow[x] = __longlong_as_double((long long)dxb);
+      Prow[x] = par[x];
+      double res;
+      if (x == root) res = 0.0;
+      else if (dxb == T_INF || par[x] < 0) res = 100.0;
+      else {
+        PySumT ps{0.0, 0.0, 0};
+        int y = x, guard = 0;
+        while (y != root && guard++ <= N) { pyt_add(ps, pw[y], plain != 0); y = par[y]; }
+        res = pyt_get(ps, plain != 0);
+      }
+      Qrow[x] = res;
+    }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); tb.state[root] = 2; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel 1t proper: one CTA per target of the graph-row route
+// ---------------------------------------------------------------------------------------------------------------------
+struct TableShared {
+  double redd[32];
+  int32_t wsum[33];
+  int32_t ninv;     // invalid vertices of the current root
+  int32_t any;
+};
+
+// weight kappa + 1 of the graph edge (x, y): bisection of x's ascending row
+__device__ __forceinline__ double edge_weight(const GraphView& g, int x, int y) {
+  int lo = g.rowptr[x], hi = g.rowptr[x + 1];
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.col[mid] < y) lo = mid + 1; else hi = mid; }
+  return __dadd_rn(g.kappa[lo], 1.0);
+}
+
+__global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkView c, int t0, int cap, GraphView g,
+                                                                const uint32_t* __restrict__ ball_cache, SsspTables tb, int W) {
+  extern __shared__ __align__(16) unsigned long long dynt[];
+  __shared__ TableShared sh;
+  const int t = t0 + blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const bool node_mode = p.mode == TLC_MODE_NODE;
+  const int64_t vo = c.voff[t];
+  const int N = g.N;
+  // dynamic shared memory: dist u64[cap] | parent local id u16[cap] | class u8[cap] | bitmap + ranks u32[2W] | local ids u16[N]
+  unsigned long long* dist = dynt;
+  uint16_t* parl = reinterpret_cast<uint16_t*>(dynt + cap);
+  uint8_t* cls = reinterpret_cast<uint8_t*>(parl + cap);
+  uint32_t* bm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dynt) + (size_t)cap * 11);
+  uint16_t* lid = reinterpret_cast<uint16_t*>(bm + 2 * W);
+
+  // ---- 0. the vicinity (as kernel 1b's graph-row prologue): nodes = set(nodes_u) & set(nodes_v), local ids = ranks   :311-316
+  const int64_t ti = c.tidx[t];
+  const int32_t u = c.tgt[2 * ti], v = c.tgt[2 * ti + 1];
+  bool bad = u < 0 || u >= N || (!node_mode && (v < 0 || v >= N));  // dict_node KeyError   :353
+  if (!bad) bad = g.rowptr[u + 1] == g.rowptr[u] || (!node_mode && g.rowptr[v + 1] == g.rowptr[v]);
+  if (bad) {
+    if (tid == 0) { c.tn[t] = 0; c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tlu[t] = -1; c.tlv[t] = -1;
+                    c.tstatus[t] = TLC_ST_UNKNOWN_NODE; }
+    return;
+  }
+  const uint32_t* __restrict__ bu = ball_cache + (size_t)u * W;
+  const uint32_t* __restrict__ bv = ball_cache + (size_t)v * W;
+  for (int w = tid; w < W; w += nt) {
+    const uint32_t x = node_mode ? bu[w] : (bu[w] & bv[w]);
+    bm[w] = x;
+    bm[W + w] = __popc(x);
+  }
+  __syncthreads();
+  const int n = scan_words(reinterpret_cast<int32_t*>(bm + W), W, sh.wsum);
+  __syncthreads();
+  uint32_t* gb = c.dbm + (size_t)t * 2 * W;  // kernels 2v / 3v map graph ids through it
+  for (int w = tid; w < 2 * W; w += nt) gb[w] = bm[w];
+  {
+    uint32_t* l32 = reinterpret_cast<uint32_t*>(lid);
+    for (int i = tid; i < (N + 1) / 2; i += nt) l32[i] = 0xffffffffu;
+  }
+  __syncthreads();
+  for (int w = wid; w < W; w += nw) {  // a warp per bitmap word: vertex list, graph rows, graph id -> local id
+    const uint32_t bits = bm[w];
+    if (!((bits >> lane) & 1u)) continue;
+    const int lx = (int)bm[W + w] + __popc(bits & lanemask_lt());
+    const int32_t x = w * 32 + lane;
+    const int32_t ra = g.rowptr[x];
+    c.vert[vo + lx] = x;
+    c.astart[vo + lx] = ra;
+    c.adeg[vo + lx] = g.rowptr[x + 1] - ra;
+    lid[x] = (uint16_t)lx;
+  }
+  const int lu = bitmap_rank(bm, W, u);
+  const int lv = node_mode ? lu : bitmap_rank(bm, W, v);
+  uint8_t st0 = (lu >= 0 && lv >= 0) ? TLC_ST_OK : TLC_ST_TRIVIAL;
+  if (n == 0 || (node_mode && n == 1)) st0 = TLC_ST_EMPTY;  // :318 / data_utils_NC.py:103-104
+  if (tid == 0) {
+    c.tn[t] = n; c.tlu[t] = lu; c.tlv[t] = lv; c.tstatus[t] = st0;
+    if (c.count_m) c.tm[t] = 0;  // batch call: the induced edges are not counted on this route (nobody reads all rows)
+    c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tncls[t] = 0;
+  }
+  __syncthreads();
+  if (n == 0 || st0 > TLC_ST_TRIVIAL) return;
+
+  const int32_t* __restrict__ vert = c.vert + vo;
+  double* d1 = c.d1 + vo;
+  double* d2 = c.d2 + vo;
+  double* fval = c.fval + vo;
+  int32_t* hint = c.neg + vo;     // tree parent towards the last root (kernel 2v's "neighbour in an earlier block" hint)
+  int32_t* hint0 = c.vcls + vo;   // ... and towards the first root
+  int32_t* inv = c.vs0 + vo;      // list of the invalid vertices of the current root
+  double* tpw = reinterpret_cast<double*>(c.v64b + vo);  // weight of an invalid vertex's parent edge
+  const bool roots_in = lu >= 0 && lv >= 0;
+  const bool plain = (p.flags & TLC_F_SUM_PLAIN) != 0;
+  const bool two = roots_in && !node_mode && lu != lv;
+  constexpr uint8_t UNKNOWN = 0, VALID = 1, INVALID = 2;
+
+  if (!roots_in) {
+    // nx.NodeNotFound for every vertex -> dist = 100   riccidist2dgm.py:31-32,36-37
+    for (int x = tid; x < n; x += nt) { d1[x] = 100.0; d2[x] = 100.0; hint[x] = -1; hint0[x] = -1; }
+  } else {
+    for (int r = 0; r < (two ? 2 : 1); r++) {
+      const int root = r == 0 ? lu : lv;
+      const int32_t groot = r == 0 ? u : v;
+      const double* __restrict__ Drow = tb.D + (size_t)groot * N;
+      const double* __restrict__ Qrow = tb.Q + (size_t)groot * N;
+      const int32_t* __restrict__ Prow = tb.P + (size_t)groot * N;
+      double* out = r == 0 ? d1 : d2;
+      int32_t* hnt = r == 0 ? hint0 : hint;
+      if (tid == 0) sh.ninv = 0;
+      // ---- 1. classes: the branch of x stays in S <=> its table parent is in S and is valid itself ----
+      for (int x = tid; x < n; x += nt) {
+        const int32_t gx = vert[x];
+        uint8_t cl;
+        uint16_t pl = 0xffff;
+        if (x == root) cl = VALID;
+        else {
+          const int32_t gp = Prow[gx];
+          pl = gp >= 0 ? lid[gp] : (uint16_t)0xffff;
+          cl = pl == 0xffff ? INVALID : UNKNOWN;
+        }
+        cls[x] = cl; parl[x] = pl;
+        dist[x] = (unsigned long long)__double_as_longlong(Drow[gx]);
+        if (r == 0) { hint[x] = -1; hint0[x] = -1; }
+      }
+      __syncthreads();
+      for (int round = 0; round <= n; round++) {
+        int ch = 0;
+        for (int x = tid; x < n; x += nt) {
+          if (cls[x] != UNKNOWN) continue;
+          const uint8_t pc = cls[parl[x]];
+          if (pc != UNKNOWN) { cls[x] = pc; ch = 1; }   // (a stale read only delays the vertex to the next round)
+          else ch = 1;
+        }
+        if (!__syncthreads_or(ch)) break;
+      }
+      // ---- 2. the invalid vertices, their distances by pull relaxations over their own graph rows ----
+      for (int x0 = 0; x0 < n; x0 += nt) {
+        const int x = x0 + tid;
+        const bool iv = x < n && cls[x] == INVALID;
+        const unsigned bal = __ballot_sync(0xffffffffu, iv);
+        int base = 0;
+        if (bal && lane == 0) base = atomicAdd(&sh.ninv, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (iv) { inv[base + __popc(bal & lanemask_lt())] = x; dist[x] = T_INF; }
+      }
+      __syncthreads();
+      const int ninv = sh.ninv;
+      for (int round = 0; round <= ninv; round++) {
+        int ch = 0;
+        for (int i = wid; i < ninv; i += nw) {
+          const int x = inv[i];
+          const int32_t gx = vert[x];
+          const int a = g.rowptr[gx], b = g.rowptr[gx + 1];
+          unsigned long long best = T_INF;
+          for (int e = a + lane; e < b; e += 32) {
+            const uint16_t ly = lid[g.col[e]];
+            if (ly == 0xffff) continue;
+            const unsigned long long dyb = dist[ly];
+            if (dyb == T_INF) continue;
+            const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __dadd_rn(g.kappa[e], 1.0)));
+            best = cand < best ? cand : best;
+          }
+          best = shfl_min_u64(best);
+          if (lane == 0 && best < dist[x]) { dist[x] = best; ch = 1; }
+        }
+        if (!__syncthreads_or(ch)) break;
+      }
+      // ---- 3. tree rule for the invalid vertices: smallest local id y with fl(d[y] + w) == d[x] ----
+      for (int i = wid; i < ninv; i += nw) {
+        const int x = inv[i];
+        const unsigned long long dxb = dist[x];
+        if (dxb == T_INF) continue;
+        const int32_t gx = vert[x];
+        const int a = g.rowptr[gx], b = g.rowptr[gx + 1];
+        for (int e0 = a; e0 < b; e0 += 32) {
+          const int e = e0 + lane;
+          bool hit = false;
+          double w = 0.0;
+          uint16_t ly = 0xffff;
+          if (e < b) {
+            ly = lid[g.col[e]];
+            if (ly != 0xffff) {
+              const unsigned long long dyb = dist[ly];
+              w = __dadd_rn(g.kappa[e], 1.0);
+              hit = dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dxb;
+            }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (bal) {
+            if (lane == __ffs(bal) - 1) { parl[x] = ly; tpw[x] = w; }
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- 4. path sums: the table's for valid vertices, a walk in python order for the others   :30,35 ----
+      for (int x = tid; x < n; x += nt) {
+        double res;
+        const uint8_t cl = cls[x];
+        if (x == root) res = 0.0;
+        else if (cl == VALID) { res = Qrow[vert[x]]; hnt[x] = (int32_t)parl[x]; }
+        else if (dist[x] == T_INF) res = 100.0;  // nx.NetworkXNoPath -> 100 (disconnected vicinity; status 3 later)
+        else {
+          hnt[x] = (int32_t)parl[x];
+          PySumT ps{0.0, 0.0, 0};
+          int y = x, guard = 0;
+          while (y != root && guard++ <= n) {
+            const int py = (int)parl[y];
+            const double w = cls[y] == INVALID ? tpw[y] : edge_weight(g, vert[y], vert[py]);
+            pyt_add(ps, w, plain);
+            y = py;
+          }
+          res = pyt_get(ps, plain);
+        }
+        out[x] = res;
+      }
+      __syncthreads();
+    }
+    if (!two) for (int x = tid; x < n; x += nt) d2[x] = d1[x];
+    __syncthreads();
+    // `if x in [root_1, root_2]`: all three attributes 0   riccidist2dgm.py:22-25
+    if (tid == 0) { d1[lu] = 0.0; d2[lu] = 0.0; d1[lv] = 0.0; d2[lv] = 0.0; }
+  }
+  __syncthreads();
+
+  // ---- 5. descriptors + normalisation   riccidist2dgm.py:47-56 ; data_utils_NC.py:52-54 ----
+  double mx = -1.0, sm = -1.0;
+  for (int x = tid; x < n; x += nt) {
+    const double a = d1[x], b = d2[x];
+    mx = fmax(mx, fmax(a, b));
+    sm = fmax(sm, node_mode ? a : __dadd_rn(a, b));
+  }
+  double smax = block_reduce_max(mx, sh.redd);
+  double ssum = block_reduce_max(sm, sh.redd);
+  const bool norm = (p.flags & TLC_F_NORM) != 0;
+  if (norm) {
+    if (p.flags & TLC_F_NORM_EPS) { smax = __dadd_rn(smax, 1e-10); ssum = __dadd_rn(ssum, 1e-10); }
+    else if (smax == 0.0 || ssum == 0.0) {  // ZeroDivisionError -> zeros   riccidist2dgm.py:54-56,356-357
+      if (tid == 0) c.tstatus[t] = TLC_ST_DEGENERATE;
+      return;
+    }
+  }
+  for (int x = tid; x < n; x += nt) {
+    const double a = d1[x], b = d2[x];
+    double f;
+    if (p.descriptor == TLC_DESC_MIN) f = fmin(a, b);
+    else if (p.descriptor == TLC_DESC_MAX) f = fmax(a, b);
+    else f = node_mode ? a : __dadd_rn(a, b);
+    if (norm) f = __ddiv_rn(f, p.descriptor == TLC_DESC_SUM ? ssum : smax);
+    fval[x] = f;
+  }
+}
+
+}  // namespace
+
+// build the table rows of the targets' endpoints that do not exist yet (once per graph and root)
+void launch_sssp_build(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const SsspTables& tb,
+                       const float* gminw, double* pw_scratch, int grid, cudaStream_t st) {
+  if (!tb.D || E <= 0) return;
+  cudaMemsetAsync(tb.count, 0, sizeof(int), st);
+  const int mgrid = (int)std::min<int64_t>((2 * E + 255) / 256, 4096);
+  sssp_mark_kernel<<<mgrid, 256, 0, st>>>(targets, E, p.mode == TLC_MODE_NODE ? 1 : 0, g, tb);
+  count_launch();
+  const size_t bytes = (size_t)g.N * (8 + 4 + 1) + 16;
+  cudaFuncSetAttribute((const void*)sssp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaFuncSetAttribute((const void*)sssp_build_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  sssp_build_kernel<<<grid, 1024, bytes, st>>>(g, tb, gminw, pw_scratch, (p.flags & TLC_F_SUM_PLAIN) ? 1 : 0);
+  count_launch();
+}
+
+size_t sssp_build_smem(int N) { return (size_t)N * (8 + 4 + 1) + 16; }
+
+void launch_filtration_table(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
+                             const SsspTables& tb, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
+  const int W = (g.N + 31) / 32;
+  const int cap = (int)((n_max + 7) / 8 * 8);
+  const size_t bytes = (size_t)cap * 11 + (size_t)2 * W * 4 + ((size_t)g.N + 1) / 2 * 4 + 16;
+  if (block < 128) block = 128;
+  if (bytes + sizeof(TableShared) > 110 * 1024 && block >= 512) block = 1024;  // one resident CTA per SM: give it 32 warps
+  if (const char* env = getenv("TLC_TABLE_BLOCK")) block = atoi(env);  // (tuning experiments)
+  cudaFuncSetAttribute((const void*)filtration_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaFuncSetAttribute((const void*)filtration_table_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  filtration_table_kernel<<<cnt, block, bytes, st>>>(p, c, t0, cap, g, vs.ball_cache, tb, W);
+  count_launch();
+}
+
+// shared memory kernel 1t needs for a vicinity of n_max vertices (the host checks it against the 227 KB limit)
+size_t filtration_table_smem(int N, int64_t n_max) {
+  const int W = (N + 31) / 32;
+  const int cap = (int)((n_max + 7) / 8 * 8);
+  return (size_t)cap * 11 + (size_t)2 * W * 4 + ((size_t)N + 1) / 2 * 4 + 16 + sizeof(TableShared);
+}
+
+}  // namespace tlc

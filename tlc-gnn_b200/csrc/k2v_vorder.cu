@@ -29,7 +29,7 @@
 namespace tlc {
 namespace {
 
-__global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, int t0, int smem_ints, int bm_in_smem) {
+__global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, int t0, int smem_ints, int bm_in_smem, int sort_cap) {
   extern __shared__ int32_t dyn[];
   __shared__ SortShared sh;
   const int t = t0 + blockIdx.x;
@@ -48,10 +48,14 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
   // so only vertices sharing a float can be out of place); then every run of equal floats is put into exact
   // (float64 value, id) order by the thread that finds its start -- runs are exact ties (already in id order by
   // stability) or a handful of near-equal values.  Half the radix passes of a 64-bit sort.
-  uint32_t* k0 = reinterpret_cast<uint32_t*>(c.v64a + vo);
-  uint32_t* k1 = reinterpret_cast<uint32_t*>(c.v64b + vo);
-  uint32_t* p0 = reinterpret_cast<uint32_t*>(c.vs0 + vo);
-  uint32_t* p1 = reinterpret_cast<uint32_t*>(c.vs1 + vo);
+  // the sort's ping-pong buffers (keys + payload, 16 B per vertex) live in shared memory when the launch made room for the
+  // sub-range's largest vicinity (sort_cap >= n): every radix pass then scatters through shared memory instead of the arena
+  uint32_t* sort_base = reinterpret_cast<uint32_t*>(dyn + smem_ints) + (bm_in_smem ? 2 * c.W : 0);
+  const bool sort_smem = sort_cap >= n && sort_cap > 0;
+  uint32_t* k0 = sort_smem ? sort_base : reinterpret_cast<uint32_t*>(c.v64a + vo);
+  uint32_t* k1 = sort_smem ? sort_base + sort_cap : reinterpret_cast<uint32_t*>(c.v64b + vo);
+  uint32_t* p0 = sort_smem ? sort_base + 2 * sort_cap : reinterpret_cast<uint32_t*>(c.vs0 + vo);
+  uint32_t* p1 = sort_smem ? sort_base + 3 * sort_cap : reinterpret_cast<uint32_t*>(c.vs1 + vo);
   // normalised filtrations live in [0, 1]: a 24-bit fixed-point image floor(f * 2^24) is monotone too and saves a radix
   // pass; collisions (values closer than 6e-8) are equal-key runs, fixed below exactly like equal floats
   int out_of_unit = 0;
@@ -186,11 +190,14 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
 void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
   const int smem_ints = n_max * 4 <= 160 * 1024 ? (int)n_max : 0;
   const int bm_in_smem = c.dbm != nullptr && (size_t)c.W * 8 <= 48 * 1024;
-  const size_t bytes = (size_t)smem_ints * 4 + (bm_in_smem ? (size_t)c.W * 8 : 0);
+  size_t bytes = (size_t)smem_ints * 4 + (bm_in_smem ? (size_t)c.W * 8 : 0);
+  int sort_cap = (int)((n_max + 3) / 4 * 4);
+  if (smem_ints == 0 || bytes + (size_t)sort_cap * 16 > 200 * 1024 || getenv("TLC_VORDER_GLOBAL_SORT")) sort_cap = 0;
+  bytes += (size_t)sort_cap * 16;
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (const char* env = getenv("TLC_VORDER_BLOCK")) block = atoi(env);  // (tuning experiments)
-  vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints, bm_in_smem);
+  vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints, bm_in_smem, sort_cap);
   count_launch();
 }
 

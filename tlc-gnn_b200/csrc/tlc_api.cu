@@ -121,6 +121,12 @@ struct tlc_graph {
   int small_hop = -1, small_mode = -1;
   double small_ms[3] = {0, 0, 0};
   int64_t small_rows[4] = {0, 0, 0, 0};  // last call: rows finished by class A / B / C / handed to the staged pipeline
+  // kernel 1t: per-root shortest-path tables of the whole graph (valid for sssp_plain), scratch of the build kernel
+  SsspTables sssp{};
+  double* sssp_pw = nullptr;
+  int sssp_plain = -1;
+  bool sssp_tried = false;
+  int64_t last_table = 0;  // targets of the last call whose filtration came from the tables
   // multi-GPU exchange by peer stores: this rank's table, the mapped tables of all ranks, exchange epoch
   void* peer_own = nullptr;
   int64_t peer_rows = 0;
@@ -253,6 +259,38 @@ static int ensure_vicinity_scratch(tlc_graph* g, const Params& p) {
   return TLC_OK;
 }
 
+// kernel 1t's tables: three [N][N] arrays, allocated once when the graph is small enough (N <= 16384: the build kernel keeps a
+// root's whole distance / parent vector in shared memory) and 20 N^2 bytes fit TLC_SSSP_CACHE_GB (default 8, 0 disables)
+static int ensure_sssp_tables(tlc_graph* g, const Params& p) {
+  const int plain = (p.flags & TLC_F_SUM_PLAIN) ? 1 : 0;
+  if (!g->sssp_tried) {
+    g->sssp_tried = true;
+    const char* env = getenv("TLC_SSSP_CACHE_GB");
+    const double gb = env ? atof(env) : 8.0;
+    const size_t N = (size_t)g->gv.N;
+    const size_t need = N * N * 20;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (gb > 0 && N <= 16384 && (double)need <= gb * (double)(1ull << 30) && need <= free_b / 3 &&
+        sssp_build_smem((int)N) <= 227 * 1024) {
+      CK(cudaMalloc((void**)&g->sssp.D, N * N * 8));
+      CK(cudaMalloc((void**)&g->sssp.Q, N * N * 8));
+      CK(cudaMalloc((void**)&g->sssp.P, N * N * 4));
+      CK(cudaMalloc((void**)&g->sssp.state, N * 4));
+      CK(cudaMalloc((void**)&g->sssp.list, N * 4));
+      CK(cudaMalloc((void**)&g->sssp.count, 64));
+      CK(cudaMalloc((void**)&g->sssp_pw, (size_t)g->sm_count * N * 8));
+      CK(cudaMemset(g->sssp.state, 0, N * 4));
+      g->sssp_plain = plain;
+    }
+  }
+  if (g->sssp.D && g->sssp_plain != plain) {  // the path sums depend on the summation rule: rebuild on demand
+    CK(cudaMemsetAsync(g->sssp.state, 0, (size_t)g->gv.N * 4, g->stream));
+    g->sssp_plain = plain;
+  }
+  return TLC_OK;
+}
+
 // carve the arena for a chunk with T targets, Nv vertices, Ne edges (pairs = Nv + Ne + T)
 static size_t chunk_bytes(int64_t T, int64_t Nv, int64_t Ne, int64_t Na, int64_t Wd = 0) {
   const int64_t Np = Nv + Ne + T;
@@ -359,7 +397,7 @@ struct SubRange { int t0, cnt; int64_t n_max; };
 
 static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_t n_max, int64_t m_max,
                        const std::vector<SubRange>& subs, double* d_pi,
-                       float* d_pi32, uint8_t* d_status, bool want_lists, StageTimer& tm) {
+                       float* d_pi32, uint8_t* d_status, bool want_lists, StageTimer& tm, bool use_table = false) {
   cudaStream_t st = g->stream;
   const int block = block_for(m_max);
   VicinityScratch vs = make_vs(g);
@@ -374,7 +412,10 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
       const SubRange& r = subs[i];
       cudaStream_t s = st;
       if (fork && i > 0 && i <= 3) { s = g->side[i - 1]; cudaStreamWaitEvent(s, g->ev_fork, 0); }
-      if (c.dbm) launch_filtration_direct(g->gv, p, c, vs, g->gminw, r.t0, r.cnt, block, r.n_max, s);
+      if (c.dbm && use_table && filtration_table_smem(g->gv.N, r.n_max) <= 226 * 1024) {
+        launch_filtration_table(g->gv, p, c, vs, g->sssp, r.t0, r.cnt, block, r.n_max, s);
+        g->last_table += r.cnt;
+      } else if (c.dbm) launch_filtration_direct(g->gv, p, c, vs, g->gminw, r.t0, r.cnt, block, r.n_max, s);
       else launch_filtration(p, c, r.t0, r.cnt, block, r.n_max, s);
       if (s != st) { cudaEventRecord(g->ev_join[i - 1], s); cudaStreamWaitEvent(st, g->ev_join[i - 1], 0); }
     }
@@ -517,6 +558,16 @@ static int run_staged(tlc_graph* g, const int32_t* d_targets, int64_t E, const t
   }
   // the batch call on the graph-row route skips counting the induced edges (kernel 1b counts them as it reads the rows)
   const bool light = call_direct && detail == nullptr;
+  // kernel 1t: the graph-row route's filtration from per-root tables of the whole graph, where they are affordable
+  bool use_table = false;
+  g->last_table = 0;
+  if (call_direct && !(p.flags & TLC_F_NO_TABLE) && !getenv("TLC_NO_TABLE")) {
+    if ((rc = ensure_sssp_tables(g, p))) return rc;
+    if (g->sssp.D) {
+      use_table = true;
+      launch_sssp_build(g->gv, p, d_targets, E, g->sssp, g->gminw, g->sssp_pw, g->sm_count, st);
+    }
+  }
   if (light)
     launch_vicinity_light(g->gv, p, d_targets, E, g->d_n, g->d_m, g->d_ds, g->d_st, g->d_bytes, vs, g->sm_count, st);
   else
@@ -676,7 +727,7 @@ static int run_staged(tlc_graph* g, const int32_t* d_targets, int64_t E, const t
       if (!light) CK(cudaMemcpyAsync((void*)c.tm, h_tm + pos, (size_t)T * 4, cudaMemcpyHostToDevice, st));
       int fb0 = 0, fb1 = 0;
       CK(cudaMemcpyAsync(&fb0, g->work_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
-      run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm);
+      run_stages(g, p, c, n_max, m_max, subs, d_pi, d_pi32, d_status, detail != nullptr, tm, use_table);
       CK(cudaMemcpyAsync(&fb1, g->work_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
       if (light) CK(cudaMemcpyAsync(h_tm + pos, c.tm, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -974,7 +1025,7 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
   //   weight kappa + 1 finite and > 0 (networkx's Dijkstra precondition; kernel 1b orders distances by their bit patterns)
   for (int32_t x = 0; x < N; x++)
     if (rowptr[x + 1] < rowptr[x]) return fail(TLC_E_INVALID, "rowptr is not monotone at node " + std::to_string(x));
-  for (int32_t x = 0; x < N; x++) {
+  for (int32_t x = 0; x < N; x++) {  // pass 1: every row well formed on its own (pass 2 bisects the rows)
     for (int64_t e = rowptr[x]; e < rowptr[x + 1]; e++) {
       const int32_t y = col[e];
       if (y < 0 || y >= N) return fail(TLC_E_INVALID, "col out of range in row " + std::to_string(x));
@@ -983,6 +1034,11 @@ int tlc_graph_create(int32_t N, int64_t nnz, const int32_t* rowptr, const int32_
       const double w = kappa[e] + 1.0;
       if (!(w > 0.0) || !std::isfinite(w))
         return fail(TLC_E_INVALID, "kappa + 1 must be finite and > 0 (edge " + std::to_string(x) + "-" + std::to_string(y) + ")");
+    }
+  }
+  for (int32_t x = 0; x < N; x++) {  // pass 2: symmetry
+    for (int64_t e = rowptr[x]; e < rowptr[x + 1]; e++) {
+      const int32_t y = col[e];
       const int32_t* lo = col + rowptr[y];
       const int32_t* hi = col + rowptr[y + 1];
       const int32_t* it = std::lower_bound(lo, hi, x);
@@ -1074,6 +1130,8 @@ int tlc_graph_destroy(tlc_graph* g) {
   cudaFree(g->sm_list_b); cudaFree(g->sm_list_c); cudaFree(g->sm_sub); cudaFree(g->sm_idx); cudaFree(g->sm_pi);
   cudaFree(g->sm_pi32); cudaFree(g->sm_st); cudaFree(g->sm_dev);
   if (g->sm_host) cudaFreeHost(g->sm_host);
+  cudaFree(g->sssp.D); cudaFree(g->sssp.Q); cudaFree(g->sssp.P); cudaFree(g->sssp.state); cudaFree(g->sssp.list);
+  cudaFree(g->sssp.count); cudaFree(g->sssp_pw);
   for (void* q : g->peer_opened) cudaIpcCloseMemHandle(q);
   cudaFree(g->peer_own); cudaFree(g->peer_ticket); cudaFree(g->px_pi32); cudaFree(g->px_pi); cudaFree(g->px_st);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
@@ -1226,6 +1284,130 @@ int tlc_small_diagrams(tlc_graph* g, const int32_t* targets, int64_t E, const tl
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   if (pkind) for (int64_t i = 0; i < P; i++) pkind[i] = k8[(size_t)i];
+  return TLC_OK;
+}
+
+int tlc_ollivier_ricci(int device, int32_t N, int64_t nnz, const int32_t* rowptr, const int32_t* col, double alpha,
+                       double* out_kappa, int32_t* out_iters) {
+  if (N <= 0 || nnz < 0 || !rowptr || (nnz > 0 && (!col || !out_kappa))) return fail(TLC_E_INVALID, "bad arguments");
+  if (rowptr[0] != 0 || rowptr[N] != nnz) return fail(TLC_E_INVALID, "rowptr[0] != 0 or rowptr[N] != nnz");
+  if (!(alpha >= 0.0 && alpha <= 1.0)) return fail(TLC_E_INVALID, "alpha must lie in [0, 1]");
+  // the same structural contract as tlc_graph_create: ascending rows without duplicates or self-loops, symmetric
+  for (int32_t x = 0; x < N; x++) {
+    if (rowptr[x + 1] < rowptr[x]) return fail(TLC_E_INVALID, "rowptr is not monotone at node " + std::to_string(x));
+    for (int64_t e = rowptr[x]; e < rowptr[x + 1]; e++) {
+      const int32_t y = col[e];
+      if (y < 0 || y >= N) return fail(TLC_E_INVALID, "col out of range in row " + std::to_string(x));
+      if (y == x) return fail(TLC_E_INVALID, "self-loop at node " + std::to_string(x));  // (OllivierRicci removes self-loops)
+      if (e > rowptr[x] && col[e - 1] >= y) return fail(TLC_E_INVALID, "row " + std::to_string(x) + " is not strictly ascending");
+    }
+  }
+  // edge list (x < y), mirror positions, support sizes
+  const int TOPK = 3000;
+  std::vector<int64_t> epos, emir;
+  std::vector<int32_t> esrc;
+  std::vector<int64_t> esize;
+  for (int32_t x = 0; x < N; x++) {
+    for (int64_t e = rowptr[x]; e < rowptr[x + 1]; e++) {
+      const int32_t y = col[e];
+      const int32_t* lo = col + rowptr[y];
+      const int32_t* hi = col + rowptr[y + 1];
+      const int32_t* it = std::lower_bound(lo, hi, x);
+      if (it == hi || *it != x) return fail(TLC_E_INVALID, "graph is not symmetric: (" + std::to_string(x) + "," + std::to_string(y) + ") has no mirror entry");
+      if (x < y) {
+        epos.push_back(e); emir.push_back(it - col); esrc.push_back(x);
+        const int64_t sa = std::min<int64_t>(rowptr[x + 1] - rowptr[x], TOPK) + 1, sb = std::min<int64_t>(rowptr[y + 1] - rowptr[y], TOPK) + 1;
+        esize.push_back(std::max(sa, sb));
+      }
+    }
+  }
+  if (nnz == 0) return TLC_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TLC_E_NODEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(TLC_E_INVALID, "device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int sms = prop.multiProcessorCount;
+  const int64_t E = (int64_t)epos.size();
+  // size classes: both supports <= 120 (vectors and the code matrix in shared memory, several CTAs per SM),
+  // <= 1024 (vectors in shared memory, codes in HBM), the rest (<= 3001)
+  std::vector<int64_t> order((size_t)E);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t p, int64_t q) { return esize[(size_t)p] < esize[(size_t)q]; });
+  std::vector<int64_t> h_pos((size_t)E), h_mir((size_t)E);
+  std::vector<int32_t> h_src((size_t)E);
+  int64_t c0 = 0, c1 = 0;
+  for (int64_t i = 0; i < E; i++) {
+    const int64_t o = order[(size_t)i];
+    h_pos[(size_t)i] = epos[(size_t)o]; h_mir[(size_t)i] = emir[(size_t)o]; h_src[(size_t)i] = esrc[(size_t)o];
+    if (esize[(size_t)o] <= 120) c0 = i + 1;
+    if (esize[(size_t)o] <= 1024) c1 = i + 1;
+  }
+  const size_t Wc = ((size_t)N + 31) / 32;
+  DevBuf b_rp, b_col, b_b1, b_b2, b_acc, b_state, b_list, b_cnt, b_tg, b_pos, b_mir, b_src, b_out, b_it, b_wsum, b_slab, b_bm;
+  CK(b_rp.alloc((size_t)(N + 1) * 4)); CK(b_col.alloc((size_t)nnz * 4));
+  CK(b_b1.alloc((size_t)N * Wc * 4)); CK(b_b2.alloc((size_t)N * Wc * 4));
+  CK(b_acc.alloc((size_t)N * 16)); CK(b_state.alloc((size_t)N * 4)); CK(b_list.alloc((size_t)N * 4)); CK(b_cnt.alloc(64));
+  CK(b_tg.alloc((size_t)N * 8));
+  CK(b_pos.alloc((size_t)E * 8)); CK(b_mir.alloc((size_t)E * 8)); CK(b_src.alloc((size_t)E * 4));
+  CK(b_out.alloc((size_t)nnz * 8)); CK(b_it.alloc((size_t)nnz * 4)); CK(b_wsum.alloc((size_t)(TOPK + 1) * 8));
+  cudaStream_t st = nullptr;
+  CK(cudaMemcpy(b_rp.p, rowptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b_col.p, col, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b_pos.p, h_pos.data(), (size_t)E * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b_mir.p, h_mir.data(), (size_t)E * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b_src.p, h_src.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(b_out.p, 0, (size_t)nnz * 8));
+  CK(cudaMemset(b_it.p, 0, (size_t)nnz * 4));
+  {
+    std::vector<int32_t> tg((size_t)N * 2);
+    for (int32_t i = 0; i < N; i++) { tg[2 * (size_t)i] = i; tg[2 * (size_t)i + 1] = i; }
+    CK(cudaMemcpy(b_tg.p, tg.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+    // neighbour weight base ** (-(w ** exp_power)) = e ** -1 and its running sums, as python's sum() adds them
+    const double wnb = std::exp(-1.0);
+    std::vector<double> ws((size_t)TOPK + 1, 0.0);
+    for (int k = 1; k <= TOPK; k++) ws[(size_t)k] = ws[(size_t)k - 1] + wnb;
+    CK(cudaMemcpy(b_wsum.p, ws.data(), ws.size() * 8, cudaMemcpyHostToDevice));
+  }
+  // closed 1-hop and 2-hop balls of every node (kernel 1's ball expansion)
+  GraphView gv{N, nnz, b_rp.as<int32_t>(), b_col.as<int32_t>(), nullptr, nullptr};
+  for (int hop = 1; hop <= 2; hop++) {
+    Params pp{hop, TLC_MODE_NODE, TLC_DESC_SUM, 5, 0, 0};
+    size_t Wd = 0;
+    bool smem = false;
+    const int grid = vicinity_grid(device, gv, pp, &Wd, &smem);
+    if (!smem && !b_bm.p) CK(b_bm.alloc((size_t)grid * 2 * Wd * 4));
+    CK(cudaMemset(b_state.p, 0, (size_t)N * 4));
+    VicinityScratch vs{smem ? nullptr : b_bm.as<uint32_t>(), nullptr, grid, (hop == 1 ? b_b1 : b_b2).as<uint32_t>(),
+                       b_acc.as<unsigned long long>(), b_state.as<int32_t>(), b_list.as<int32_t>(), b_cnt.as<int>()};
+    launch_ball_cache(gv, pp, b_tg.as<int32_t>(), N, vs, st);
+  }
+  const double kval[4] = {std::exp(0.0 / -1e-1), std::exp(1.0 / -1e-1), std::exp(2.0 / -1e-1), std::exp(3.0 / -1e-1)};
+  const double wnb = std::exp(-1.0);
+  auto run = [&](int64_t lo, int64_t hi, int cap, bool codes_smem, int per_sm) -> int {
+    if (hi <= lo) return TLC_OK;
+    const int grid = (int)std::min<int64_t>(hi - lo, (int64_t)sms * per_sm);
+    size_t stride = 0;
+    if (!codes_smem) {
+      stride = ((size_t)cap * cap + 255) / 256 * 256;
+      if (b_slab.p) { cudaFree(b_slab.p); b_slab.p = nullptr; }
+      CK(b_slab.alloc(stride * (size_t)grid));
+    }
+    launch_ricci(b_rp.as<int32_t>(), b_col.as<int32_t>(), b_b1.as<uint32_t>(), b_b2.as<uint32_t>(), (int)Wc,
+                 b_pos.as<int64_t>() + lo, b_mir.as<int64_t>() + lo, b_src.as<int32_t>() + lo, hi - lo, alpha, kval,
+                 b_wsum.as<double>(), wnb, TOPK, 1000, 1e-9, cap, codes_smem, b_slab.as<uint8_t>(), stride, grid,
+                 b_out.as<double>(), b_it.as<int32_t>(), st);
+    return TLC_OK;
+  };
+  int rc;
+  if ((rc = run(0, c0, 120, true, 8))) return rc;
+  if ((rc = run(c0, c1, 1024, false, 2))) return rc;
+  if ((rc = run(c1, E, TOPK + 1, false, 1))) return rc;
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out_kappa, b_out.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost));
+  if (out_iters) CK(cudaMemcpy(out_iters, b_it.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost));
   return TLC_OK;
 }
 
@@ -1433,6 +1615,8 @@ int tlc_last_counts(tlc_graph* g, int64_t* out5) {  // out5: 8 slots
 }
 
 int64_t tlc_last_direct(tlc_graph* g) { return g ? g->last_direct : 0; }
+
+int64_t tlc_last_table(tlc_graph* g) { return g ? g->last_table : 0; }
 
 int tlc_last_small(tlc_graph* g, double* out7) {
   if (!g || !out7) return TLC_E_INVALID;

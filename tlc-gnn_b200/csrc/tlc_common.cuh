@@ -207,6 +207,29 @@ void launch_gather_rows(const double* table, int64_t rows, int r2, const int64_t
 void launch_scatter_rows(const double* src_pi, const float* src_pi32, const uint8_t* src_st, const int64_t* idx, int64_t k,
                          int r2, double* dst_pi, float* dst_pi32, uint8_t* dst_st, int sm_count, cudaStream_t st);
 
+// kernel 1t (k1t_sssp_table.cu): per-root shortest-path tables of the whole graph, [N][N] each, rows built on demand
+struct SsspTables {
+  double* D;       // fl-distance from the root (bit pattern of the Dijkstra fixpoint), +inf where unreachable
+  double* Q;       // python-order path sum x -> root (100 where unreachable)
+  int32_t* P;      // tree parent (graph id), -1 for the root / unreachable
+  int32_t* state;  // [N] 0 row not built, 1 claimed in this call, 2 built
+  int32_t* list;   // [N] roots to build in this call
+  int* count;
+};
+void launch_sssp_build(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const SsspTables& tb,
+                       const float* gminw, double* pw_scratch, int grid, cudaStream_t st);
+size_t sssp_build_smem(int N);
+void launch_filtration_table(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,
+                             const SsspTables& tb, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
+size_t filtration_table_smem(int N, int64_t n_max);
+
+// kernel 6 (k6_ricci.cu): Ollivier-Ricci curvature (Sinkhorn) of a host-prepared edge list
+void launch_ricci(const int32_t* rowptr, const int32_t* col, const uint32_t* ball1, const uint32_t* ball2, int W,
+                  const int64_t* epos, const int64_t* emir, const int32_t* esrc, int64_t E, double alpha, const double* kval4,
+                  const double* wsum, double wnb, int topk, int max_iter, double stop_thr, int cap, bool codes_smem,
+                  uint8_t* slab, size_t slab_stride, int grid, double* out, int32_t* iters, cudaStream_t st);
+size_t ricci_smem_bytes(int cap, bool codes_smem);
+
 // kernel S (k0_small.cu): the whole path for small vicinities in one launch per size class
 struct SmallDiag {  // optional diagram output: pairs of row t at poff[t] (capacity n + m + 2 per row)
   const int64_t* poff;

@@ -35,3 +35,28 @@ def compute_persistence_image(g, ricci_cur, train_edges, train_edges_false, val_
     os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
     np.save(filename, pi.pi_sg)                                   # :102
     return pi.pi_sg, PITable(pi.pi_sg, splits=splits, device=device)
+
+
+def compute_ricci_curvature(data=None, edge_index=None, alpha=0.5, device=0):
+    """Mirror of loaddatas.py:105-123: Ollivier-Ricci curvature (alpha-lazy measures, Sinkhorn transport) of every edge of
+    the graph given by `data.edge_index` (or `edge_index`, a [2, E] array of node labels) -- computed by kernel 6
+    (tlc_ollivier_ricci) instead of GraphRicciCurvature + POT.  Returns the reference's `ricci_list`: [[n1, n2, kappa],
+    [n2, n1, kappa], ...] sorted, ready for graph2pi(g, ricci_curv=...).  As nx.Graph does, duplicate edges collapse and
+    self-loops are dropped (OllivierRicci removes them)."""
+    from tlc_b200 import api
+    from tlc_b200.graphgen import build_csr
+    ei = np.asarray(edge_index if edge_index is not None else data.edge_index)
+    ei = ei.reshape(2, -1)
+    labels, inv = np.unique(ei.reshape(-1), return_inverse=True)       # sorted labels -> dense ids
+    e = inv.reshape(2, -1).T.astype(np.int64)
+    e = e[e[:, 0] != e[:, 1]]
+    N = len(labels)
+    key = np.unique(np.minimum(e[:, 0], e[:, 1]) * N + np.maximum(e[:, 0], e[:, 1]))
+    und = np.stack([key // N, key % N], 1)
+    rowptr, col, _ = build_csr(N, und, np.zeros(len(und)))
+    kap = api.ollivier_ricci(rowptr, col, alpha=alpha, device=device)
+    out = []
+    for x in range(N):
+        for q in range(rowptr[x], rowptr[x + 1]):
+            out.append([labels[x].item(), labels[col[q]].item(), float(kap[q])])
+    return sorted(out)

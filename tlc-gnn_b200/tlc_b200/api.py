@@ -236,7 +236,7 @@ class VicinityGraph:
         L.lib().tlc_last_counts(self._h, out.ctypes.data)
         return dict(live=int(out[0]), sum_n=int(out[1]), sum_m=int(out[2]), chunks=int(out[3]), handed_back=int(out[4]),
                     blocks_general=int(out[5]), blocks_rowcheck=int(out[6]), blocks=int(out[7]),
-                    graph_row_route=int(L.lib().tlc_last_direct(self._h)))
+                    graph_row_route=int(L.lib().tlc_last_direct(self._h)), table_route=int(L.lib().tlc_last_table(self._h)))
 
     def last_algorithmic_bytes(self):
         tot = C.c_double(0)
@@ -276,3 +276,15 @@ def pimg_transform(dgm, resolution=5, device=0):
 
 def launch_count():
     return int(L.lib().tlc_launch_count())
+
+
+def ollivier_ricci(rowptr, col, alpha=0.5, device=0, return_iters=False):
+    """Ollivier-Ricci curvature (Sinkhorn transport) of every directed CSR entry of an unweighted graph: what
+    loaddatas.compute_ricci_curvature (OllivierRicci(alpha=0.5, method="Sinkhorn")) computes before the path."""
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    cl = np.ascontiguousarray(col, dtype=np.int32)
+    out = np.zeros(cl.size, dtype=np.float64)
+    it = np.zeros(cl.size, dtype=np.int32)
+    L.check(L.lib().tlc_ollivier_ricci(int(device), int(rp.size - 1), int(cl.size), rp.ctypes.data, cl.ctypes.data, float(alpha),
+                                       out.ctypes.data, it.ctypes.data))
+    return (out, it) if return_iters else out
