@@ -35,6 +35,9 @@ extern "C" {
                                   roots always members; no edge at all -> TLC_ST_EMPTY (`return None, None`)
                                   Knowledge_Distillation/data_utils_LP.py:107-118 */
 
+#define TLC_MODE_EDGE_UNION 3 /* ball(u) | ball(v): `range == 'union'` of the legacy sg2pimg   riccidist2dgm.py:242-247 */
+#define TLC_MODE_EDGE_REMOVEINTER 4 /* (ball(u) | ball(v)) - (ball(u) & ball(v)) + [u, v]: `range == 'removeinter'`   :289-296 */
+
 /* ---- descriptor: which node attribute is the filtration     riccidist2dgm.py:47-49 ---- */
 #define TLC_DESC_MIN 0
 #define TLC_DESC_MAX 1

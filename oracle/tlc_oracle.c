@@ -27,6 +27,8 @@
 #define TLO_MODE_EDGE 0 /* riccidist2dgm.py:311-316 : ball(u) & ball(v)            */
 #define TLO_MODE_NODE 1 /* Knowledge_Distillation/data_utils_NC.py:97-100 : ball(u) */
 #define TLO_MODE_EDGE_FORCED 2 /* Knowledge_Distillation/data_utils_LP.py:107-112 : (ball(u) & ball(v)) + [u] + [v] */
+#define TLO_MODE_EDGE_UNION 3 /* sg2pimg range == 'union' riccidist2dgm.py:242-247 : nodes_u + nodes_v */
+#define TLO_MODE_EDGE_REMOVEINTER 4 /* range == 'removeinter' :289-296 : list(set(nodes_union) - nodes_intersec) + [u, v] */
 
 #define TLO_DESC_MIN 0
 #define TLO_DESC_MAX 1
@@ -394,6 +396,16 @@ static int run_target(const tlo_graph *g, int32_t u, int32_t v, const tlo_params
     memcpy(bu, w->queue, (size_t)cu * 4);
     int32_t cv = ball(g, v, p->hop, w->mark_v, w->queue);
     ws_reserve(w, (cu < cv ? cu : cv) + 2, 0);
+    if (p->mode == TLO_MODE_EDGE_UNION || p->mode == TLO_MODE_EDGE_REMOVEINTER) {
+      const int rem = p->mode == TLO_MODE_EDGE_REMOVEINTER;
+      ws_reserve(w, cu + cv + 2, 0);
+      for (int32_t i = 0; i < cu; i++) if (!(rem && w->mark_v[bu[i]])) w->vert[n++] = bu[i];             /* nodes_u (minus the intersection) */
+      for (int32_t i = 0; i < cv; i++) if (!w->mark_u[w->queue[i]]) w->vert[n++] = w->queue[i];           /* nodes_v not already taken */
+      if (rem) {                                              /* + [u, v]   :293 (g.subgraph dedups: only where the removal took them) */
+        if (w->mark_v[u]) w->vert[n++] = u;
+        if (v != u && w->mark_u[v]) w->vert[n++] = v;
+      }
+    } else
     for (int32_t i = 0; i < cu; i++) if (w->mark_v[bu[i]]) w->vert[n++] = bu[i];
     if (forced) { /* nodes = list(set(nodes_u) & set(nodes_v)) + [u] + [v]   data_utils_LP.py:111 (g.subgraph dedups) */
       if (!w->mark_v[u]) w->vert[n++] = u;

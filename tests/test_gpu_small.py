@@ -191,3 +191,23 @@ def test_small_full_cora_batch_equals_staged():
         assert np.array_equal(st_s, st_g) and cnt_s == cnt_g
         assert rel_err(pi_s, pi_g) < 1e-12
     g.close()
+
+
+@pytest.mark.parametrize("mode,omode", [(L.MODE_EDGE_UNION, orc.MODE_EDGE_UNION), (L.MODE_EDGE_REMOVEINTER, orc.MODE_EDGE_REMOVEINTER)])
+def test_union_and_removeinter_ranges(mode, omode):
+    """the vicinity shapes of the legacy sg2pimg(range='union' / 'removeinter'), riccidist2dgm.py:242-247, 289-296:
+    kernel S and the staged pipeline against the oracle"""
+    csr, ne, N = make("pubmed", 0.3, True)
+    g = api.VicinityGraph(*csr, device=0)
+    og = orc.OracleGraph(*csr)
+    rng = np.random.default_rng(21)
+    tg = np.concatenate([ne[rng.choice(len(ne), 96, replace=False)], rng.integers(0, N, size=(16, 2))]).astype(np.int32)
+    fl, ofl = L.F_NORM | L.F_EXTENDED, orc.F_NORM | orc.F_EXTENDED
+    taken = check_diagrams(g, og, tg, 1, "sum", fl, ofl, mode=mode)
+    assert taken > 0
+    o = og.run_batch(tg, hop=1, mode=omode, flags=ofl)
+    for f in (fl, fl | L.F_NO_SMALL):
+        pi, status, cnt = g.vicinity_pi(tg, hop=1, mode=mode, flags=f)
+        assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
+        assert rel_err(pi, o["pi"]) < IMG_TOL
+    g.close()

@@ -306,10 +306,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       for (int w0 = 0; w0 < W; w0 += NT) {
         const int w = w0 + tid;
         uint32_t bits = 0;
-        if (w < W) {
-          bits = node_mode ? bu[w] : (bu[w] & bv[w]);
-          if (forced) { if (w == (u >> 5)) bits |= 1u << (u & 31); if (w == (v >> 5)) bits |= 1u << (v & 31); }  // data_utils_LP.py:111
-        }
+        if (w < W) bits = combine_balls(p.mode, bu[w], bv[w], w, u, v);
         int tot;
         const int pre = tm.exscan(__popc(bits), tot);
         if (n + tot <= NC) {

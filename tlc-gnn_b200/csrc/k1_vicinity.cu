@@ -112,10 +112,8 @@ __device__ int build_vicinity(const GraphView& g, const Params& p, int32_t u, in
     const uint32_t* __restrict__ bu = vs.ball_cache + (size_t)u * W;
     const uint32_t* __restrict__ bv = vs.ball_cache + (size_t)v * W;
     const bool edge = p.mode != TLC_MODE_NODE;
-    const bool forced = p.mode == TLC_MODE_EDGE_FORCED;  // nodes = list(set(nodes_u) & set(nodes_v)) + [u] + [v]   data_utils_LP.py:111
     for (int w = tid; w < W; w += nt) {
-      uint32_t x = edge ? (bu[w] & bv[w]) : bu[w];
-      if (forced) { if (w == (u >> 5)) x |= 1u << (u & 31); if (w == (v >> 5)) x |= 1u << (v & 31); }
+      const uint32_t x = combine_balls(p.mode, bu[w], edge ? bv[w] : 0u, w, u, v);
       bm_u[w] = x;
       bm_v[w] = __popc(x);
     }
@@ -131,10 +129,8 @@ __device__ int build_vicinity(const GraphView& g, const Params& p, int32_t u, in
   ball(g, u, p.hop, bm_u, q0, q1, sh);
   if (p.mode != TLC_MODE_NODE) {
     ball(g, v, p.hop, bm_v, q0, q1, sh);
-    const bool forced = p.mode == TLC_MODE_EDGE_FORCED;
-    for (int w = tid; w < W; w += nt) {  // nodes = set(nodes_u) & set(nodes_v)   :315
-      uint32_t x = bm_u[w] & bm_v[w];
-      if (forced) { if (w == (u >> 5)) x |= 1u << (u & 31); if (w == (v >> 5)) x |= 1u << (v & 31); }
+    for (int w = tid; w < W; w += nt) {  // nodes = set(nodes_u) & set(nodes_v)   :315 (or the mode's other combination)
+      const uint32_t x = combine_balls(p.mode, bm_u[w], bm_v[w], w, u, v);
       bm_u[w] = x;
       bm_v[w] = __popc(x);
     }

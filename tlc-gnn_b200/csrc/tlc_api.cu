@@ -480,7 +480,7 @@ static int check_params(const tlc_params* p) {
   if (!p) return fail(TLC_E_INVALID, "params is NULL");
   if (p->resolution < 1 || p->resolution > 16) return fail(TLC_E_INVALID, "resolution must be in 1..16");
   if (p->hop < 0) return fail(TLC_E_INVALID, "hop must be >= 0");
-  if (p->mode != TLC_MODE_EDGE && p->mode != TLC_MODE_NODE && p->mode != TLC_MODE_EDGE_FORCED) return fail(TLC_E_INVALID, "bad mode");
+  if (p->mode < TLC_MODE_EDGE || p->mode > TLC_MODE_EDGE_REMOVEINTER) return fail(TLC_E_INVALID, "bad mode");
   if ((p->flags & TLC_F_ASC_ONLY) && (p->flags & TLC_F_EXTENDED))
     return fail(TLC_E_INVALID, "TLC_F_ASC_ONLY excludes TLC_F_EXTENDED (the loops need the Pos/Neg lists)");
   return TLC_OK;
@@ -519,7 +519,7 @@ static int run_staged(tlc_graph* g, const int32_t* d_targets, int64_t E, const t
   // where the materialised route reads the 2m induced ones, so it is taken where the vicinities are dense in the graph
   const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
   const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
-  const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc && p.mode != TLC_MODE_EDGE_FORCED &&
+  const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc && p.mode <= TLC_MODE_NODE &&
                          !(p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)) &&
                          !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
   double direct_ratio = 2.0;
@@ -1166,12 +1166,23 @@ int tlc_vicinity_pi(tlc_graph* g, const int32_t* targets, int64_t E, const tlc_p
   double* d_pi = g->io_pi;
   uint8_t* d_st = g->io_st;
   CK(cudaMemcpyAsync(d_t, targets, (size_t)E * 8, cudaMemcpyHostToDevice, g->stream));
-  rc = run_pipeline(g, d_t, E, p, d_pi, nullptr, d_st, cnt_compute, nullptr);
+  // (cnt_compute is taken from the statuses that travel to the host anyway: no extra copy + synchronisation inside the pipeline)
+  rc = run_pipeline(g, d_t, E, p, d_pi, nullptr, d_st, nullptr, nullptr);
   if (rc == TLC_OK) {
+    uint8_t* h_st = out_status;
+    if (!h_st && cnt_compute) {
+      if ((rc = ensure_pinned(g, (size_t)E + ALIGN))) return rc;
+      h_st = reinterpret_cast<uint8_t*>(g->h_pin);
+    }
     cudaError_t e1 = cudaMemcpyAsync(out_pi, d_pi, (size_t)E * r2 * 8, cudaMemcpyDeviceToHost, g->stream);
-    cudaError_t e2 = out_status ? cudaMemcpyAsync(out_status, d_st, (size_t)E, cudaMemcpyDeviceToHost, g->stream) : cudaSuccess;
+    cudaError_t e2 = h_st ? cudaMemcpyAsync(h_st, d_st, (size_t)E, cudaMemcpyDeviceToHost, g->stream) : cudaSuccess;
     cudaError_t e3 = cudaStreamSynchronize(g->stream);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail(TLC_E_CUDA, "copy back failed");
+    else if (cnt_compute) {  // targets whose image row was really computed (riccidist2dgm.py:354)
+      int64_t cnt = 0;
+      for (int64_t i = 0; i < E; i++) cnt += h_st[i] <= TLC_ST_TRIVIAL;
+      *cnt_compute = cnt;
+    }
   }
   return rc;
 }

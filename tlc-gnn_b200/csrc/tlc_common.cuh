@@ -93,6 +93,22 @@ __device__ __forceinline__ int bitmap_rank(const uint32_t* bm, int W, int g) {
   return (int)bm[W + (g >> 5)] + __popc(word & ((1u << (g & 31)) - 1u));
 }
 
+// word w of the vicinity bitmap from the two closed k-hop ball bitmaps of the target (u, v), by vicinity mode
+//   EDGE: ball(u) & ball(v) (riccidist2dgm.py:311-316) | NODE: ball(u) (data_utils_NC.py:97-100) | EDGE_FORCED: (& ) + [u, v]
+//   (data_utils_LP.py:111) | EDGE_UNION: ball(u) | ball(v) (riccidist2dgm.py:242-247) | EDGE_REMOVEINTER: (|) - (&) + [u, v] (:289-296)
+__device__ __forceinline__ uint32_t combine_balls(int mode, uint32_t bu, uint32_t bv, int w, int u, int v) {
+  uint32_t x;
+  if (mode == TLC_MODE_NODE) x = bu;
+  else if (mode == TLC_MODE_EDGE_UNION) x = bu | bv;
+  else if (mode == TLC_MODE_EDGE_REMOVEINTER) x = bu ^ bv;
+  else x = bu & bv;
+  if (mode == TLC_MODE_EDGE_FORCED || mode == TLC_MODE_EDGE_REMOVEINTER) {
+    if (w == (u >> 5)) x |= 1u << (u & 31);
+    if (w == (v >> 5)) x |= 1u << (v & 31);
+  }
+  return x;
+}
+
 // order-preserving map double -> u64 (all finite values, -0 < +0 irrelevant here)
 __device__ __forceinline__ unsigned long long f64_to_ordered(double x) {
   unsigned long long b = (unsigned long long)__double_as_longlong(x);

@@ -143,6 +143,32 @@ class graph2pi():
             raise IndexError("list index out of range")                            # accelerated_PD.py:122
         return pi[0].reshape(resolution, resolution)
 
+    def sg2pimg(self, u, v, hop, weight_graph=True, norm=False, extended_flag=False, range='intersection',
+                descriptor="seal", resolution=5):
+        """riccidist2dgm.py:228-305 (u, v are NEW labels): the image of ONE target for a vicinity shape `range` in
+        'intersection' | 'union' | 'removeinter'.  The reference computes these diagrams with dionysus (the legacy
+        path); here they come from the same union-find kernels as sg2dgm_accelerate (the same extended persistence),
+        including its connectivity assertion.  `weight_graph` is accepted for the signature (the path always uses the
+        Ricci weights, as sg2dgm_accelerate hard-codes at :320)."""
+        modes = {"intersection": L.MODE_EDGE, "union": L.MODE_EDGE_UNION, "removeinter": L.MODE_EDGE_REMOVEINTER}
+        if range not in modes:
+            raise SystemExit("Error: 'range' should be 'union' or 'intersection'! ")   # :303-305 (print + sys.exit())
+        desc = descriptor if descriptor in _DESCRIPTORS else -1
+        pi, status, _ = self._graph.vicinity_pi(np.array([[u, v]], dtype=np.int32), hop=hop, mode=modes[range], descriptor=desc,
+                                                resolution=resolution, flags=self._flags(norm, extended_flag))
+        st = int(status[0])
+        if st in (L.ST_EMPTY, L.ST_DISCONNECTED):
+            raise AssertionError("vicinity is not one connected component")
+        if st == L.ST_DEGENERATE:
+            raise ZeroDivisionError("float division by zero")
+        if st == L.ST_UNKNOWN_NODE:
+            raise KeyError((u, v))
+        if st == L.ST_BAD_DESCRIPTOR:
+            raise KeyError(descriptor)
+        if st == L.ST_NO_TREE_EDGES:
+            raise IndexError("list index out of range")
+        return pi[0].reshape(resolution, resolution)
+
     def get_pimg_for_one_edge(self, u, v, hop=2, norm=True, extended_flag=False, resolution=5, descriptor='min', cnt=0):
         """riccidist2dgm.py:348-357 (note: the reference forces norm=True at :353)."""
         try:

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("TLC_LIB") or os.path.join(_HERE, "libtlc_b200.so")  # TLC_LIB: a differently tuned build (experiments)
 
 # mirrors of the header's constants
-MODE_EDGE, MODE_NODE, MODE_EDGE_FORCED = 0, 1, 2
+MODE_EDGE, MODE_NODE, MODE_EDGE_FORCED, MODE_EDGE_UNION, MODE_EDGE_REMOVEINTER = 0, 1, 2, 3, 4
 DESC = {"min": 0, "max": 1, "sum": 2}
 F_NORM, F_EXTENDED, F_KEEP_ZERO, F_NORM_EPS, F_SUM_PLAIN, F_EDGE_SORTED = 1, 2, 4, 8, 16, 32
 F_NO_DIRECT, F_DIRECT, F_ASC_ONLY = 64, 128, 256
