@@ -80,6 +80,15 @@ extern "C" {
 #define TLC_F_FILT_CENTRALITY 1024u /* filt='centrality': nx.degree_centrality (d * 1/(n-1)) / (max + 1e-10)   :118-121 */
 #define TLC_F_FILT_CLUSTERING 2048u /* filt='clustering': nx.clustering (2 T / (d (d-1))) / (max + 1e-10)      :122-125 */
 
+#define TLC_F_FILT_HKS 16384u /* filt='hks' (the PDGNN generators' default): heat kernel signature of the UNWEIGHTED vicinity,
+                                  hks(x) = sum_k exp(-t lambda_k) phi_k(x)^2 = [exp(-t L)]_xx, L the symmetric normalised
+                                  Laplacian, divided by (max + 1e-10)   Knowledge_Distillation/data_utils_NC.py:87-93,115-117.
+                                  t = tlc_graph_set_hks_time (default 0.1).  The reference diagonalises L (scipy eigh); the
+                                  kernel evaluates the same diagonal through the Taylor series of exp((t/2) N) e_x, N = I - L:
+                                  float64, agreement ~1e-13 -- values are not bit-identical to a LAPACK run (nor is LAPACK to
+                                  itself across builds), so this filtration is pinned to 1e-9, not bit for bit */
+#define TLC_F_FILT_ANY_STRUCT (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING | TLC_F_FILT_HKS)
+
 /* ---- pair kinds, in the reference's concatenation order    accelerated_PD.py:110, riccidist2dgm.py:328 ---- */
 #define TLC_K_UP 0      /* PD_up   : 0-dim ordinary                 accelerated_PD.py:65-66 */
 #define TLC_K_ESS 1     /* [min,max]                                accelerated_PD.py:110   */
@@ -228,6 +237,9 @@ int tlc_table_create(tlc_graph *g, int64_t rows, int32_t r2, void **dev_rows, un
 int tlc_table_attach(tlc_graph *g, int32_t nranks, int32_t my_rank, const unsigned char *handles64);
 int tlc_vicinity_pi_exchange(tlc_graph *g, const int32_t *dev_targets, const int64_t *dev_row_index, int64_t E,
                              const tlc_params *p, int64_t *cnt_compute);
+
+/* diffusion time of TLC_F_FILT_HKS (hks_time of data_utils_NC.compute_persistence_image, default 0.1); 0 < t <= 50 */
+int tlc_graph_set_hks_time(tlc_graph *g, double t);
 
 /* run this graph's kernels on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
  * graph's own non-blocking stream -- to run on the legacy default stream pass cudaStreamLegacy, (void*)0x1).

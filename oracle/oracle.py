@@ -16,6 +16,21 @@ MODE_EDGE, MODE_NODE, MODE_EDGE_FORCED, MODE_EDGE_UNION, MODE_EDGE_REMOVEINTER =
 DESC = {"min": 0, "max": 1, "sum": 2}
 F_NORM, F_EXTENDED, F_KEEP_ZERO, F_NORM_EPS, F_SUM_PLAIN, F_ASIS_FV = 1, 2, 4, 8, 16, 32
 F_FILT_DEGREE, F_FILT_CENTRALITY, F_FILT_CLUSTERING = 512, 1024, 2048
+
+
+def hks_signature(n, elo, ehi, time=0.1):
+    """Knowledge_Distillation/data_utils_NC.py:87-93,115-117 on a vicinity given by its canonical edge list: the reference's
+    own lines (nx.adjacency_matrix -> csgraph.laplacian(normed=True) -> eigh -> sum of squares), then / (max + 1e-10)"""
+    import scipy.sparse as sp
+    from scipy.linalg import eigh
+    from scipy.sparse import csgraph
+    a = np.asarray(elo, dtype=np.int64)
+    b = np.asarray(ehi, dtype=np.int64)
+    A = sp.coo_matrix((np.ones(2 * len(a)), (np.concatenate([a, b]), np.concatenate([b, a]))), shape=(n, n)).tocsr()
+    Lm = csgraph.laplacian(A, normed=True)
+    egvals, egvectors = eigh(Lm.toarray())
+    f = np.square(egvectors).dot(np.diag(np.exp(-time * egvals))).sum(axis=1)
+    return f / (max(f) + 1e-10)
 K_UP, K_ESS, K_DOWN, K_ESS_REV, K_ONE = 0, 1, 2, 3, 4
 ST_NAMES = ["OK", "TRIVIAL", "EMPTY", "DISCONNECTED", "DEGENERATE", "UNKNOWN_NODE", "BAD_DESCRIPTOR", "NO_TREE_EDGES"]
 
@@ -60,6 +75,9 @@ def lib():
         _lib.tlo_run_one.restype = C.c_int
         _lib.tlo_run_one.argtypes = [C.POINTER(_Graph), C.c_int32, C.c_int32, C.POINTER(_Params), C.c_void_p,
                                      C.POINTER(_Detail)]
+        _lib.tlo_run_one_fval.restype = C.c_int
+        _lib.tlo_run_one_fval.argtypes = [C.POINTER(_Graph), C.c_int32, C.c_int32, C.POINTER(_Params), C.c_void_p, C.c_void_p,
+                                          C.POINTER(_Detail)]
         _lib.tlo_run_batch.restype = C.c_int64
         _lib.tlo_run_batch.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_int64, C.POINTER(_Params), C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -106,8 +124,9 @@ class OracleGraph:
                                   status.ctypes.data, n.ctypes.data, m.ctypes.data, npairs.ctypes.data)
         return dict(pi=pi, status=status, n=n, m=m, npairs=npairs, cnt_compute=int(cnt))
 
-    def run_one(self, u, v, hop=2, mode=MODE_EDGE, descriptor="sum", resolution=5, flags=F_NORM, img_mask=None):
-        """every intermediate of one target (stage-level parity checks)."""
+    def run_one(self, u, v, hop=2, mode=MODE_EDGE, descriptor="sum", resolution=5, flags=F_NORM, img_mask=None, fval=None):
+        """every intermediate of one target (stage-level parity checks).  fval: filtration values to use instead of the
+        computed ones (canonical vertex order), e.g. a heat kernel signature evaluated with the reference's numpy lines."""
         if img_mask is None:
             img_mask = default_img_mask(bool(flags & F_EXTENDED), bool(flags & F_KEEP_ZERO))
         p = self._params(hop, mode, descriptor, resolution, flags, img_mask)
@@ -122,7 +141,11 @@ class OracleGraph:
         for k, a in bufs.items():
             setattr(det, k, a.ctypes.data)
         img = np.zeros(resolution * resolution)
-        st = lib().tlo_run_one(C.byref(self._g), int(u), int(v), C.byref(p), img.ctypes.data, C.byref(det))
+        if fval is not None:
+            fv = np.ascontiguousarray(fval, dtype=np.float64)
+            st = lib().tlo_run_one_fval(C.byref(self._g), int(u), int(v), C.byref(p), fv.ctypes.data, img.ctypes.data, C.byref(det))
+        else:
+            st = lib().tlo_run_one(C.byref(self._g), int(u), int(v), C.byref(p), img.ctypes.data, C.byref(det))
         n, m, npairs = det.n, det.m, det.npairs
         out = dict(status=st, n=n, m=m, lu=det.lu, lv=det.lv, img=img, npos=det.npos, nneg=det.nneg)
         for k in ("vert", "d1", "d2", "fval"):

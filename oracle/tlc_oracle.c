@@ -306,6 +306,8 @@ static void sssp_root_sums(tlo_ws *w, int32_t n, int32_t root, int plain, heap_t
   }
 }
 
+static __thread const double *g_ext_fval; /* per worker thread: filtration values handed in by tlo_run_one_fval */
+
 /* sort contexts (qsort has no closure) */
 static __thread const double *g_key; /* per worker thread */
 static int cmp_asc(const void *a, const void *b) { /* stable sort by (value) == sort by (value, original index) */
@@ -544,6 +546,11 @@ static int run_target(const tlo_graph *g, int32_t u, int32_t v, const tlo_params
     }
     for (int32_t x = 0; x < n; x++) w->fval[x] = w->fval[x] / (mx + 1e-10);
   }
+  if (g_ext_fval) {
+    /* caller-supplied filtration values in canonical vertex order (tlo_run_one_fval): e.g. the heat kernel signature, which
+       the test computes with the reference's own numpy / scipy lines (data_utils_NC.py:87-93,115-117) */
+    for (int32_t x = 0; x < n; x++) w->fval[x] = g_ext_fval[x];
+  }
   if (det && det->fval) memcpy(det->fval, w->fval, (size_t)n * 8);
   if (p->descriptor < 0 || p->descriptor > 2) return TLO_ST_BAD_DESCRIPTOR; /* KeyError accelerated_PD.py:13 */
 
@@ -696,6 +703,15 @@ int tlo_run_one(const tlo_graph *g, int32_t u, int32_t v, const tlo_params *p, d
   if (st > TLO_ST_TRIVIAL) for (int32_t i = 0; i < p->resolution * p->resolution; i++) img[i] = 0.0;
   free(h.a);
   ws_free(w);
+  return st;
+}
+
+/* one target with the filtration values supplied by the caller (canonical vertex order, length = the vicinity's n as a
+ * previous tlo_run_one reports it): everything after build_fv -- keys, sweeps, loops, image -- as usual */
+int tlo_run_one_fval(const tlo_graph *g, int32_t u, int32_t v, const tlo_params *p, const double *fval_in, double *img, tlo_detail *det) {
+  g_ext_fval = fval_in;
+  int st = tlo_run_one(g, u, v, p, img, det);
+  g_ext_fval = NULL;
   return st;
 }
 

@@ -211,3 +211,34 @@ def test_union_and_removeinter_ranges(mode, omode):
         assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"]
         assert rel_err(pi, o["pi"]) < IMG_TOL
     g.close()
+
+
+@pytest.mark.parametrize("t", [0.1, 1.0, 5.0])
+def test_hks_filtration(t):
+    """filt='hks' of the PDGNN generators (data_utils_NC.py:87-93,115-117): the kernel's Taylor evaluation against the
+    reference's own numpy / scipy lines (eigh of the normalised Laplacian) to 1e-10, and everything downstream of the
+    filtration bit-exact against the oracle fed with the SAME values"""
+    csr, ne, N = make("pubmed", 0.3, True)
+    g = api.VicinityGraph(*csr, device=0)
+    g.set_hks_time(t)
+    og = orc.OracleGraph(*csr)
+    ids = np.random.default_rng(5).choice(N, 24, replace=False).astype(np.int32)
+    tg = np.stack([ids, ids], 1)
+    fl = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS | L.F_FILT_HKS
+    ofl = orc.F_NORM | orc.F_EXTENDED | orc.F_KEEP_ZERO | orc.F_NORM_EPS
+    d = g.vicinity_detail(tg, hop=2, mode=L.MODE_NODE, flags=fl)
+    checked = 0
+    for i, (u, _) in enumerate(tg):
+        a = g.per_target(d, i)
+        if a["status"] > 1:
+            continue
+        ref = orc.hks_signature(a["n"], a["elo"], a["ehi"], time=t)
+        assert np.max(np.abs(a["fval"] - ref)) < 1e-10, (i, np.max(np.abs(a["fval"] - ref)))
+        o = og.run_one(int(u), int(u), hop=2, mode=orc.MODE_NODE, flags=ofl, fval=a["fval"])
+        assert a["status"] == o["status"]
+        assert np.array_equal(a["pkind"], o["pkind"]) and np.array_equal(a["pbv"], o["pbv"]) and np.array_equal(a["pdv"], o["pdv"])
+        assert np.array_equal(a["pbirth"], o["pbirth"]) and np.array_equal(a["pdeath"], o["pdeath"])
+        assert rel_err(a["img"], o["img"]) < IMG_TOL
+        checked += 1
+    assert checked >= 12
+    g.close()

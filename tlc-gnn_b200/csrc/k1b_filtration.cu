@@ -534,6 +534,78 @@ __global__ void __launch_bounds__(256) clustering_filtration_kernel(Params p, Ch
   for (int x = tid; x < n; x += nt) fval[x] = __ddiv_rn(fval[x], m);
 }
 
+// Heat kernel signature as a filtration (Knowledge_Distillation/data_utils_NC.py:87-93, 115-117):
+//   A = nx.adjacency_matrix(subgraph) (unweighted), L = csgraph.laplacian(A, normed=True), (lambda, phi) = eigh(L),
+//   hks(x) = sum_k phi_k(x)^2 exp(-t lambda_k) = [exp(-t L)]_xx,   then / (max + 1e-10).
+// With N = D^-1/2 A D^-1/2 (L = I - N on the vertices of positive degree; scipy puts 0 on the diagonal of an isolated
+// vertex: hks = 1 there), exp(-t L) = e^-t exp(t N) and, N being symmetric, [exp(t N)]_xx = || exp((t/2) N) e_x ||^2.
+// One CTA per vicinity: for each vertex x the CTA pushes e_x through the Taylor series z = sum_j ((t/2)^j / j!) N^j e_x
+// (`terms` terms, the host chooses them so that the remainder is < 1e-18; ||N|| <= 1), two ping-pong vectors in shared
+// memory when they fit, rows of the induced adjacency dealt to the threads.
+__global__ void __launch_bounds__(256) hks_filtration_kernel(Params p, ChunkView c, double t, int terms, int cap) {
+  extern __shared__ __align__(16) double hsm[];
+  __shared__ double redd[32];
+  const int tt = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n = c.tn[tt];
+  if (n == 0 || c.tstatus[tt] > TLC_ST_TRIVIAL) return;
+  const int64_t vo = c.voff[tt], ao = c.aoff[tt];
+  const int32_t* __restrict__ astart = c.astart + vo;
+  const int32_t* __restrict__ adeg = c.adeg + vo;
+  const uint32_t* __restrict__ anb = c.anb + ao;
+  double* fval = c.fval + vo;
+  const bool in_smem = n <= cap;
+  double* isd = in_smem ? hsm : c.d1 + vo;                                   // 1 / sqrt(degree), 0 for an isolated vertex
+  double* y0 = in_smem ? hsm + cap : reinterpret_cast<double*>(c.v64a + vo);
+  double* y1 = in_smem ? hsm + 2 * cap : reinterpret_cast<double*>(c.v64b + vo);
+  double* zz = in_smem ? hsm + 3 * cap : reinterpret_cast<double*>(c.v64c + vo);
+  for (int a = tid; a < n; a += nt) {
+    const int dg = adeg[a];
+    isd[a] = dg > 0 ? __ddiv_rn(1.0, sqrt((double)dg)) : 0.0;
+    c.neg[vo + a] = -1; c.vcls[vo + a] = -1;  // (no shortest-path tree here: kernel 2v gets no neighbour hint)
+  }
+  __syncthreads();
+  const double h = 0.5 * t;
+  for (int x = 0; x < n; x++) {
+    if (adeg[x] == 0) { if (tid == 0) fval[x] = 1.0; continue; }   // (uniform over the CTA)
+    for (int a = tid; a < n; a += nt) { const double e = a == x ? 1.0 : 0.0; y0[a] = e; zz[a] = e; }
+    __syncthreads();
+    double cj = 1.0;
+    double* src = y0;
+    double* dst = y1;
+    for (int j = 1; j <= terms; j++) {
+      cj = cj * h / (double)j;
+      for (int a = tid; a < n; a += nt) {
+        const int s0 = astart[a], dg = adeg[a];
+        double acc = 0.0;
+        for (int q = 0; q < dg; q++) { const int b = (int)anb[s0 + q]; acc += isd[b] * src[b]; }
+        const double v = isd[a] * acc;
+        dst[a] = v;
+        zz[a] += cj * v;
+      }
+      __syncthreads();
+      double* tmp = src; src = dst; dst = tmp;
+    }
+    double part = 0.0;
+    for (int a = tid; a < n; a += nt) part += zz[a] * zz[a];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();
+    if ((tid & 31) == 0) redd[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (nt + 31) / 32; w++) tot += redd[w];
+      fval[x] = exp(-t) * tot;
+    }
+    __syncthreads();
+  }
+  // filtration_val /= (max(filtration_val) + 1e-10)   :117
+  double mx = -1.0;
+  for (int a = tid; a < n; a += nt) mx = fmax(mx, fval[a]);
+  const double m = __dadd_rn(block_reduce_max(mx, redd), 1e-10);
+  for (int a = tid; a < n; a += nt) fval[a] = __ddiv_rn(fval[a], m);
+}
+
 template <bool DIRECT>
 static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max,
                                   const DirectArgs& da, cudaStream_t st) {
@@ -569,6 +641,19 @@ static void launch_filtration_any(const Params& p, const ChunkView& c, int t0, i
 
 void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st) {
   launch_filtration_any<false>(p, c, t0, cnt, block, n_max, DirectArgs{}, st);
+}
+
+void launch_hks_filtration(const Params& p, const ChunkView& c, double t, int64_t n_max, cudaStream_t st) {
+  // Taylor terms: (t/2)^j / j! below 1e-18 (and past the series' largest term)
+  int terms = 1;
+  double cj = 0.5 * t;
+  while (terms < 400 && (cj > 1e-18 || terms < 0.5 * t)) { terms++; cj = cj * 0.5 * t / terms; }
+  int cap = (int)((n_max + 1) / 2 * 2);
+  if ((size_t)cap * 32 > 200 * 1024) cap = 0;  // larger vicinities keep the vectors in the arena
+  const size_t bytes = (size_t)cap * 32;
+  cudaFuncSetAttribute((const void*)hks_filtration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  hks_filtration_kernel<<<c.T, 256, bytes, st>>>(p, c, t, terms, cap);
+  count_launch();
 }
 
 void launch_degree_filtration(const Params& p, const ChunkView& c, cudaStream_t st) {

@@ -121,6 +121,7 @@ struct tlc_graph {
   int small_hop = -1, small_mode = -1;
   double small_ms[3] = {0, 0, 0};
   int64_t small_rows[4] = {0, 0, 0, 0};  // last call: rows finished by class A / B / C / handed to the staged pipeline
+  double hks_time = 0.1;   // diffusion time of TLC_F_FILT_HKS (data_utils_NC.py: hks_time = 0.1)
   // kernel 1t: per-root shortest-path tables of the whole graph (valid for sssp_plain), scratch of the build kernel
   SsspTables sssp{};
   double* sssp_pw = nullptr;
@@ -404,7 +405,8 @@ static void run_stages(tlc_graph* g, const Params& p, const ChunkView& c, int64_
   tm.mark(1);
   if (!c.dbm) launch_vicinity_fill(g->gv, p, c, vs, g->work_counter, st);
   tm.mark(2);
-  if (p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)) launch_degree_filtration(p, c, st);
+  if (p.flags & TLC_F_FILT_HKS) launch_hks_filtration(p, c, g->hks_time, n_max, st);
+  else if (p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)) launch_degree_filtration(p, c, st);
   else {
     const bool fork = subs.size() > 1 && g->ev_fork != nullptr;
     if (fork) cudaEventRecord(g->ev_fork, st);
@@ -520,7 +522,7 @@ static int run_staged(tlc_graph* g, const int32_t* d_targets, int64_t E, const t
   const int64_t Wd = ((int64_t)g->gv.N + 31) / 32;
   const bool want_desc_call = ((p.flags & TLC_F_EXTENDED) != 0 || detail != nullptr) && !(p.flags & TLC_F_ASC_ONLY);
   const bool direct_ok = g->ball_cache != nullptr && g->gminw != nullptr && !want_desc_call && !bad_desc && p.mode <= TLC_MODE_NODE &&
-                         !(p.flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)) &&
+                         !(p.flags & TLC_F_FILT_ANY_STRUCT) &&
                          !(p.flags & (TLC_F_NO_DIRECT | TLC_F_EDGE_SORTED)) && (size_t)Wd * 8 <= 64 * 1024;
   double direct_ratio = 2.0;
   if (const char* env = getenv("TLC_DIRECT_RATIO")) direct_ratio = atof(env);
@@ -898,7 +900,7 @@ static constexpr size_t SM_STATS_OFF = 16;  // SmallStats behind the three defer
 static bool small_applicable(const tlc_graph* g, const tlc_params* up, int64_t E, const tlc_detail* detail) {
   if (detail || E <= 0 || E >= ((int64_t)1 << 31)) return false;
   if (up->resolution != 5 || up->descriptor < 0 || up->descriptor > 2) return false;
-  if (up->flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING | TLC_F_EDGE_SORTED | TLC_F_DIRECT |
+  if (up->flags & (TLC_F_FILT_ANY_STRUCT | TLC_F_EDGE_SORTED | TLC_F_DIRECT |
                    TLC_F_NO_DIRECT | TLC_F_NO_SMALL | TLC_F_ASC_ONLY)) return false;
   if (getenv("TLC_NO_SMALL")) return false;
   return true;
@@ -1252,7 +1254,7 @@ int tlc_small_diagrams(tlc_graph* g, const int32_t* targets, int64_t E, const tl
   if (E == 0) return TLC_OK;
   if (E >= ((int64_t)1 << 31)) return fail(TLC_E_INVALID, "E must be < 2^31");
   if (up->resolution != 5 || up->descriptor < 0 || up->descriptor > 2 ||
-      (up->flags & (TLC_F_FILT_DEGREE | TLC_F_FILT_CENTRALITY | TLC_F_FILT_CLUSTERING)))
+      (up->flags & TLC_F_FILT_ANY_STRUCT))
     return fail(TLC_E_INVALID, "kernel S serves the Ricci-distance filtrations with a 5 x 5 image");
   CK(cudaSetDevice(g->device));
   Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
@@ -1609,6 +1611,13 @@ int tlc_vicinity_pi_exchange(tlc_graph* g, const int32_t* dev_targets, const int
   g->peer_epoch++;
   launch_peer_wait(reinterpret_cast<const unsigned int*>(g->peer_own), g->peer_epoch * (unsigned int)g->peers.n, g->stream);
   CK(cudaGetLastError());
+  return TLC_OK;
+}
+
+int tlc_graph_set_hks_time(tlc_graph* g, double t) {
+  if (!g) return fail(TLC_E_INVALID, "NULL graph");
+  if (!(t > 0.0 && t <= 50.0)) return fail(TLC_E_INVALID, "hks time must lie in (0, 50]");
+  g->hks_time = t;
   return TLC_OK;
 }
 

@@ -200,6 +200,7 @@ void launch_vicinity_fill(const GraphView& g, const Params& p, const ChunkView& 
                           int* work_counter, cudaStream_t st);
 void launch_filtration(const Params& p, const ChunkView& c, int t0, int cnt, int block, int64_t n_max, cudaStream_t st);
 void launch_degree_filtration(const Params& p, const ChunkView& c, cudaStream_t st);
+void launch_hks_filtration(const Params& p, const ChunkView& c, double t, int64_t n_max, cudaStream_t st);
 // graph-row route: builds the vicinity (bitmap, ranks, vertex list, roots, status) itself and runs the shortest-path
 // phases over the graph's own CSR rows filtered by the bitmap (everything L2-resident, no adjacency in HBM)
 void launch_filtration_direct(const GraphView& g, const Params& p, const ChunkView& c, const VicinityScratch& vs,

@@ -8,7 +8,8 @@ Per node the reference returns the 9-tuple
 or `(None, None)` when the ball has no edge (:103-104).  Here all nodes of a call go through ONE C-ABI call
 (`tlc_vicinity_detail`, node mode, KD flags: zero-persistence pairs kept, division by max + 1e-10, images of
 Ord0 u Ext1 / Ord0 / Ext1).  filt = 'ricci' (the hot path), 'degree', 'centrality' and 'clustering' (:118-128)
-are computed on the GPU; 'hks' (an eigendecomposition) is not.
+and 'hks' (the generators' default; :87-93,115-117, through the Taylor series of the heat kernel instead of an
+eigendecomposition, agreement ~1e-13) are computed on the GPU.
 
 Order conventions: the reference's local vertex numbering and pair order follow networkx's sub-graph view iteration
 (implementation-defined).  This mirror uses the canonical order: local ids ascending by graph id,
@@ -24,7 +25,8 @@ from tlc_b200 import _lib as L
 KD_FLAGS = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
 
 
-_FILT_FLAGS = {"ricci": 0, "degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY, "clustering": L.F_FILT_CLUSTERING}   # data_utils_NC.py:115-142
+_FILT_FLAGS = {"ricci": 0, "degree": L.F_FILT_DEGREE, "centrality": L.F_FILT_CENTRALITY, "clustering": L.F_FILT_CLUSTERING,
+               "hks": L.F_FILT_HKS}   # data_utils_NC.py:115-142 ('hks': set the diffusion time with g2pi._graph.set_hks_time, default 0.1)
 
 
 def compute_persistence_images(g2pi, nodes, hop=2, resolution=5, as_torch=False, filt="ricci", budget=None):

@@ -17,6 +17,7 @@ F_NO_DIRECT, F_DIRECT, F_ASC_ONLY = 64, 128, 256
 F_FILT_DEGREE, F_FILT_CENTRALITY, F_FILT_CLUSTERING = 512, 1024, 2048
 F_NO_SMALL = 4096
 F_NO_TABLE = 8192
+F_FILT_HKS = 16384
 ST_NOT_SMALL = 255
 K_UP, K_ESS, K_DOWN, K_ESS_REV, K_ONE = 0, 1, 2, 3, 4
 ST_OK, ST_TRIVIAL, ST_EMPTY, ST_DISCONNECTED, ST_DEGENERATE, ST_UNKNOWN_NODE, ST_BAD_DESCRIPTOR, ST_NO_TREE_EDGES = range(8)
@@ -27,7 +28,7 @@ EXPORTS = ["tlc_graph_create", "tlc_graph_destroy", "tlc_vicinity_pi", "tlc_vici
            "tlc_launch_count", "tlc_last_stage_ms", "tlc_last_algorithmic_bytes", "tlc_graph_set_stream",
            "tlc_last_counts", "tlc_last_direct", "tlc_pi_gather", "tlc_last_small", "tlc_small_diagrams",
            "tlc_table_create", "tlc_table_attach", "tlc_vicinity_pi_exchange", "tlc_last_table",
-           "tlc_ollivier_ricci"]
+           "tlc_ollivier_ricci", "tlc_graph_set_hks_time"]
 
 
 class Params(C.Structure):
@@ -100,6 +101,8 @@ def lib():
     L.tlc_last_direct.argtypes = [vp]
     L.tlc_ollivier_ricci.restype = C.c_int
     L.tlc_ollivier_ricci.argtypes = [C.c_int, i32, i64, vp, vp, C.c_double, vp, vp]
+    L.tlc_graph_set_hks_time.restype = C.c_int
+    L.tlc_graph_set_hks_time.argtypes = [vp, C.c_double]
     L.tlc_last_table.restype = i64
     L.tlc_last_table.argtypes = [vp]
     L.tlc_last_small.restype = C.c_int

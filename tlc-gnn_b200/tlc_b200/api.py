@@ -206,6 +206,10 @@ class VicinityGraph:
             self._h, _dev_ptr(targets_dev, "int32", (k, 2), self.device, "targets_dev") if k else None,
             _dev_ptr(row_index_dev, "int64", (k,), self.device, "row_index_dev") if k else None, k, C.byref(p), None))
 
+    def set_hks_time(self, t):
+        """diffusion time of the heat-kernel-signature filtration (flag F_FILT_HKS; data_utils_NC: hks_time = 0.1)"""
+        L.check(L.lib().tlc_graph_set_hks_time(self._h, float(t)))
+
     def last_small(self):
         """kernel S in the last call: device ms of its two launches (TLC_STAGE_TIMING=1), rows finished per class, rows
         handed on to the staged pipeline."""
