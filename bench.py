@@ -515,6 +515,7 @@ def run_cuda(args):
     launches = api.launch_count() - launches0
     ks_last = g.last_small()
     table_rows_last = g.last_counts().get("table_route", 0)
+    table_build_ms = g.table_build_ms()
     census = None
     if table_rows_last > 0 and world == 1:
         # kernel 1t does not read all rows, so nobody counted the induced edges of those targets: an exact counting pass
@@ -637,7 +638,7 @@ def run_cuda(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "stage_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()}},
                 "handed_back_per_step": handed_back / args.steps, "kernel_S_last_step": ks_last,
-                "table_route_last_step": table_rows_last, "edge_census": census,
+                "table_route_last_step": table_rows_last, "sssp_table_build_ms_one_time": table_build_ms, "edge_census": census,
                 "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "handoff": handoff, "secondary": secondary}
         sys.stdout.flush()

@@ -70,7 +70,7 @@ extern "C" {
 
 #define TLC_F_NO_TABLE 8192u /* graph-row route: never use the per-root shortest-path tables (kernel 1t), always run kernel 1b's
                                 Dijkstra per target.  Default: on graphs of <= 16384 nodes whose tables fit the budget
-                                (20 N^2 bytes <= TLC_SSSP_CACHE_GB, default 8) the distances, tree parents and path sums of a
+                                (28 N^2 bytes <= TLC_SSSP_CACHE_GB, default 8) the distances, tree parents and path sums of a
                                 root over the WHOLE graph are computed once; a vicinity vertex whose tree branch stays inside
                                 the vicinity takes its values from the table, the others are relaxed over their own rows.
                                 Same results bit for bit */
@@ -270,6 +270,8 @@ int64_t tlc_last_direct(tlc_graph *g);
  * those targets of a BATCH call the induced edges are not counted (no kernel reads all their rows any more): they are
  * missing from tlc_last_counts' sum m and from the 16 m term of tlc_last_algorithmic_bytes; tlc_vicinity_sizes counts them. */
 int64_t tlc_last_table(tlc_graph *g);
+/* device ms the one-time build of the shortest-path tables took (all N roots, at the first graph-row call that uses them) */
+double tlc_table_build_ms(tlc_graph *g);
 /* kernel S in the last call: out[0..2] = device ms of the class A (warp per target, n <= 64) / class B (128-thread CTA,
  * n <= 256) / class C (256-thread CTA, n <= 1024) launch (TLC_STAGE_TIMING=1), out[3..5] = rows they finished,
  * out[6] = rows handed on to the staged pipeline */

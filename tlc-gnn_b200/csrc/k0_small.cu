@@ -133,6 +133,9 @@ struct SmallArgs {
   uint8_t* out_status;      // [E] or nullptr
   int32_t* defer_list;      // rows that do not fit this class
   int* defer_count;
+  int32_t* big_list;        // class A: rows with more than big_thresh vertices (no class takes them), or nullptr
+  int* big_count;
+  int big_thresh;
   int32_t *out_n, *out_m;   // optional [E]: vicinity sizes of the handled targets
   // optional diagram output (tlc_small_diagrams): pairs of row t at poff[t]
   const int64_t* poff;
@@ -318,7 +321,12 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
       if (n > NC) deferred = true;
     }
     if (deferred) {
-      if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)row;
+      // too many vertices for this class: on to the next one -- or, beyond every class (class A sees that at once from
+      // the popcount), straight to the staged pipeline's list, so that it can start while classes B / C still run
+      if (tid == 0) {
+        if (a.big_list && n > a.big_thresh) a.big_list[atomicAdd(a.big_count, 1)] = (int32_t)row;
+        else a.defer_list[atomicAdd(a.defer_count, 1)] = (int32_t)row;
+      }
       continue;
     }
     SPROF(0);
@@ -794,18 +802,19 @@ static void launch_class(const SmallArgs& a, int grid, cudaStream_t st) {
 // class A: a warp per target (n <= 64, <= 256 induced edges); class B: a 128-thread CTA per target (n <= 256, <= 2048 edges);
 // class C: a 256-thread CTA per target (n <= 1024, <= 4096 edges).
 // counters[0] / [1] / [2]: rows deferred from A to B (list_b) / from B to C (list_c) / from C to the staged pipeline (list_b
-// again: class B has consumed it by then); zeroed here.
+// again: class B has consumed it by then); counters[3]: rows class A sends straight to the staged pipeline (list_big: more
+// than 1024 vertices).  phases: 1 = class A (zeroes the counters), 2 = classes B and C.
 void launch_small(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
-                  double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int* counters,
-                  int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count, cudaStream_t st,
-                  cudaEvent_t ev_mid, cudaEvent_t ev_mid2) {
+                  double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int32_t* list_big,
+                  int* counters, int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count,
+                  int phases, cudaStream_t st, cudaEvent_t ev_mid2) {
   SmallArgs a{};
   a.stats = stats; a.ball_acc = vs.ball_acc;
 #ifdef SMALL_PROFILE
   static unsigned long long* d_prof = nullptr;
   if (!d_prof) { cudaMalloc((void**)&d_prof, 48 * 8); cudaMemset(d_prof, 0, 48 * 8); }
   a.prof = d_prof;
-  if (getenv("SMALL_PROFILE_DUMP")) {
+  if (getenv("SMALL_PROFILE_DUMP") && (phases & 1)) {
     unsigned long long h[48];
     cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost);
     static const char* nm[10] = {"vicinity", "adjacency", "filtration", "sort_asc", "sweep_asc", "sort_desc", "sweep_desc", "tree_root", "loops", "image"};
@@ -821,30 +830,34 @@ void launch_small(const GraphView& g, const Params& p, const int32_t* targets, i
     a.poff = diag->poff; a.dnp = diag->np; a.dkind = diag->kind; a.dbv = diag->bv; a.ddv = diag->dv;
     a.dbirth = diag->birth; a.ddeath = diag->death; a.want_desc = 1;
   }
-  cudaMemsetAsync(counters, 0, 3 * sizeof(int), st);
-  if (stats) cudaMemsetAsync(stats, 0, sizeof(SmallStats), st);
-  // class A over every target
-  a.list = nullptr; a.list_count = nullptr; a.defer_list = list_b; a.defer_count = counters;
-  {
+  if (phases & 1) {
+    cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
+    if (stats) cudaMemsetAsync(stats, 0, sizeof(SmallStats), st);
+    // class A over every target
+    a.cls = 0;
+    a.list = nullptr; a.list_count = nullptr; a.defer_list = list_b; a.defer_count = counters;
+    a.big_list = list_big; a.big_count = counters + 3; a.big_thresh = 1024;
     const int64_t want = (E + 3) / 4;
     const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count * 16);
     launch_class<32, 64, 512>(a, std::max(grid, 1), st);
   }
-  if (ev_mid) cudaEventRecord(ev_mid, st);
-  // class B over the rows class A deferred
-  a.cls = 1;
-  a.list = list_b; a.list_count = counters; a.defer_list = list_c; a.defer_count = counters + 1;
-  {
-    const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count * 3);
-    launch_class<128, 256, 4096>(a, std::max(grid, 1), st);
-  }
-  if (ev_mid2) cudaEventRecord(ev_mid2, st);
-  // class C over the rows class B deferred; what it cannot take either goes back into list_b for the staged pipeline
-  a.cls = 2;
-  a.list = list_c; a.list_count = counters + 1; a.defer_list = list_b; a.defer_count = counters + 2;
-  {
-    const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count);
-    launch_class<256, 1024, 8192>(a, std::max(grid, 1), st);
+  if (phases & 2) {
+    a.big_list = nullptr; a.big_count = nullptr; a.big_thresh = 0;
+    // class B over the rows class A deferred
+    a.cls = 1;
+    a.list = list_b; a.list_count = counters; a.defer_list = list_c; a.defer_count = counters + 1;
+    {
+      const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count * 3);
+      launch_class<128, 256, 4096>(a, std::max(grid, 1), st);
+    }
+    if (ev_mid2) cudaEventRecord(ev_mid2, st);
+    // class C over the rows class B deferred; what it cannot take either goes back into list_b for the staged pipeline
+    a.cls = 2;
+    a.list = list_c; a.list_count = counters + 1; a.defer_list = list_b; a.defer_count = counters + 2;
+    {
+      const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count);
+      launch_class<256, 1024, 8192>(a, std::max(grid, 1), st);
+    }
   }
 }
 

@@ -6,6 +6,7 @@
 //     D_r[x] = least fixpoint of d[y] = min_x fl(d[x] + w(x, y)) on G          (what Dijkstra returns, fl(+) monotone)
 //     P_r[x] = smallest id y with fl(D_r[y] + w(y, x)) == D_r[x]               (the tree rule of kernel 1b / the oracle)
 //     Q_r[x] = python-order sum of the weights along x -> P_r[x] -> ... -> r   (:30,35)
+//     W_r[x] = w(x, P_r[x]), the weight of the tree edge (the walks of the vertices below need it term by term)
 // For a vicinity S containing r call x VALID when its whole tree branch x -> ... -> r lies in S.  Then, exactly:
 //   * d_S[x] == D_r[x]: d_S >= D_r (fewer edges), and along the branch d_S[x] <= fl(d_S[p] + w) = fl(D_r[p] + w) = D_r[x];
 //   * the tree parent inside S is P_r[x]: every candidate y in S (fl(d_S[y] + w) == d_S[x]) is a candidate in G as well
@@ -18,7 +19,7 @@
 // suite runs both; TLC_F_NO_TABLE selects kernel 1b).
 //
 // Rows read per target drop from 2 x D_S (every row of the vicinity, once per root) to the rows of the invalid
-// vertices; the table rows of u and v (D, Q, P: 20 N bytes each) are streamed instead.
+// vertices; the table rows of u and v (D, Q, W, P: 28 N bytes each) are streamed instead.
 #include <cstdlib>
 
 #include "tlc_common.cuh"
@@ -84,6 +85,13 @@ __global__ void sssp_mark_kernel(const int32_t* __restrict__ targets, int64_t E,
     if (node_mode && (i & 1)) continue;
     const int32_t x = targets[i];
     if (x < 0 || x >= g.N || g.rowptr[x + 1] == g.rowptr[x]) continue;
+    if (tb.state[x] == 0 && atomicCAS(&tb.state[x], 0, 1) == 0) tb.list[atomicAdd(tb.count, 1)] = x;
+  }
+}
+
+__global__ void sssp_mark_all_kernel(GraphView g, SsspTables tb) {  // every node with an edge whose row does not exist yet
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < g.N; x += gridDim.x * blockDim.x) {
+    if (g.rowptr[x + 1] == g.rowptr[x]) continue;
     if (tb.state[x] == 0 && atomicCAS(&tb.state[x], 0, 1) == 0) tb.list[atomicAdd(tb.count, 1)] = x;
   }
 }
@@ -183,10 +191,12 @@ __global__ void __launch_bounds__(1024) sssp_build_kernel(GraphView g, SsspTable
     double* Drow = tb.D + (size_t)root * N;
     double* Qrow = tb.Q + (size_t)root * N;
     int32_t* Prow = tb.P + (size_t)root * N;
+    double* Wrow = tb.PW + (size_t)root * N;
     for (int x = tid; x < N; x += nt) {
       const unsigned long long dxb = dist[x];
       Drow[x] = __longlong_as_double((long long)dxb);
       Prow[x] = par[x];
+      Wrow[x] = par[x] >= 0 ? pw[x] : 0.0;
       double res;
       if (x == root) res = 0.0;
       else if (dxb == T_INF || par[x] < 0) res = 100.0;
@@ -210,15 +220,11 @@ struct TableShared {
   double redd[32];
   int32_t wsum[33];
   int32_t ninv;     // invalid vertices of the current root
+  int32_t nextra;   // further chunks of their long rows
+  int32_t dinv;     // sum of their graph degrees
   int32_t any;
 };
-
-// weight kappa + 1 of the graph edge (x, y): bisection of x's ascending row
-__device__ __forceinline__ double edge_weight(const GraphView& g, int x, int y) {
-  int lo = g.rowptr[x], hi = g.rowptr[x + 1];
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.col[mid] < y) lo = mid + 1; else hi = mid; }
-  return __dadd_rn(g.kappa[lo], 1.0);
-}
+constexpr int ROW_CHUNK = 128;  // entries of a graph row per work item of the pull relaxation
 
 __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkView c, int t0, int cap, GraphView g,
                                                                 const uint32_t* __restrict__ ball_cache, SsspTables tb, int W) {
@@ -293,6 +299,8 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
   int32_t* hint = c.neg + vo;     // tree parent towards the last root (kernel 2v's "neighbour in an earlier block" hint)
   int32_t* hint0 = c.vcls + vo;   // ... and towards the first root
   int32_t* inv = c.vs0 + vo;      // list of the invalid vertices of the current root
+  int32_t* extra = c.vs1 + vo;    // further row chunks of the long invalid rows: (index in inv[]) << 12 | chunk
+  int32_t* bpos = c.vs2 + vo;     // per vertex: smallest row position of a tree-parent candidate
   double* tpw = reinterpret_cast<double*>(c.v64b + vo);  // weight of an invalid vertex's parent edge
   const bool roots_in = lu >= 0 && lv >= 0;
   const bool plain = (p.flags & TLC_F_SUM_PLAIN) != 0;
@@ -308,10 +316,11 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
       const int32_t groot = r == 0 ? u : v;
       const double* __restrict__ Drow = tb.D + (size_t)groot * N;
       const double* __restrict__ Qrow = tb.Q + (size_t)groot * N;
+      const double* __restrict__ Wrow = tb.PW + (size_t)groot * N;
       const int32_t* __restrict__ Prow = tb.P + (size_t)groot * N;
       double* out = r == 0 ? d1 : d2;
       int32_t* hnt = r == 0 ? hint0 : hint;
-      if (tid == 0) sh.ninv = 0;
+      if (tid == 0) { sh.ninv = 0; sh.nextra = 0; sh.dinv = 0; }
       // ---- 1. classes: the branch of x stays in S <=> its table parent is in S and is valid itself ----
       for (int x = tid; x < n; x += nt) {
         const int32_t gx = vert[x];
@@ -339,6 +348,9 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         if (!__syncthreads_or(ch)) break;
       }
       // ---- 2. the invalid vertices, their distances by pull relaxations over their own graph rows ----
+      // Work items are row CHUNKS: item i < ninv is the first chunk of invalid vertex i, the further chunks of the long
+      // rows (hubs) are listed once per root in extra[] -- a hub's row is then spread over many warps instead of stalling
+      // one.  A chunk's best candidate goes into the vertex's distance with a shared-memory atomic min.
       for (int x0 = 0; x0 < n; x0 += nt) {
         const int x = x0 + tid;
         const bool iv = x < n && cls[x] == INVALID;
@@ -346,56 +358,80 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         int base = 0;
         if (bal && lane == 0) base = atomicAdd(&sh.ninv, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (iv) { inv[base + __popc(bal & lanemask_lt())] = x; dist[x] = T_INF; }
+        if (iv) {
+          const int32_t gx = vert[x];
+          inv[base + __popc(bal & lanemask_lt())] = x;
+          dist[x] = T_INF; bpos[x] = 0x7fffffff;
+          atomicAdd(&sh.dinv, g.rowptr[gx + 1] - g.rowptr[gx]);
+        }
       }
       __syncthreads();
       const int ninv = sh.ninv;
+      int chunk = ROW_CHUNK;
+      while (sh.dinv / chunk > n / 2) chunk *= 2;  // (the extra chunks must fit the n slots of extra[])
+      for (int i = tid; i < ninv; i += nt) {
+        const int32_t gx = vert[inv[i]];
+        const int cnt = (g.rowptr[gx + 1] - g.rowptr[gx] + chunk - 1) / chunk;
+        if (cnt > 1) {
+          const int at = atomicAdd(&sh.nextra, cnt - 1);
+          for (int j = 1; j < cnt; j++) extra[at + j - 1] = (i << 12) | j;
+        }
+      }
+      __syncthreads();
+      const int nextra = sh.nextra;
+      auto relax_chunk = [&](int x, int j) -> bool {  // chunk j of x's graph row; true if the distance improved
+        const int32_t gx = vert[x];
+        const int a = g.rowptr[gx] + j * chunk, b = min(g.rowptr[gx + 1], a + chunk);
+        unsigned long long best = T_INF;
+        for (int e = a + lane; e < b; e += 32) {
+          const int yg = g.col[e];
+          const double w = __dadd_rn(g.kappa[e], 1.0);  // (both loads issue together)
+          const uint16_t ly = lid[yg];
+          if (ly == 0xffff) continue;
+          const unsigned long long dyb = dist[ly];
+          if (dyb == T_INF) continue;
+          const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
+          best = cand < best ? cand : best;
+        }
+        best = shfl_min_u64(best);
+        return lane == 0 && best < dist[x] && best < atomicMin(&dist[x], best);
+      };
       for (int round = 0; round <= ninv; round++) {
         int ch = 0;
-        for (int i = wid; i < ninv; i += nw) {
-          const int x = inv[i];
-          const int32_t gx = vert[x];
-          const int a = g.rowptr[gx], b = g.rowptr[gx + 1];
-          unsigned long long best = T_INF;
-          for (int e = a + lane; e < b; e += 32) {
-            const uint16_t ly = lid[g.col[e]];
-            if (ly == 0xffff) continue;
-            const unsigned long long dyb = dist[ly];
-            if (dyb == T_INF) continue;
-            const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __dadd_rn(g.kappa[e], 1.0)));
-            best = cand < best ? cand : best;
-          }
-          best = shfl_min_u64(best);
-          if (lane == 0 && best < dist[x]) { dist[x] = best; ch = 1; }
-        }
+        for (int i = wid; i < ninv; i += nw) if (relax_chunk(inv[i], 0)) ch = 1;
+        for (int k = wid; k < nextra; k += nw) { const int pk = extra[k]; if (relax_chunk(inv[pk >> 12], pk & 4095)) ch = 1; }
         if (!__syncthreads_or(ch)) break;
       }
-      // ---- 3. tree rule for the invalid vertices: smallest local id y with fl(d[y] + w) == d[x] ----
-      for (int i = wid; i < ninv; i += nw) {
-        const int x = inv[i];
+      // ---- 3. tree rule for the invalid vertices: smallest local id y (= smallest row position) with fl(d[y] + w) == d[x] ----
+      auto parent_chunk = [&](int x, int j) {
         const unsigned long long dxb = dist[x];
-        if (dxb == T_INF) continue;
+        if (dxb == T_INF) return;
         const int32_t gx = vert[x];
-        const int a = g.rowptr[gx], b = g.rowptr[gx + 1];
+        const int a = g.rowptr[gx] + j * chunk, b = min(g.rowptr[gx + 1], a + chunk);
         for (int e0 = a; e0 < b; e0 += 32) {
           const int e = e0 + lane;
           bool hit = false;
-          double w = 0.0;
-          uint16_t ly = 0xffff;
           if (e < b) {
-            ly = lid[g.col[e]];
+            const uint16_t ly = lid[g.col[e]];
             if (ly != 0xffff) {
               const unsigned long long dyb = dist[ly];
-              w = __dadd_rn(g.kappa[e], 1.0);
-              hit = dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w)) == dxb;
+              hit = dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __dadd_rn(g.kappa[e], 1.0))) == dxb;
             }
           }
           const unsigned bal = __ballot_sync(0xffffffffu, hit);
           if (bal) {
-            if (lane == __ffs(bal) - 1) { parl[x] = ly; tpw[x] = w; }
+            if (lane == 0) atomicMin(&bpos[x], e0 + __ffs(bal) - 1);
             break;
           }
         }
+      };
+      for (int i = wid; i < ninv; i += nw) parent_chunk(inv[i], 0);
+      for (int k = wid; k < nextra; k += nw) { const int pk = extra[k]; parent_chunk(inv[pk >> 12], pk & 4095); }
+      __syncthreads();
+      for (int i = tid; i < ninv; i += nt) {
+        const int x = inv[i];
+        const int pos = bpos[x];
+        if (pos != 0x7fffffff) { parl[x] = lid[g.col[pos]]; tpw[x] = __dadd_rn(g.kappa[pos], 1.0); }
       }
       __syncthreads();
       // ---- 4. path sums: the table's for valid vertices, a walk in python order for the others   :30,35 ----
@@ -411,7 +447,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
           int y = x, guard = 0;
           while (y != root && guard++ <= n) {
             const int py = (int)parl[y];
-            const double w = cls[y] == INVALID ? tpw[y] : edge_weight(g, vert[y], vert[py]);
+            const double w = cls[y] == INVALID ? tpw[y] : Wrow[vert[y]];  // (a valid vertex's parent edge is the table's)
             pyt_add(ps, w, plain);
             y = py;
           }
@@ -459,12 +495,18 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
 }  // namespace
 
 // build the table rows of the targets' endpoints that do not exist yet (once per graph and root)
+// targets == nullptr: every node of the graph (the eager build of the first call)
 void launch_sssp_build(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const SsspTables& tb,
                        const float* gminw, double* pw_scratch, int grid, cudaStream_t st) {
-  if (!tb.D || E <= 0) return;
+  if (!tb.D) return;
   cudaMemsetAsync(tb.count, 0, sizeof(int), st);
-  const int mgrid = (int)std::min<int64_t>((2 * E + 255) / 256, 4096);
-  sssp_mark_kernel<<<mgrid, 256, 0, st>>>(targets, E, p.mode == TLC_MODE_NODE ? 1 : 0, g, tb);
+  if (targets) {
+    if (E <= 0) return;
+    const int mgrid = (int)std::min<int64_t>((2 * E + 255) / 256, 4096);
+    sssp_mark_kernel<<<mgrid, 256, 0, st>>>(targets, E, p.mode == TLC_MODE_NODE ? 1 : 0, g, tb);
+  } else {
+    sssp_mark_all_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(g, tb);
+  }
   count_launch();
   const size_t bytes = (size_t)g.N * (8 + 4 + 1) + 16;
   cudaFuncSetAttribute((const void*)sssp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

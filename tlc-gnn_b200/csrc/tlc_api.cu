@@ -108,7 +108,9 @@ struct tlc_graph {
   double alg_bytes = 0, alg_bytes_bfs = 0, alg_bytes_uf = 0;
   bool timing = false;
   // kernel S (fused small-vicinity path): deferral lists, counters + statistics, their pinned host mirror
-  int32_t *sm_list_b = nullptr, *sm_list_c = nullptr;
+  int32_t *sm_list_b = nullptr, *sm_list_c = nullptr, *sm_list_big = nullptr;
+  cudaStream_t small_stream = nullptr;   // classes B / C of kernel S run here while the staged pipeline takes the big targets
+  cudaEvent_t ev_small_a = nullptr, ev_small_bc = nullptr;
   int32_t* sm_sub = nullptr;       // [cap][2] targets handed on to the staged pipeline
   int64_t* sm_idx = nullptr;       // [cap] their rows
   double* sm_pi = nullptr;         // [cap][r2] staged results of those rows, scattered back
@@ -126,7 +128,8 @@ struct tlc_graph {
   SsspTables sssp{};
   double* sssp_pw = nullptr;
   int sssp_plain = -1;
-  bool sssp_tried = false;
+  bool sssp_tried = false, sssp_all = false;
+  double sssp_build_ms = 0;   // device time of the (one-time) table build
   int64_t last_table = 0;  // targets of the last call whose filtration came from the tables
   // multi-GPU exchange by peer stores: this rank's table, the mapped tables of all ranks, exchange epoch
   void* peer_own = nullptr;
@@ -260,8 +263,8 @@ static int ensure_vicinity_scratch(tlc_graph* g, const Params& p) {
   return TLC_OK;
 }
 
-// kernel 1t's tables: three [N][N] arrays, allocated once when the graph is small enough (N <= 16384: the build kernel keeps a
-// root's whole distance / parent vector in shared memory) and 20 N^2 bytes fit TLC_SSSP_CACHE_GB (default 8, 0 disables)
+// kernel 1t's tables: four [N][N] arrays, allocated once when the graph is small enough (N <= 16384: the build kernel keeps a
+// root's whole distance / parent vector in shared memory) and 28 N^2 bytes fit TLC_SSSP_CACHE_GB (default 8, 0 disables)
 static int ensure_sssp_tables(tlc_graph* g, const Params& p) {
   const int plain = (p.flags & TLC_F_SUM_PLAIN) ? 1 : 0;
   if (!g->sssp_tried) {
@@ -269,7 +272,7 @@ static int ensure_sssp_tables(tlc_graph* g, const Params& p) {
     const char* env = getenv("TLC_SSSP_CACHE_GB");
     const double gb = env ? atof(env) : 8.0;
     const size_t N = (size_t)g->gv.N;
-    const size_t need = N * N * 20;
+    const size_t need = N * N * 28;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (gb > 0 && N <= 16384 && (double)need <= gb * (double)(1ull << 30) && need <= free_b / 3 &&
@@ -277,6 +280,7 @@ static int ensure_sssp_tables(tlc_graph* g, const Params& p) {
       CK(cudaMalloc((void**)&g->sssp.D, N * N * 8));
       CK(cudaMalloc((void**)&g->sssp.Q, N * N * 8));
       CK(cudaMalloc((void**)&g->sssp.P, N * N * 4));
+      CK(cudaMalloc((void**)&g->sssp.PW, N * N * 8));
       CK(cudaMalloc((void**)&g->sssp.state, N * 4));
       CK(cudaMalloc((void**)&g->sssp.list, N * 4));
       CK(cudaMalloc((void**)&g->sssp.count, 64));
@@ -285,9 +289,10 @@ static int ensure_sssp_tables(tlc_graph* g, const Params& p) {
       g->sssp_plain = plain;
     }
   }
-  if (g->sssp.D && g->sssp_plain != plain) {  // the path sums depend on the summation rule: rebuild on demand
+  if (g->sssp.D && g->sssp_plain != plain) {  // the path sums depend on the summation rule: rebuild
     CK(cudaMemsetAsync(g->sssp.state, 0, (size_t)g->gv.N * 4, g->stream));
     g->sssp_plain = plain;
+    g->sssp_all = false;
   }
   return TLC_OK;
 }
@@ -567,7 +572,21 @@ static int run_staged(tlc_graph* g, const int32_t* d_targets, int64_t E, const t
     if ((rc = ensure_sssp_tables(g, p))) return rc;
     if (g->sssp.D) {
       use_table = true;
-      launch_sssp_build(g->gv, p, d_targets, E, g->sssp, g->gminw, g->sssp_pw, g->sm_count, st);
+      if (!g->sssp_all) {
+        // the rows of ALL roots, once per graph (and summation rule): a full pass over a dataset touches every node anyway,
+        // and a handful of late rows would cost a whole single-CTA shortest-path run in the middle of a step
+        cudaEvent_t b0 = nullptr, b1 = nullptr;
+        cudaEventCreate(&b0); cudaEventCreate(&b1);
+        cudaEventRecord(b0, st);
+        launch_sssp_build(g->gv, p, nullptr, 0, g->sssp, g->gminw, g->sssp_pw, g->sm_count, st);
+        cudaEventRecord(b1, st);
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, b0, b1);
+        g->sssp_build_ms = ms;
+        cudaEventDestroy(b0); cudaEventDestroy(b1);
+        g->sssp_all = true;
+      }
     }
   }
   if (light)
@@ -867,14 +886,19 @@ static int ensure_small_buffers(tlc_graph* g, int64_t E) {
   if (!g->sm_dev) {
     CK(cudaMalloc((void**)&g->sm_dev, 256));
     CK(cudaMallocHost((void**)&g->sm_host, 256));
+    CK(cudaEventCreateWithFlags(&g->ev_small_a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g->ev_small_bc, cudaEventDisableTiming));
+    if (!getenv("TLC_NO_SIDE_STREAMS")) CK(cudaStreamCreateWithFlags(&g->small_stream, cudaStreamNonBlocking));
   }
   if (E <= g->sm_cap) return TLC_OK;
   if (g->sm_list_b) cudaFree(g->sm_list_b);
   if (g->sm_list_c) cudaFree(g->sm_list_c);
-  g->sm_list_b = g->sm_list_c = nullptr; g->sm_cap = 0;
+  if (g->sm_list_big) cudaFree(g->sm_list_big);
+  g->sm_list_b = g->sm_list_c = g->sm_list_big = nullptr; g->sm_cap = 0;
   const int64_t cap = E + E / 8 + 1024;
   CK(cudaMalloc((void**)&g->sm_list_b, (size_t)cap * 4));
   CK(cudaMalloc((void**)&g->sm_list_c, (size_t)cap * 4));
+  CK(cudaMalloc((void**)&g->sm_list_big, (size_t)cap * 4));
   g->sm_cap = cap;
   return TLC_OK;
 }
@@ -906,13 +930,51 @@ static bool small_applicable(const tlc_graph* g, const tlc_params* up, int64_t E
   return true;
 }
 
-// kernel S over the whole call, then the staged pipeline over the rows it handed on
+// statistics of a staged sub-call, accumulated across the (up to two) sub-calls of a kernel S call
+struct StagedAcc {
+  double ms[10] = {0};
+  int64_t live = 0, nv = 0, ne = 0, fb = 0, general = 0, rowcheck = 0, blocks = 0, direct = 0, table = 0;
+  int chunks = 0;
+  double bytes = 0;
+  void add(const tlc_graph* g) {
+    for (int i = 0; i < 10; i++) ms[i] += g->stage_ms[i];
+    live += g->last_live; nv += g->last_nv; ne += g->last_ne; fb += g->last_fb; general += g->last_general;
+    rowcheck += g->last_rowcheck; blocks += g->last_blocks; direct += g->last_direct; table += g->last_table;
+    chunks += g->nchunks; bytes += g->alg_bytes;
+  }
+};
+
+// the staged pipeline over a device-side list of rows, results scattered back into the caller's tables
+static int run_staged_list(tlc_graph* g, const int32_t* d_targets, const int32_t* d_list, int64_t k, const tlc_params* up,
+                           double* d_pi, float* d_pi32, uint8_t* d_status, StageTimer& tm, StagedAcc& acc) {
+  const int r2 = up->resolution * up->resolution;
+  cudaStream_t st = g->stream;
+  int rc;
+  if ((rc = ensure_small_sub(g, k, r2))) return rc;
+  launch_gather_targets(d_targets, d_list, k, g->sm_sub, g->sm_idx, st);
+  tlc_params up2 = *up;
+  up2.flags |= TLC_F_NO_SMALL;
+  const size_t keep_base = g->ev_base;
+  g->ev_base = tm.used;  // the nested call's stage events live behind this call's
+  rc = run_staged(g, g->sm_sub, k, &up2, g->sm_pi, g->sm_pi32, g->sm_st, nullptr, nullptr);
+  g->ev_base = keep_base;
+  if (rc) return rc;
+  launch_scatter_rows(g->sm_pi, d_pi32 ? g->sm_pi32 : nullptr, d_status ? g->sm_st : nullptr, g->sm_idx, k, r2, d_pi, d_pi32,
+                      d_status, g->sm_count, st);
+  CK(cudaStreamSynchronize(st));
+  acc.add(g);
+  return TLC_OK;
+}
+
+// kernel S over the whole call, the staged pipeline over the rows it hands on.  Class A (a warp per target) sees every
+// target and sorts the rest into "classes B / C" and "more than 1024 vertices: staged"; classes B and C then run on a
+// stream of their own WHILE the staged pipeline takes the big targets (whose single-lane sweeps are the critical path of
+// extended calls); what class C cannot take either (<= 1024 vertices but more than 4096 edges) follows at the end.
 static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tlc_params* up, double* d_pi, float* d_pi32,
                      uint8_t* d_status, int64_t* cnt_compute, bool* fell_through) {
   *fell_through = false;
   CK(cudaSetDevice(g->device));
   Params p{up->hop, up->mode, up->descriptor, up->resolution, up->flags, up->img_mask};
-  const int r2 = p.resolution * p.resolution;
   cudaStream_t st = g->stream;
   int rc;
   if ((rc = ensure_call_buffers(g, E))) return rc;
@@ -924,56 +986,61 @@ static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tl
   const char* tenv = getenv("TLC_STAGE_TIMING");
   g->timing = tenv && atoi(tenv) != 0;
   StageTimer tm(g->timing, st, &g->ev_pool, g->ev_base);
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev1b = nullptr, ev2 = nullptr;
-  if (g->timing) { ev0 = tm.take(); ev1 = tm.take(); ev1b = tm.take(); ev2 = tm.take(); }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb0 = nullptr, ev1b = nullptr, ev2 = nullptr;
+  if (g->timing) { ev0 = tm.take(); ev1 = tm.take(); evb0 = tm.take(); ev1b = tm.take(); ev2 = tm.take(); }
   VicinityScratch vs = make_vs(g);
   int* counters = reinterpret_cast<int*>(g->sm_dev);
   SmallStats* d_stats = reinterpret_cast<SmallStats*>(g->sm_dev + SM_STATS_OFF);
   launch_ball_cache(g->gv, p, d_targets, E, vs, st);
   if (ev0) cudaEventRecord(ev0, st);
-  launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, counters, nullptr, nullptr,
-               nullptr, d_stats, g->sm_count, st, ev1, ev1b);
-  if (ev2) cudaEventRecord(ev2, st);
+  launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, g->sm_list_big, counters,
+               nullptr, nullptr, nullptr, d_stats, g->sm_count, 1, st, nullptr);
+  if (ev1) cudaEventRecord(ev1, st);
+  CK(cudaEventRecord(g->ev_small_a, st));
+  CK(cudaMemcpyAsync(g->sm_host, g->sm_dev, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int nB = reinterpret_cast<const int*>(g->sm_host)[0], nBig = reinterpret_cast<const int*>(g->sm_host)[3];
+  if (nBig == E) {  // nothing for kernel S: the staged pipeline takes the whole call, and the next calls do not try again
+    g->small_skip = 32;
+    *fell_through = true;
+    return TLC_OK;
+  }
+  // classes B and C on their own stream, behind class A
+  cudaStream_t sb = g->small_stream ? g->small_stream : st;
+  if (nB > 0) {
+    if (sb != st) CK(cudaStreamWaitEvent(sb, g->ev_small_a, 0));
+    if (evb0) cudaEventRecord(evb0, sb);
+    launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, g->sm_list_big, counters,
+                 nullptr, nullptr, nullptr, d_stats, g->sm_count, 2, sb, ev1b);
+    if (ev2) cudaEventRecord(ev2, sb);
+    if (sb != st) CK(cudaEventRecord(g->ev_small_bc, sb));
+  }
+  StagedAcc acc;
+  if (nBig > 0 && (rc = run_staged_list(g, d_targets, g->sm_list_big, nBig, up, d_pi, d_pi32, d_status, tm, acc))) return rc;
+  if (nB > 0 && sb != st) CK(cudaStreamWaitEvent(st, g->ev_small_bc, 0));
   CK(cudaMemcpyAsync(g->sm_host, g->sm_dev, SM_STATS_OFF + sizeof(SmallStats), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const int nC = reinterpret_cast<const int*>(g->sm_host)[2];  // rows no class could take (listed in sm_list_b)
+  const int nC = nB > 0 ? reinterpret_cast<const int*>(g->sm_host)[2] : 0;  // rows class C could not take (listed in sm_list_b)
   const SmallStats hs = *reinterpret_cast<const SmallStats*>(g->sm_host + SM_STATS_OFF);
   float msA = 0, msB = 0, msC = 0;
-  if (g->timing) { cudaEventElapsedTime(&msA, ev0, ev1); cudaEventElapsedTime(&msB, ev1, ev1b); cudaEventElapsedTime(&msC, ev1b, ev2); }
+  if (g->timing) {
+    cudaEventElapsedTime(&msA, ev0, ev1);
+    if (nB > 0) { cudaEventElapsedTime(&msB, evb0, ev1b); cudaEventElapsedTime(&msC, ev1b, ev2); }
+  }
+  if (nC > 0 && (rc = run_staged_list(g, d_targets, g->sm_list_b, nC, up, d_pi, d_pi32, d_status, tm, acc))) return rc;
   // a call whose vicinities are mostly too large: do not try again for a while (the size check alone costs a pass over
   // two ball bitmaps per target)
-  if ((int64_t)nC * 4 > E * 3) g->small_skip = 32;
-  if (nC == E) { *fell_through = true; return TLC_OK; }  // nothing handled: the staged pipeline takes the whole call
-  double o_ms[10] = {0};
-  int64_t s_live = 0, s_nv = 0, s_ne = 0, s_fb = 0, s_general = 0, s_rowcheck = 0, s_blocks = 0, s_direct = 0;
-  int s_chunks = 0;
-  double s_bytes = 0;
-  if (nC > 0) {
-    if ((rc = ensure_small_sub(g, nC, r2))) return rc;
-    launch_gather_targets(d_targets, g->sm_list_b, nC, g->sm_sub, g->sm_idx, st);
-    tlc_params up2 = *up;
-    up2.flags |= TLC_F_NO_SMALL;
-    const size_t keep_base = g->ev_base;
-    g->ev_base = tm.used;
-    rc = run_staged(g, g->sm_sub, nC, &up2, g->sm_pi, g->sm_pi32, g->sm_st, nullptr, nullptr);
-    g->ev_base = keep_base;
-    if (rc) return rc;
-    launch_scatter_rows(g->sm_pi, d_pi32 ? g->sm_pi32 : nullptr, d_status ? g->sm_st : nullptr, g->sm_idx, nC, r2, d_pi, d_pi32,
-                        d_status, g->sm_count, st);
-    CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < 10; i++) o_ms[i] = g->stage_ms[i];
-    s_live = g->last_live; s_nv = g->last_nv; s_ne = g->last_ne; s_fb = g->last_fb; s_general = g->last_general;
-    s_rowcheck = g->last_rowcheck; s_blocks = g->last_blocks; s_direct = g->last_direct; s_chunks = g->nchunks; s_bytes = g->alg_bytes;
-  }
-  for (int i = 0; i < 10; i++) g->stage_ms[i] = o_ms[i];
+  if (((int64_t)nC + nBig) * 4 > E * 3) g->small_skip = 32;
+  for (int i = 0; i < 10; i++) g->stage_ms[i] = acc.ms[i];
   g->stage_ms[9] += msA + msB + msC;
   g->small_ms[0] = msA; g->small_ms[1] = msB; g->small_ms[2] = msC;
   g->small_rows[0] = (int64_t)hs.handled[0]; g->small_rows[1] = (int64_t)hs.handled[1]; g->small_rows[2] = (int64_t)hs.handled[2];
-  g->small_rows[3] = nC;
-  g->last_live = s_live + (int64_t)hs.live; g->last_nv = s_nv + (int64_t)hs.sum_n; g->last_ne = s_ne + (int64_t)hs.sum_m;
-  g->last_fb = s_fb; g->last_general = s_general; g->last_rowcheck = s_rowcheck; g->last_blocks = s_blocks; g->last_direct = s_direct;
-  g->nchunks = s_chunks;
-  g->alg_bytes = s_bytes + hs.bytes;
+  g->small_rows[3] = (int64_t)nC + nBig;
+  g->last_live = acc.live + (int64_t)hs.live; g->last_nv = acc.nv + (int64_t)hs.sum_n; g->last_ne = acc.ne + (int64_t)hs.sum_m;
+  g->last_fb = acc.fb; g->last_general = acc.general; g->last_rowcheck = acc.rowcheck; g->last_blocks = acc.blocks;
+  g->last_direct = acc.direct; g->last_table = acc.table;
+  g->nchunks = acc.chunks;
+  g->alg_bytes = acc.bytes + hs.bytes;
   if (cnt_compute) {
     *cnt_compute = 0;
     if (d_status) {
@@ -1129,10 +1196,14 @@ int tlc_graph_destroy(tlc_graph* g) {
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   for (int i = 0; i < 3; i++) { if (g->side[i]) cudaStreamDestroy(g->side[i]); if (g->ev_join[i]) cudaEventDestroy(g->ev_join[i]); }
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->small_stream) cudaStreamDestroy(g->small_stream);
+  if (g->ev_small_a) cudaEventDestroy(g->ev_small_a);
+  if (g->ev_small_bc) cudaEventDestroy(g->ev_small_bc);
+  cudaFree(g->sm_list_big);
   cudaFree(g->sm_list_b); cudaFree(g->sm_list_c); cudaFree(g->sm_sub); cudaFree(g->sm_idx); cudaFree(g->sm_pi);
   cudaFree(g->sm_pi32); cudaFree(g->sm_st); cudaFree(g->sm_dev);
   if (g->sm_host) cudaFreeHost(g->sm_host);
-  cudaFree(g->sssp.D); cudaFree(g->sssp.Q); cudaFree(g->sssp.P); cudaFree(g->sssp.state); cudaFree(g->sssp.list);
+  cudaFree(g->sssp.D); cudaFree(g->sssp.Q); cudaFree(g->sssp.P); cudaFree(g->sssp.PW); cudaFree(g->sssp.state); cudaFree(g->sssp.list);
   cudaFree(g->sssp.count); cudaFree(g->sssp_pw);
   for (void* q : g->peer_opened) cudaIpcCloseMemHandle(q);
   cudaFree(g->peer_own); cudaFree(g->peer_ticket); cudaFree(g->px_pi32); cudaFree(g->px_pi); cudaFree(g->px_st);
@@ -1279,8 +1350,8 @@ int tlc_small_diagrams(tlc_graph* g, const int32_t* targets, int64_t E, const tl
                b_birth.as<double>(), b_death.as<double>()};
   VicinityScratch vs = make_vs(g);
   launch_ball_cache(g->gv, p, g->io_t, E, vs, st);
-  launch_small(g->gv, p, g->io_t, E, vs, g->io_pi, nullptr, g->io_st, g->sm_list_b, g->sm_list_c,
-               reinterpret_cast<int*>(g->sm_dev), g->d_n, g->d_m, &dg, nullptr, g->sm_count, st, nullptr, nullptr);
+  launch_small(g->gv, p, g->io_t, E, vs, g->io_pi, nullptr, g->io_st, g->sm_list_b, g->sm_list_c, g->sm_list_big,
+               reinterpret_cast<int*>(g->sm_dev), g->d_n, g->d_m, &dg, nullptr, g->sm_count, 3, st, nullptr);
   std::vector<uint8_t> k8((size_t)P + 1);
   if (npairs) CK(cudaMemcpyAsync(npairs, b_np.p, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
   if (P > 0) {
@@ -1637,6 +1708,7 @@ int tlc_last_counts(tlc_graph* g, int64_t* out5) {  // out5: 8 slots
 int64_t tlc_last_direct(tlc_graph* g) { return g ? g->last_direct : 0; }
 
 int64_t tlc_last_table(tlc_graph* g) { return g ? g->last_table : 0; }
+double tlc_table_build_ms(tlc_graph* g) { return g ? g->sssp_build_ms : 0.0; }
 
 int tlc_last_small(tlc_graph* g, double* out7) {
   if (!g || !out7) return TLC_E_INVALID;

@@ -229,6 +229,7 @@ struct SsspTables {
   double* D;       // fl-distance from the root (bit pattern of the Dijkstra fixpoint), +inf where unreachable
   double* Q;       // python-order path sum x -> root (100 where unreachable)
   int32_t* P;      // tree parent (graph id), -1 for the root / unreachable
+  double* PW;      // weight kappa + 1 of the tree edge (x, P[x])
   int32_t* state;  // [N] 0 row not built, 1 claimed in this call, 2 built
   int32_t* list;   // [N] roots to build in this call
   int* count;
@@ -261,9 +262,9 @@ struct SmallStats {  // device accumulators of one call
   double bytes;                   // their compulsory bytes B_e
 };
 void launch_small(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
-                  double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int* counters,
-                  int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count, cudaStream_t st,
-                  cudaEvent_t ev_mid, cudaEvent_t ev_mid2);
+                  double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int32_t* list_big,
+                  int* counters, int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count,
+                  int phases, cudaStream_t st, cudaEvent_t ev_mid2);
 // rows of a sub-list: sub[i] = targets[list[i]], idx[i] = list[i]
 void launch_gather_targets(const int32_t* targets, const int32_t* list, int64_t k, int32_t* sub, int64_t* idx, cudaStream_t st);
 

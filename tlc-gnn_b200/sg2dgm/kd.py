@@ -111,6 +111,8 @@ def compute_persistence_image(g2pi, u, v=None, filt="ricci", hks_time=0.1, hop=2
     argument is the graph2pi object that holds graph and curvature."""
     if mode != "PI":
         raise NotImplementedError("only mode='PI' is on the GPU path")
+    if filt == "hks":
+        g2pi._graph.set_hks_time(hks_time)
     if v is None:
         return compute_persistence_images(g2pi, [u], hop=hop, filt=filt)[0]
     return compute_persistence_images_lp(g2pi, [(u, v)], hop=hop, filt=filt)[0]

@@ -28,7 +28,7 @@ EXPORTS = ["tlc_graph_create", "tlc_graph_destroy", "tlc_vicinity_pi", "tlc_vici
            "tlc_launch_count", "tlc_last_stage_ms", "tlc_last_algorithmic_bytes", "tlc_graph_set_stream",
            "tlc_last_counts", "tlc_last_direct", "tlc_pi_gather", "tlc_last_small", "tlc_small_diagrams",
            "tlc_table_create", "tlc_table_attach", "tlc_vicinity_pi_exchange", "tlc_last_table",
-           "tlc_ollivier_ricci", "tlc_graph_set_hks_time"]
+           "tlc_ollivier_ricci", "tlc_graph_set_hks_time", "tlc_table_build_ms"]
 
 
 class Params(C.Structure):
@@ -103,6 +103,8 @@ def lib():
     L.tlc_ollivier_ricci.argtypes = [C.c_int, i32, i64, vp, vp, C.c_double, vp, vp]
     L.tlc_graph_set_hks_time.restype = C.c_int
     L.tlc_graph_set_hks_time.argtypes = [vp, C.c_double]
+    L.tlc_table_build_ms.restype = C.c_double
+    L.tlc_table_build_ms.argtypes = [vp]
     L.tlc_last_table.restype = i64
     L.tlc_last_table.argtypes = [vp]
     L.tlc_last_small.restype = C.c_int

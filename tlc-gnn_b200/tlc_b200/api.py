@@ -210,6 +210,10 @@ class VicinityGraph:
         """diffusion time of the heat-kernel-signature filtration (flag F_FILT_HKS; data_utils_NC: hks_time = 0.1)"""
         L.check(L.lib().tlc_graph_set_hks_time(self._h, float(t)))
 
+    def table_build_ms(self):
+        """device ms of the one-time build of the per-root shortest-path tables (kernel 1t), 0 if they are not in use"""
+        return float(L.lib().tlc_table_build_ms(self._h))
+
     def last_small(self):
         """kernel S in the last call: device ms of its two launches (TLC_STAGE_TIMING=1), rows finished per class, rows
         handed on to the staged pipeline."""
