@@ -26,17 +26,35 @@ from tlc_b200.table import PITable  # noqa: E402
 
 
 def main():
-    small = len(sys.argv) > 1 and sys.argv[1] == "small"   # smaller batches (sanitizer runs)
+    small = "small" in sys.argv[1:]                         # smaller batches (sanitizer runs)
+    only = [a[5:].split(",") for a in sys.argv[1:] if a.startswith("only=")]   # only=computers,pubmed,cora,ricci,gather
+    want = lambda sec: not only or sec in only[0]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     # ---- Computers-shaped ----
+    if want("computers"):
+        section_computers(small, dev)
+    if want("pubmed"):
+        section_pubmed(small)
+    if want("cora"):
+        section_cora(small)
+    if want("ricci"):
+        section_ricci(small)
+    if want("gather"):
+        section_gather(dev)
+    print("all kernels launched: %d launches" % api.launch_count())
+
+
+def section_computers(small, dev):
     c, labels, ne, csr, perm = bench.make_workload("computers")
     g = api.VicinityGraph(*csr, device=0)
     B = 64 if small else 512
     for s in range(2):
         tg = bench.batch_targets(ne, perm, s, 0, 1, B)
         g.vicinity_pi(tg, hop=2, flags=L.F_NORM)                               # graph-row route
-    tg = bench.batch_targets(ne, perm, 7, 0, 1, 16 if small else 96)
+    tg = bench.batch_targets(ne, perm, 3, 0, 1, B)
+    g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_NO_TABLE)                    # phased Dijkstra (kernel 1b) instead of the SSSP tables
+    tg = bench.batch_targets(ne, perm, 7, 0, 1, 16 if small else 32)
     g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_EXTENDED)                    # materialised route + loops (CTA per vicinity)
     g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_EDGE_SORTED | L.F_NO_DIRECT)  # edge-sorted ascending sweep
     tg = bench.batch_targets(ne, perm, 9, 0, 1, 512 if small else 4096)
@@ -49,7 +67,9 @@ def main():
     g.vicinity_pi_exchange(t_dev, rows, hop=1, flags=L.F_NORM)
     torch.cuda.synchronize()
     g.close()
-    # ---- PubMed-shaped ----
+
+
+def section_pubmed(small):
     c, labels, ne, csr, perm = bench.make_workload("pubmed")
     g = api.VicinityGraph(*csr, device=0)
     B = 1024 if small else 8192
@@ -62,22 +82,44 @@ def main():
     kd = L.F_NORM | L.F_EXTENDED | L.F_KEEP_ZERO | L.F_NORM_EPS
     g.vicinity_pi(nodes, hop=2, mode=L.MODE_NODE, flags=kd | L.F_FILT_DEGREE)       # PDGNN structural filtrations
     g.vicinity_pi(nodes, hop=2, mode=L.MODE_NODE, flags=kd | L.F_FILT_CLUSTERING)
+    g.set_hks_time(0.1)
+    g.vicinity_pi(nodes, hop=2, mode=L.MODE_NODE, flags=kd | L.F_FILT_HKS)            # heat kernel signature
+    tg = bench.batch_targets(ne, perm, 5, 0, 1, 256 if small else 2048)
+    g.vicinity_pi(tg, hop=1, mode=L.MODE_EDGE_UNION, flags=L.F_NORM | L.F_EXTENDED)   # legacy vicinity shapes
+    g.vicinity_pi(tg, hop=1, mode=L.MODE_EDGE_REMOVEINTER, flags=L.F_NORM | L.F_EXTENDED)
     g.close()
-    # ---- Cora-shaped, hop-distance filtration: hundreds of exact ties -> kernel 3v hands targets back (redo + scatter) ----
+
+
+def section_ricci(small):
+    """Ollivier-Ricci curvature of every edge (kernel 6)"""
+    n_r = 600 if small else 3000
+    rng = np.random.default_rng(5)
+    from tlc_b200.graphgen import build_csr
+    e = rng.integers(0, n_r, size=(4 * n_r, 2))
+    e = e[e[:, 0] != e[:, 1]]
+    key = np.unique(np.minimum(e[:, 0], e[:, 1]) * n_r + np.maximum(e[:, 0], e[:, 1]))
+    rp, cl, _ = build_csr(n_r, np.stack([key // n_r, key % n_r], 1), np.zeros(len(key)))
+    api.ollivier_ricci(rp, cl, device=0)
+
+
+def section_cora(small):
+    """Cora-shaped, hop-distance filtration: hundreds of exact ties -> kernel 3v hands targets back (redo + scatter)"""
     c, labels, ne, csr, perm = bench.make_workload("cora")
     g = api.VicinityGraph(*csr, device=0)
     tg = bench.batch_targets(ne, perm, 0, 0, 1, 256 if small else 2048)
     g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_DIRECT)
     g.vicinity_pi(tg, hop=3, flags=L.F_NORM)
     g.close()
-    # ---- decoder hand-off ----
+
+
+def section_gather(dev):
+    """decoder hand-off"""
     E = 100000
     table = PITable(torch.rand((E, 25), dtype=torch.float64, device=dev), splits=[60000, 30000, 2500, 2500, 2500, 2500])
     idx = torch.randint(0, E, (50000,), device=dev)
     out = torch.empty((50000, 25), dtype=torch.float32, device=dev)
     table.gather(index=idx, out=out)
     torch.cuda.synchronize()
-    print("all kernels launched: %d launches" % api.launch_count())
 
 
 if __name__ == "__main__":

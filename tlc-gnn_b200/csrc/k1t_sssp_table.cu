@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
   int32_t* hint = c.neg + vo;     // tree parent towards the last root (kernel 2v's "neighbour in an earlier block" hint)
   int32_t* hint0 = c.vcls + vo;   // ... and towards the first root
   int32_t* inv = c.vs0 + vo;      // list of the invalid vertices of the current root
-  int32_t* extra = c.vs1 + vo;    // further row chunks of the long invalid rows: (index in inv[]) << 12 | chunk
+  int32_t* extra = c.vs1 + vo;    // further row chunks of the long invalid rows: local vertex id << 12 | chunk
   int32_t* bpos = c.vs2 + vo;     // per vertex: smallest row position of a tree-parent candidate
   double* tpw = reinterpret_cast<double*>(c.v64b + vo);  // weight of an invalid vertex's parent edge
   const bool roots_in = lu >= 0 && lv >= 0;
@@ -374,59 +374,99 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         const int cnt = (g.rowptr[gx + 1] - g.rowptr[gx] + chunk - 1) / chunk;
         if (cnt > 1) {
           const int at = atomicAdd(&sh.nextra, cnt - 1);
-          for (int j = 1; j < cnt; j++) extra[at + j - 1] = (i << 12) | j;
+          for (int j = 1; j < cnt; j++) extra[at + j - 1] = (inv[i] << 12) | j;
         }
       }
       __syncthreads();
-      const int nextra = sh.nextra;
-      auto relax_chunk = [&](int x, int j) -> bool {  // chunk j of x's graph row; true if the distance improved
-        const int32_t gx = vert[x];
-        const int a = g.rowptr[gx] + j * chunk, b = min(g.rowptr[gx + 1], a + chunk);
-        unsigned long long best = T_INF;
-        for (int e = a + lane; e < b; e += 32) {
-          const int yg = g.col[e];
-          const double w = __dadd_rn(g.kappa[e], 1.0);  // (both loads issue together)
-          const uint16_t ly = lid[yg];
+      const int nextra = sh.nextra, nitems = ninv + nextra;
+      // A warp takes items wid, wid + nw, ...: 32 of them at a time, their row bounds fetched lane-parallel, and the first
+      // 128 records of item q + 1 are in flight while item q is reduced (the chain vertex -> row bounds -> records ->
+      // distance would otherwise cost three dependent HBM/L2 latencies per item).
+      auto item_bounds = [&](int i, int& x, int& a, int& b) {
+        x = -1; a = 0; b = 0;
+        if (i < nitems) {
+          const int pk = i < ninv ? (inv[i] << 12) : extra[i - ninv];
+          x = pk >> 12;
+          const int ra = c.astart[vo + x];
+          a = ra + (pk & 4095) * chunk;
+          b = min(ra + c.adeg[vo + x], a + chunk);
+        }
+      };
+      auto load4 = [&](int a, int b, uint4 (&rc)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = a + q * 32 + lane;
+          rc[q] = e < b ? __ldg(g.rec + e) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+        }
+      };
+      auto fold4 = [&](const uint4 (&rc)[4], unsigned long long best) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (rc[q].x == 0xffffffffu) continue;
+          const uint16_t ly = lid[rc[q].x];
           if (ly == 0xffff) continue;
           const unsigned long long dyb = dist[ly];
           if (dyb == T_INF) continue;
+          const double w = __hiloint2double((int)rc[q].w, (int)rc[q].z);
           const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
           best = cand < best ? cand : best;
         }
-        best = shfl_min_u64(best);
-        return lane == 0 && best < dist[x] && best < atomicMin(&dist[x], best);
+        return best;
       };
       for (int round = 0; round <= ninv; round++) {
         int ch = 0;
-        for (int i = wid; i < ninv; i += nw) if (relax_chunk(inv[i], 0)) ch = 1;
-        for (int k = wid; k < nextra; k += nw) { const int pk = extra[k]; if (relax_chunk(inv[pk >> 12], pk & 4095)) ch = 1; }
+        for (int k0 = 0; wid + k0 * nw < nitems; k0 += 32) {
+          int mx, ma, mb;
+          item_bounds(wid + (k0 + lane) * nw, mx, ma, mb);
+          const int cnt = min(32, (nitems - wid - k0 * nw + nw - 1) / nw);
+          uint4 cur[4], nxt[4];
+          load4(__shfl_sync(0xffffffffu, ma, 0), __shfl_sync(0xffffffffu, mb, 0), cur);
+          for (int q = 0; q < cnt; q++) {
+            const int x = __shfl_sync(0xffffffffu, mx, q), a = __shfl_sync(0xffffffffu, ma, q), b = __shfl_sync(0xffffffffu, mb, q);
+            const int qn = min(q + 1, 31);
+            const int an = __shfl_sync(0xffffffffu, ma, qn), bn = __shfl_sync(0xffffffffu, mb, qn);
+            if (q + 1 < cnt) load4(an, bn, nxt);
+            unsigned long long best = fold4(cur, T_INF);
+            for (int e0 = a + 128; e0 < b; e0 += 128) {  // (only when the chunk was widened beyond 128 records)
+              load4(e0, b, cur);
+              best = fold4(cur, best);
+            }
+            best = shfl_min_u64(best);
+            if (lane == 0 && best < dist[x] && best < atomicMin(&dist[x], best)) ch = 1;
+#pragma unroll
+            for (int z = 0; z < 4; z++) cur[z] = nxt[z];
+          }
+        }
         if (!__syncthreads_or(ch)) break;
       }
       // ---- 3. tree rule for the invalid vertices: smallest local id y (= smallest row position) with fl(d[y] + w) == d[x] ----
-      auto parent_chunk = [&](int x, int j) {
-        const unsigned long long dxb = dist[x];
-        if (dxb == T_INF) return;
-        const int32_t gx = vert[x];
-        const int a = g.rowptr[gx] + j * chunk, b = min(g.rowptr[gx + 1], a + chunk);
-        for (int e0 = a; e0 < b; e0 += 32) {
-          const int e = e0 + lane;
-          bool hit = false;
-          if (e < b) {
-            const uint16_t ly = lid[g.col[e]];
-            if (ly != 0xffff) {
-              const unsigned long long dyb = dist[ly];
-              hit = dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __dadd_rn(g.kappa[e], 1.0))) == dxb;
+      for (int k0 = 0; wid + k0 * nw < nitems; k0 += 32) {
+        int mx, ma, mb;
+        item_bounds(wid + (k0 + lane) * nw, mx, ma, mb);
+        const int cnt = min(32, (nitems - wid - k0 * nw + nw - 1) / nw);
+        for (int q = 0; q < cnt; q++) {
+          const int x = __shfl_sync(0xffffffffu, mx, q), a = __shfl_sync(0xffffffffu, ma, q), b = __shfl_sync(0xffffffffu, mb, q);
+          const unsigned long long dxb = dist[x];
+          if (dxb == T_INF) continue;
+          for (int e0 = a; e0 < b; e0 += 32) {
+            const int e = e0 + lane;
+            bool hit = false;
+            if (e < b) {
+              const uint4 rc = __ldg(g.rec + e);
+              const uint16_t ly = lid[rc.x];
+              if (ly != 0xffff) {
+                const unsigned long long dyb = dist[ly];
+                hit = dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __hiloint2double((int)rc.w, (int)rc.z))) == dxb;
+              }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {
+              if (lane == 0) atomicMin(&bpos[x], e0 + __ffs(bal) - 1);
+              break;
             }
           }
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (bal) {
-            if (lane == 0) atomicMin(&bpos[x], e0 + __ffs(bal) - 1);
-            break;
-          }
         }
-      };
-      for (int i = wid; i < ninv; i += nw) parent_chunk(inv[i], 0);
-      for (int k = wid; k < nextra; k += nw) { const int pk = extra[k]; parent_chunk(inv[pk >> 12], pk & 4095); }
+      }
       __syncthreads();
       for (int i = tid; i < ninv; i += nt) {
         const int x = inv[i];
