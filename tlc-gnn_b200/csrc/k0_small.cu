@@ -786,6 +786,65 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) small_kernel(SmallArgs a)
   }
 }
 
+// Rows class A deferred (64 < n <= 1024): count the induced adjacency entries and route each row to the class that can
+// hold it -- B (n <= 256, <= 4096 entries), C (n <= 1024, <= 8192 entries) -- or to the staged pipeline's list.  With the
+// sizes known up front the three run side by side (run_small) instead of B, then C, then the staged leftovers.
+__global__ void __launch_bounds__(256) small_classify_kernel(SmallArgs a, int32_t* list_b2, int* count_b2, int32_t* list_c,
+                                                             int* count_c) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(16) int32_t xchg_all[48];
+  __shared__ int32_t vert[1024];
+  __shared__ int s_entries;
+  uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);
+  Team<256> tm{(int)threadIdx.x, xchg_all};
+  const int tid = tm.tid, lane = tid & 31, wid = tid >> 5;
+  const bool node_mode = a.p.mode == TLC_MODE_NODE;
+  const int W = a.W;
+  const int count = *a.list_count;
+  for (int it = blockIdx.x; it < count; it += gridDim.x) {
+    __syncthreads();
+    const int32_t row = a.list[it];
+    const int32_t u = a.targets[2 * (int64_t)row], v = a.targets[2 * (int64_t)row + 1];
+    const uint32_t* __restrict__ bu = a.ball_cache + (size_t)u * W;
+    const uint32_t* __restrict__ bv = a.ball_cache + (size_t)(node_mode ? u : v) * W;
+    if (tid == 0) s_entries = 0;
+    int n = 0;
+    for (int w0 = 0; w0 < W; w0 += 256) {
+      const int w = w0 + tid;
+      uint32_t bits = 0;
+      if (w < W) { bits = combine_balls(a.p.mode, bu[w], bv[w], w, u, v); bm[w] = bits; }
+      int tot;
+      const int pre = tm.exscan(__popc(bits), tot);
+      if (n + tot <= 1024) {
+        int k = n + pre;
+        while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; vert[k++] = w * 32 + b; }
+      }
+      n += tot;
+    }
+    __syncthreads();
+    int cnt = 0;
+    if (n <= 1024) {
+      for (int i = wid; i < n; i += 8) {
+        const int32_t x = vert[i];
+        const int ra = a.g.rowptr[x], rb = a.g.rowptr[x + 1];
+        for (int e = ra + lane; e < rb; e += 32) {
+          const int32_t y = a.g.col[e];
+          cnt += (bm[y >> 5] >> (y & 31)) & 1u;
+        }
+      }
+      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULLM, cnt, o);
+      if (lane == 0 && cnt) atomicAdd(&s_entries, cnt);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int d2 = s_entries;
+      if (n <= 256 && d2 <= 4096) list_b2[atomicAdd(count_b2, 1)] = row;
+      else if (n <= 1024 && d2 <= 8192) list_c[atomicAdd(count_c, 1)] = row;
+      else a.big_list[atomicAdd(a.big_count, 1)] = row;
+    }
+  }
+}
+
 template <int NT, int NC, int AC>
 static void launch_class(const SmallArgs& a, int grid, cudaStream_t st) {
   using M = SmallMem<NC, AC>;
@@ -803,11 +862,11 @@ static void launch_class(const SmallArgs& a, int grid, cudaStream_t st) {
 // class C: a 256-thread CTA per target (n <= 1024, <= 4096 edges).
 // counters[0] / [1] / [2]: rows deferred from A to B (list_b) / from B to C (list_c) / from C to the staged pipeline (list_b
 // again: class B has consumed it by then); counters[3]: rows class A sends straight to the staged pipeline (list_big: more
-// than 1024 vertices).  phases: 1 = class A (zeroes the counters), 2 = classes B and C.
+// than 1024 vertices); counters[4]: rows of list_b2.  phases: 1 = class A (zeroes the counters), 2 = classes B then C.
 void launch_small(const GraphView& g, const Params& p, const int32_t* targets, int64_t E, const VicinityScratch& vs,
                   double* out_pi, float* out_pi32, uint8_t* out_status, int32_t* list_b, int32_t* list_c, int32_t* list_big,
                   int* counters, int32_t* out_n, int32_t* out_m, const SmallDiag* diag, SmallStats* stats, int sm_count,
-                  int phases, cudaStream_t st, cudaEvent_t ev_mid2) {
+                  int phases, cudaStream_t st, cudaEvent_t ev_mid2, int32_t* list_b2) {
   SmallArgs a{};
   a.stats = stats; a.ball_acc = vs.ball_acc;
 #ifdef SMALL_PROFILE
@@ -831,7 +890,7 @@ void launch_small(const GraphView& g, const Params& p, const int32_t* targets, i
     a.dbirth = diag->birth; a.ddeath = diag->death; a.want_desc = 1;
   }
   if (phases & 1) {
-    cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
+    cudaMemsetAsync(counters, 0, 8 * sizeof(int), st);
     if (stats) cudaMemsetAsync(stats, 0, sizeof(SmallStats), st);
     // class A over every target
     a.cls = 0;
@@ -858,6 +917,31 @@ void launch_small(const GraphView& g, const Params& p, const int32_t* targets, i
       const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count);
       launch_class<256, 1024, 8192>(a, std::max(grid, 1), st);
     }
+  }
+  // The side-by-side flow of run_small: 4 = route class A's deferred rows by their exact sizes (list_b -> list_b2 / list_c /
+  // list_big), 8 = class B over list_b2, 16 = class C over list_c; what either still cannot take goes into list_b.
+  if (phases & 4) {
+    a.list = list_b; a.list_count = counters;
+    a.big_list = list_big; a.big_count = counters + 3;
+    const size_t bytes = (size_t)a.W * 4 + 16;
+    cudaFuncSetAttribute((const void*)small_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count * 4);
+    small_classify_kernel<<<std::max(grid, 1), 256, bytes, st>>>(a, list_b2, counters + 4, list_c, counters + 1);
+    count_launch();
+  }
+  if (phases & 8) {
+    a.big_list = nullptr; a.big_count = nullptr; a.big_thresh = 0;
+    a.cls = 1;
+    a.list = list_b2; a.list_count = counters + 4; a.defer_list = list_b; a.defer_count = counters + 2;
+    const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count * 3);
+    launch_class<128, 256, 4096>(a, std::max(grid, 1), st);
+  }
+  if (phases & 16) {
+    a.big_list = nullptr; a.big_count = nullptr; a.big_thresh = 0;
+    a.cls = 2;
+    a.list = list_c; a.list_count = counters + 1; a.defer_list = list_b; a.defer_count = counters + 2;
+    const int grid = (int)std::min<int64_t>(E, (int64_t)sm_count);
+    launch_class<256, 1024, 8192>(a, std::max(grid, 1), st);
   }
 }
 

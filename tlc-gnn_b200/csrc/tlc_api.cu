@@ -108,7 +108,9 @@ struct tlc_graph {
   double alg_bytes = 0, alg_bytes_bfs = 0, alg_bytes_uf = 0;
   bool timing = false;
   // kernel S (fused small-vicinity path): deferral lists, counters + statistics, their pinned host mirror
-  int32_t *sm_list_b = nullptr, *sm_list_c = nullptr, *sm_list_big = nullptr;
+  int32_t *sm_list_b = nullptr, *sm_list_c = nullptr, *sm_list_big = nullptr, *sm_list_b2 = nullptr;
+  cudaStream_t small_stream2 = nullptr;  // ... class C beside class B
+  cudaEvent_t ev_small_c = nullptr;
   cudaStream_t small_stream = nullptr;   // classes B / C of kernel S run here while the staged pipeline takes the big targets
   cudaEvent_t ev_small_a = nullptr, ev_small_bc = nullptr;
   int32_t* sm_sub = nullptr;       // [cap][2] targets handed on to the staged pipeline
@@ -207,6 +209,7 @@ static int ensure_arena(tlc_graph* g, size_t need_min, size_t need_all) {
   }
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t had = g->arena_bytes;
   if (g->arena) { free_b += g->arena_bytes; cudaFree(g->arena); g->arena = nullptr; g->arena_bytes = 0; }
   size_t want = g->arena_req;
   if (want == 0) {
@@ -215,6 +218,13 @@ static int ensure_arena(tlc_graph* g, size_t need_min, size_t need_all) {
     want = (size_t)(gb * (double)(1ull << 30));
   }
   want = std::max(std::min(want, need_all + need_all / 2), need_min);  // (no 24 GiB for a handful of small vicinities; 50 % headroom: calls of similar size do not reallocate)
+  // a floor and geometric growth: the handful of large vicinities kernel S leaves to the staged pipeline differs a lot
+  // from call to call, and every reallocation is a device-wide synchronisation (measured: 10 - 60 ms per call)
+  {
+    size_t limit = g->arena_req;
+    if (limit == 0) { const char* env = getenv("TLC_ARENA_GB"); limit = (size_t)((env ? atof(env) : 24.0) * (double)(1ull << 30)); }
+    want = std::max(want, std::min(limit, std::max<size_t>(2 * had, (size_t)256 << 20)));
+  }
   const size_t cap = (size_t)((double)free_b * 0.85);
   if (want > cap) want = cap;
   if (want < need_min)
@@ -888,17 +898,23 @@ static int ensure_small_buffers(tlc_graph* g, int64_t E) {
     CK(cudaMallocHost((void**)&g->sm_host, 256));
     CK(cudaEventCreateWithFlags(&g->ev_small_a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g->ev_small_bc, cudaEventDisableTiming));
-    if (!getenv("TLC_NO_SIDE_STREAMS")) CK(cudaStreamCreateWithFlags(&g->small_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g->ev_small_c, cudaEventDisableTiming));
+    if (!getenv("TLC_NO_SIDE_STREAMS")) {
+      CK(cudaStreamCreateWithFlags(&g->small_stream, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&g->small_stream2, cudaStreamNonBlocking));
+    }
   }
   if (E <= g->sm_cap) return TLC_OK;
   if (g->sm_list_b) cudaFree(g->sm_list_b);
   if (g->sm_list_c) cudaFree(g->sm_list_c);
   if (g->sm_list_big) cudaFree(g->sm_list_big);
-  g->sm_list_b = g->sm_list_c = g->sm_list_big = nullptr; g->sm_cap = 0;
+  if (g->sm_list_b2) cudaFree(g->sm_list_b2);
+  g->sm_list_b = g->sm_list_c = g->sm_list_big = g->sm_list_b2 = nullptr; g->sm_cap = 0;
   const int64_t cap = E + E / 8 + 1024;
   CK(cudaMalloc((void**)&g->sm_list_b, (size_t)cap * 4));
   CK(cudaMalloc((void**)&g->sm_list_c, (size_t)cap * 4));
   CK(cudaMalloc((void**)&g->sm_list_big, (size_t)cap * 4));
+  CK(cudaMalloc((void**)&g->sm_list_b2, (size_t)cap * 4));
   g->sm_cap = cap;
   return TLC_OK;
 }
@@ -917,7 +933,7 @@ static int ensure_small_sub(tlc_graph* g, int64_t k, int r2) {
   return TLC_OK;
 }
 
-static constexpr size_t SM_STATS_OFF = 16;  // SmallStats behind the three deferral counters in sm_dev / sm_host
+static constexpr size_t SM_STATS_OFF = 32;  // SmallStats behind the eight list counters in sm_dev / sm_host
 
 // which calls kernel S (k0_small.cu) can take: the batch call with a Ricci-distance filtration and a 5 x 5 image on a
 // graph whose ball cache exists; the route-forcing diagnostic flags keep their meaning (they name staged kernels)
@@ -986,8 +1002,8 @@ static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tl
   const char* tenv = getenv("TLC_STAGE_TIMING");
   g->timing = tenv && atoi(tenv) != 0;
   StageTimer tm(g->timing, st, &g->ev_pool, g->ev_base);
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb0 = nullptr, ev1b = nullptr, ev2 = nullptr;
-  if (g->timing) { ev0 = tm.take(); ev1 = tm.take(); evb0 = tm.take(); ev1b = tm.take(); ev2 = tm.take(); }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb0 = nullptr, ev1b = nullptr, evc0 = nullptr, ev2 = nullptr;
+  if (g->timing) { ev0 = tm.take(); ev1 = tm.take(); evb0 = tm.take(); ev1b = tm.take(); evc0 = tm.take(); ev2 = tm.take(); }
   VicinityScratch vs = make_vs(g);
   int* counters = reinterpret_cast<int*>(g->sm_dev);
   SmallStats* d_stats = reinterpret_cast<SmallStats*>(g->sm_dev + SM_STATS_OFF);
@@ -996,36 +1012,50 @@ static int run_small(tlc_graph* g, const int32_t* d_targets, int64_t E, const tl
   launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, g->sm_list_big, counters,
                nullptr, nullptr, nullptr, d_stats, g->sm_count, 1, st, nullptr);
   if (ev1) cudaEventRecord(ev1, st);
+  // the rows class A deferred, routed by their exact sizes: class B, class C and the staged pipeline then run side by side
+  launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, g->sm_list_big, counters,
+               nullptr, nullptr, nullptr, d_stats, g->sm_count, 4, st, nullptr, g->sm_list_b2);
   CK(cudaEventRecord(g->ev_small_a, st));
-  CK(cudaMemcpyAsync(g->sm_host, g->sm_dev, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(g->sm_host, g->sm_dev, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const int nB = reinterpret_cast<const int*>(g->sm_host)[0], nBig = reinterpret_cast<const int*>(g->sm_host)[3];
+  const int nB = reinterpret_cast<const int*>(g->sm_host)[4], nCc = reinterpret_cast<const int*>(g->sm_host)[1];
+  const int nBig = reinterpret_cast<const int*>(g->sm_host)[3];
   if (nBig == E) {  // nothing for kernel S: the staged pipeline takes the whole call, and the next calls do not try again
     g->small_skip = 32;
     *fell_through = true;
     return TLC_OK;
   }
-  // classes B and C on their own stream, behind class A
   cudaStream_t sb = g->small_stream ? g->small_stream : st;
+  cudaStream_t sc = g->small_stream2 ? g->small_stream2 : st;
   if (nB > 0) {
     if (sb != st) CK(cudaStreamWaitEvent(sb, g->ev_small_a, 0));
     if (evb0) cudaEventRecord(evb0, sb);
     launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, g->sm_list_big, counters,
-                 nullptr, nullptr, nullptr, d_stats, g->sm_count, 2, sb, ev1b);
-    if (ev2) cudaEventRecord(ev2, sb);
+                 nullptr, nullptr, nullptr, d_stats, g->sm_count, 8, sb, nullptr, g->sm_list_b2);
+    if (ev1b) cudaEventRecord(ev1b, sb);
     if (sb != st) CK(cudaEventRecord(g->ev_small_bc, sb));
+  }
+  if (nCc > 0) {
+    if (sc != st) CK(cudaStreamWaitEvent(sc, g->ev_small_a, 0));
+    if (evc0) cudaEventRecord(evc0, sc);
+    launch_small(g->gv, p, d_targets, E, vs, d_pi, d_pi32, d_status, g->sm_list_b, g->sm_list_c, g->sm_list_big, counters,
+                 nullptr, nullptr, nullptr, d_stats, g->sm_count, 16, sc, nullptr, g->sm_list_b2);
+    if (ev2) cudaEventRecord(ev2, sc);
+    if (sc != st) CK(cudaEventRecord(g->ev_small_c, sc));
   }
   StagedAcc acc;
   if (nBig > 0 && (rc = run_staged_list(g, d_targets, g->sm_list_big, nBig, up, d_pi, d_pi32, d_status, tm, acc))) return rc;
   if (nB > 0 && sb != st) CK(cudaStreamWaitEvent(st, g->ev_small_bc, 0));
+  if (nCc > 0 && sc != st) CK(cudaStreamWaitEvent(st, g->ev_small_c, 0));
   CK(cudaMemcpyAsync(g->sm_host, g->sm_dev, SM_STATS_OFF + sizeof(SmallStats), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const int nC = nB > 0 ? reinterpret_cast<const int*>(g->sm_host)[2] : 0;  // rows class C could not take (listed in sm_list_b)
+  const int nC = reinterpret_cast<const int*>(g->sm_host)[2];  // rows classes B / C could not take after all (listed in sm_list_b)
   const SmallStats hs = *reinterpret_cast<const SmallStats*>(g->sm_host + SM_STATS_OFF);
   float msA = 0, msB = 0, msC = 0;
   if (g->timing) {
     cudaEventElapsedTime(&msA, ev0, ev1);
-    if (nB > 0) { cudaEventElapsedTime(&msB, evb0, ev1b); cudaEventElapsedTime(&msC, ev1b, ev2); }
+    if (nB > 0) cudaEventElapsedTime(&msB, evb0, ev1b);
+    if (nCc > 0) cudaEventElapsedTime(&msC, evc0, ev2);
   }
   if (nC > 0 && (rc = run_staged_list(g, d_targets, g->sm_list_b, nC, up, d_pi, d_pi32, d_status, tm, acc))) return rc;
   // a call whose vicinities are mostly too large: do not try again for a while (the size check alone costs a pass over
@@ -1197,6 +1227,9 @@ int tlc_graph_destroy(tlc_graph* g) {
   for (int i = 0; i < 3; i++) { if (g->side[i]) cudaStreamDestroy(g->side[i]); if (g->ev_join[i]) cudaEventDestroy(g->ev_join[i]); }
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->small_stream) cudaStreamDestroy(g->small_stream);
+  if (g->small_stream2) cudaStreamDestroy(g->small_stream2);
+  if (g->ev_small_c) cudaEventDestroy(g->ev_small_c);
+  cudaFree(g->sm_list_b2);
   if (g->ev_small_a) cudaEventDestroy(g->ev_small_a);
   if (g->ev_small_bc) cudaEventDestroy(g->ev_small_bc);
   cudaFree(g->sm_list_big);
