@@ -10,7 +10,9 @@ def flush():
     global agg
     if not agg: return
     tot = sum(v[0] for v in agg.values()) or 1
-    print("== %s  [%s]  samples=%d" % (kname[:100], fname, tot))
+    files = {}
+    for (f, ln, src), v in agg.items(): files[f] = files.get(f, 0) + v[0]
+    print("== %s  [%s]  samples=%d" % (kname[:100], max(files, key=files.get), tot))
     for (f, ln, src), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:N]:
         st = sorted(v[2].items(), key=lambda kv: -kv[1])[:3]
         print("%6.2f%% ex=%-10d %-44s | %4s %s" % (100.0 * v[0] / tot, v[1], ",".join("%s:%d" % (k[6:], n) for k, n in st if n), ln, src.strip()[:100]))

@@ -539,14 +539,16 @@ __global__ void __launch_bounds__(256) clustering_filtration_kernel(Params p, Ch
 //   hks(x) = sum_k phi_k(x)^2 exp(-t lambda_k) = [exp(-t L)]_xx,   then / (max + 1e-10).
 // With N = D^-1/2 A D^-1/2 (L = I - N on the vertices of positive degree; scipy puts 0 on the diagonal of an isolated
 // vertex: hks = 1 there), exp(-t L) = e^-t exp(t N) and, N being symmetric, [exp(t N)]_xx = || exp((t/2) N) e_x ||^2.
-// One CTA per vicinity: for each vertex x the CTA pushes e_x through the Taylor series z = sum_j ((t/2)^j / j!) N^j e_x
-// (`terms` terms, the host chooses them so that the remainder is < 1e-18; ||N|| <= 1), two ping-pong vectors in shared
-// memory when they fit, rows of the induced adjacency dealt to the threads.
-__global__ void __launch_bounds__(256) hks_filtration_kernel(Params p, ChunkView c, double t, int terms, int cap) {
+// A WARP per source vertex x pushes e_x through the Taylor series z = sum_j ((t/2)^j / j!) N^j e_x (`terms` terms, the host
+// chooses them so that the remainder is < 1e-18; ||N|| <= 1): its three vectors live in shared memory, a lane owns the rows
+// a = lane, lane + 32, ... and walks each row in adjacency order (the sums do not depend on the launch geometry), and
+// nothing but __syncwarp separates the terms.  The sources of one vicinity are dealt to gridDim.y CTAs of `wpc` warps, so
+// that a hub's vicinity (n sources x terms x (n + 2m) operations) does not serialise on one SM.  hks_normalise_kernel
+// then divides by the maximum.
+__global__ void __launch_bounds__(256) hks_filtration_kernel(Params p, ChunkView c, double t, int terms, int cap, int wpc) {
   extern __shared__ __align__(16) double hsm[];
-  __shared__ double redd[32];
   const int tt = blockIdx.x;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
   const int n = c.tn[tt];
   if (n == 0 || c.tstatus[tt] > TLC_ST_TRIVIAL) return;
   const int64_t vo = c.voff[tt], ao = c.aoff[tt];
@@ -554,28 +556,32 @@ __global__ void __launch_bounds__(256) hks_filtration_kernel(Params p, ChunkView
   const int32_t* __restrict__ adeg = c.adeg + vo;
   const uint32_t* __restrict__ anb = c.anb + ao;
   double* fval = c.fval + vo;
-  const bool in_smem = n <= cap;
+  const bool in_smem = cap > 0;  // (the host sizes cap for the launch's largest vicinity, or 0: vectors in the arena, one warp)
   double* isd = in_smem ? hsm : c.d1 + vo;                                   // 1 / sqrt(degree), 0 for an isolated vertex
-  double* y0 = in_smem ? hsm + cap : reinterpret_cast<double*>(c.v64a + vo);
-  double* y1 = in_smem ? hsm + 2 * cap : reinterpret_cast<double*>(c.v64b + vo);
-  double* zz = in_smem ? hsm + 3 * cap : reinterpret_cast<double*>(c.v64c + vo);
+  const int per = (n + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int x_lo = (int)blockIdx.y * per, x_hi = min(n, x_lo + per);
+  if (x_lo >= x_hi) return;
   for (int a = tid; a < n; a += nt) {
     const int dg = adeg[a];
     isd[a] = dg > 0 ? __ddiv_rn(1.0, sqrt((double)dg)) : 0.0;
-    c.neg[vo + a] = -1; c.vcls[vo + a] = -1;  // (no shortest-path tree here: kernel 2v gets no neighbour hint)
+    if (blockIdx.y == 0) { c.neg[vo + a] = -1; c.vcls[vo + a] = -1; }  // (no shortest-path tree here: kernel 2v gets no neighbour hint)
   }
   __syncthreads();
+  if (wid >= wpc) return;
+  double* y0 = in_smem ? hsm + (size_t)cap * (1 + 3 * wid) : reinterpret_cast<double*>(c.v64a + vo);
+  double* y1 = in_smem ? y0 + cap : reinterpret_cast<double*>(c.v64b + vo);
+  double* zz = in_smem ? y1 + cap : reinterpret_cast<double*>(c.v64c + vo);
   const double h = 0.5 * t;
-  for (int x = 0; x < n; x++) {
-    if (adeg[x] == 0) { if (tid == 0) fval[x] = 1.0; continue; }   // (uniform over the CTA)
-    for (int a = tid; a < n; a += nt) { const double e = a == x ? 1.0 : 0.0; y0[a] = e; zz[a] = e; }
-    __syncthreads();
+  for (int x = x_lo + wid; x < x_hi; x += wpc) {
+    if (adeg[x] == 0) { if (lane == 0) fval[x] = 1.0; continue; }   // (scipy: 0 on the diagonal of L -> exp(0) = 1)
+    for (int a = lane; a < n; a += 32) { const double e = a == x ? 1.0 : 0.0; y0[a] = e; zz[a] = e; }
+    __syncwarp();
     double cj = 1.0;
     double* src = y0;
     double* dst = y1;
     for (int j = 1; j <= terms; j++) {
       cj = cj * h / (double)j;
-      for (int a = tid; a < n; a += nt) {
+      for (int a = lane; a < n; a += 32) {
         const int s0 = astart[a], dg = adeg[a];
         double acc = 0.0;
         for (int q = 0; q < dg; q++) { const int b = (int)anb[s0 + q]; acc += isd[b] * src[b]; }
@@ -583,23 +589,25 @@ __global__ void __launch_bounds__(256) hks_filtration_kernel(Params p, ChunkView
         dst[a] = v;
         zz[a] += cj * v;
       }
-      __syncthreads();
+      __syncwarp();
       double* tmp = src; src = dst; dst = tmp;
     }
     double part = 0.0;
-    for (int a = tid; a < n; a += nt) part += zz[a] * zz[a];
+    for (int a = lane; a < n; a += 32) part += zz[a] * zz[a];
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __syncthreads();
-    if ((tid & 31) == 0) redd[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < (nt + 31) / 32; w++) tot += redd[w];
-      fval[x] = exp(-t) * tot;
-    }
-    __syncthreads();
+    if (lane == 0) fval[x] = exp(-t) * part;
+    __syncwarp();
   }
-  // filtration_val /= (max(filtration_val) + 1e-10)   :117
+}
+
+// filtration_val /= (max(filtration_val) + 1e-10)   data_utils_NC.py:117
+__global__ void __launch_bounds__(256) hks_normalise_kernel(ChunkView c) {
+  __shared__ double redd[32];
+  const int tt = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n = c.tn[tt];
+  if (n == 0 || c.tstatus[tt] > TLC_ST_TRIVIAL) return;
+  double* fval = c.fval + c.voff[tt];
   double mx = -1.0;
   for (int a = tid; a < n; a += nt) mx = fmax(mx, fval[a]);
   const double m = __dadd_rn(block_reduce_max(mx, redd), 1e-10);
@@ -649,10 +657,15 @@ void launch_hks_filtration(const Params& p, const ChunkView& c, double t, int64_
   double cj = 0.5 * t;
   while (terms < 400 && (cj > 1e-18 || terms < 0.5 * t)) { terms++; cj = cj * 0.5 * t / terms; }
   int cap = (int)((n_max + 1) / 2 * 2);
-  if ((size_t)cap * 32 > 200 * 1024) cap = 0;  // larger vicinities keep the vectors in the arena
-  const size_t bytes = (size_t)cap * 32;
+  constexpr size_t BUDGET = 200 * 1024;
+  int wpc = (int)std::min<size_t>(8, (BUDGET / 8 / (size_t)std::max(cap, 1) - 1) / 3);  // warps whose three vectors fit next to isd[]
+  int slices = (int)std::min<int64_t>(128, std::max<int64_t>(1, (n_max + 7) / 8));     // a source per warp of the largest vicinity's CTAs (measured: 32 slices 1.25 s, one CTA 2.58 s on 2048 PubMed-shaped node vicinities)
+  if ((size_t)cap * 32 > BUDGET) { cap = 0; wpc = 1; slices = 1; }  // larger vicinities keep the (single set of) vectors in the arena
+  const size_t bytes = (size_t)cap * 8 * (1 + 3 * wpc);
   cudaFuncSetAttribute((const void*)hks_filtration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  hks_filtration_kernel<<<c.T, 256, bytes, st>>>(p, c, t, terms, cap);
+  hks_filtration_kernel<<<dim3((unsigned)c.T, (unsigned)slices), 256, bytes, st>>>(p, c, t, terms, cap, wpc);
+  count_launch();
+  hks_normalise_kernel<<<c.T, 256, 0, st>>>(c);
   count_launch();
 }
 

@@ -22,6 +22,9 @@
 // vertices; the table rows of u and v (D, Q, W, P: 28 N bytes each) are streamed instead.
 #include <cstdlib>
 
+#include <cstdio>
+#include <cstring>
+
 #include "tlc_common.cuh"
 
 namespace tlc {
@@ -222,9 +225,16 @@ struct TableShared {
   int32_t ninv;     // invalid vertices of the current root
   int32_t nextra;   // further chunks of their long rows
   int32_t dinv;     // sum of their graph degrees
+  int32_t nia;      // entries of the list of invalid-invalid adjacencies
   int32_t any;
 };
-constexpr int ROW_CHUNK = 128;  // entries of a graph row per work item of the pull relaxation
+#ifdef T1_PROFILE
+__device__ unsigned long long g_t1prof[16];
+#define TPROF(i) do { if (tid == 0) { const long long tnow_ = clock64(); atomicAdd(&g_t1prof[i], (unsigned long long)(tnow_ - tprev_)); tprev_ = tnow_; } } while (0)
+#else
+#define TPROF(i) do { } while (0)
+#endif
+
 
 __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkView c, int t0, int cap, GraphView g,
                                                                 const uint32_t* __restrict__ ball_cache, SsspTables tb, int W) {
@@ -242,6 +252,9 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
   uint32_t* bm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dynt) + (size_t)cap * 11);
   uint16_t* lid = reinterpret_cast<uint16_t*>(bm + 2 * W);
 
+#ifdef T1_PROFILE
+  long long tprev_ = clock64();
+#endif
   // ---- 0. the vicinity (as kernel 1b's graph-row prologue): nodes = set(nodes_u) & set(nodes_v), local ids = ranks   :311-316
   const int64_t ti = c.tidx[t];
   const int32_t u = c.tgt[2 * ti], v = c.tgt[2 * ti + 1];
@@ -290,6 +303,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
     c.tnp[t] = 0; c.tnpos[t] = 0; c.tnneg[t] = 0; c.tncls[t] = 0;
   }
   __syncthreads();
+      TPROF(0);
   if (n == 0 || st0 > TLC_ST_TRIVIAL) return;
 
   const int32_t* __restrict__ vert = c.vert + vo;
@@ -302,6 +316,11 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
   int32_t* extra = c.vs1 + vo;    // further row chunks of the long invalid rows: local vertex id << 12 | chunk
   int32_t* bpos = c.vs2 + vo;     // per vertex: smallest row position of a tree-parent candidate
   double* tpw = reinterpret_cast<double*>(c.v64b + vo);  // weight of an invalid vertex's parent edge
+  uint32_t* iap = reinterpret_cast<uint32_t*>(c.vord + vo);   // invalid-invalid adjacency: vertex << 16 | neighbour ...
+  int32_t* iaq = c.vrank + vo;                                // ... and the row position of the entry; slots n .. 2n - 1:
+  uint2* ia2 = reinterpret_cast<uint2*>(c.v64a + vo);
+  uint2* ia3 = reinterpret_cast<uint2*>(c.v64c + vo);
+  uint2* ia4 = reinterpret_cast<uint2*>(c.fval + vo);       // (the filtration values are written at the very end)
   const bool roots_in = lu >= 0 && lv >= 0;
   const bool plain = (p.flags & TLC_F_SUM_PLAIN) != 0;
   const bool two = roots_in && !node_mode && lu != lv;
@@ -320,7 +339,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
       const int32_t* __restrict__ Prow = tb.P + (size_t)groot * N;
       double* out = r == 0 ? d1 : d2;
       int32_t* hnt = r == 0 ? hint0 : hint;
-      if (tid == 0) { sh.ninv = 0; sh.nextra = 0; sh.dinv = 0; }
+      if (tid == 0) { sh.ninv = 0; sh.nextra = 0; sh.dinv = 0; sh.nia = 0; }
       // ---- 1. classes: the branch of x stays in S <=> its table parent is in S and is valid itself ----
       for (int x = tid; x < n; x += nt) {
         const int32_t gx = vert[x];
@@ -337,6 +356,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         if (r == 0) { hint[x] = -1; hint0[x] = -1; }
       }
       __syncthreads();
+      TPROF(1);
       for (int round = 0; round <= n; round++) {
         int ch = 0;
         for (int x = tid; x < n; x += nt) {
@@ -347,6 +367,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         }
         if (!__syncthreads_or(ch)) break;
       }
+      TPROF(2);
       // ---- 2. the invalid vertices, their distances by pull relaxations over their own graph rows ----
       // Work items are row CHUNKS: item i < ninv is the first chunk of invalid vertex i, the further chunks of the long
       // rows (hubs) are listed once per root in extra[] -- a hub's row is then spread over many warps instead of stalling
@@ -366,9 +387,12 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         }
       }
       __syncthreads();
+      TPROF(3);
       const int ninv = sh.ninv;
-      int chunk = ROW_CHUNK;
-      while (sh.dinv / chunk > n / 2) chunk *= 2;  // (the extra chunks must fit the n slots of extra[])
+      // chunk size: EIGHT LANES walk a chunk together (one 128-byte line of records per step); about four chunks per
+      // 8-lane group, between 32 and 512 records -- then doubled until the extra chunks fit the n slots of extra[]
+      int chunk = min(512, max(32, ((sh.dinv / (nt / 2) + 31) / 32) * 32));
+      while (sh.dinv / chunk > n / 2) chunk *= 2;
       for (int i = tid; i < ninv; i += nt) {
         const int32_t gx = vert[inv[i]];
         const int cnt = (g.rowptr[gx + 1] - g.rowptr[gx] + chunk - 1) / chunk;
@@ -378,94 +402,111 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         }
       }
       __syncthreads();
+      TPROF(4);
       const int nextra = sh.nextra, nitems = ninv + nextra;
-      // A warp takes items wid, wid + nw, ...: 32 of them at a time, their row bounds fetched lane-parallel, and the first
-      // 128 records of item q + 1 are in flight while item q is reduced (the chain vertex -> row bounds -> records ->
-      // distance would otherwise cost three dependent HBM/L2 latencies per item).
+      // Eight lanes walk a chunk: their 16-byte record loads fall into one 128-byte line per step (one L1 wavefront; a lane
+      // per chunk costs a wavefront per record, a warp per chunk leaves most lanes idle on these 25 - 100-record rows and
+      // pays a 32-lane reduction per row -- both measured slower).  Four loads in flight per lane, a 3-step reduction.
+      const int l8 = lane & 7, grp = tid >> 3, ngrp = nt >> 3;
+      const unsigned gm = 0xffu << (lane & 24);  // the lanes of this 8-lane group
       auto item_bounds = [&](int i, int& x, int& a, int& b) {
-        x = -1; a = 0; b = 0;
-        if (i < nitems) {
-          const int pk = i < ninv ? (inv[i] << 12) : extra[i - ninv];
-          x = pk >> 12;
-          const int ra = c.astart[vo + x];
-          a = ra + (pk & 4095) * chunk;
-          b = min(ra + c.adeg[vo + x], a + chunk);
-        }
+        const int pk = i < ninv ? (inv[i] << 12) : extra[i - ninv];
+        x = pk >> 12;
+        const int ra = c.astart[vo + x];
+        a = ra + (pk & 4095) * chunk;
+        b = min(ra + c.adeg[vo + x], a + chunk);
       };
-      auto load4 = [&](int a, int b, uint4 (&rc)[4]) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int e = a + q * 32 + lane;
-          rc[q] = e < b ? __ldg(g.rec + e) : make_uint4(0xffffffffu, 0u, 0u, 0u);
-        }
+      // The FIRST round reads every invalid row once.  The valid neighbours' distances are final: their candidates never
+      // need a second look.  The invalid neighbours go into a list of (vertex, neighbour, row position) entries -- the
+      // graph among the invalid vertices, a few entries per vertex -- and the following rounds run over that list only
+      // (measured: 3 rounds, the second changes 2 - 5 % of the vertices, the third none).  A list that outgrows its 4n
+      // slots (small vicinities that are mostly invalid) sends the root back to rounds over the rows.
+      auto ia_put = [&](int k, uint32_t pr, int pos) {
+        if (k < n) { iap[k] = pr; iaq[k] = pos; }
+        else if (k < 4 * n) { const int sgm = k / n - 1; (sgm == 0 ? ia2 : sgm == 1 ? ia3 : ia4)[k - (sgm + 1) * n] = make_uint2(pr, (uint32_t)pos); }
       };
-      auto fold4 = [&](const uint4 (&rc)[4], unsigned long long best) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          if (rc[q].x == 0xffffffffu) continue;
-          const uint16_t ly = lid[rc[q].x];
-          if (ly == 0xffff) continue;
-          const unsigned long long dyb = dist[ly];
-          if (dyb == T_INF) continue;
-          const double w = __hiloint2double((int)rc[q].w, (int)rc[q].z);
-          const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
-          best = cand < best ? cand : best;
-        }
-        return best;
+      auto ia_get = [&](int k, uint32_t& pr, int& pos) {
+        if (k < n) { pr = iap[k]; pos = iaq[k]; }
+        else { const int sgm = k / n - 1; const uint2 v2 = (sgm == 0 ? ia2 : sgm == 1 ? ia3 : ia4)[k - (sgm + 1) * n]; pr = v2.x; pos = (int)v2.y; }
       };
-      for (int round = 0; round <= ninv; round++) {
+      auto relax_rows = [&](bool first) -> int {
         int ch = 0;
-        for (int k0 = 0; wid + k0 * nw < nitems; k0 += 32) {
-          int mx, ma, mb;
-          item_bounds(wid + (k0 + lane) * nw, mx, ma, mb);
-          const int cnt = min(32, (nitems - wid - k0 * nw + nw - 1) / nw);
-          uint4 cur[4], nxt[4];
-          load4(__shfl_sync(0xffffffffu, ma, 0), __shfl_sync(0xffffffffu, mb, 0), cur);
-          for (int q = 0; q < cnt; q++) {
-            const int x = __shfl_sync(0xffffffffu, mx, q), a = __shfl_sync(0xffffffffu, ma, q), b = __shfl_sync(0xffffffffu, mb, q);
-            const int qn = min(q + 1, 31);
-            const int an = __shfl_sync(0xffffffffu, ma, qn), bn = __shfl_sync(0xffffffffu, mb, qn);
-            if (q + 1 < cnt) load4(an, bn, nxt);
-            unsigned long long best = fold4(cur, T_INF);
-            for (int e0 = a + 128; e0 < b; e0 += 128) {  // (only when the chunk was widened beyond 128 records)
-              load4(e0, b, cur);
-              best = fold4(cur, best);
-            }
-            best = shfl_min_u64(best);
-            if (lane == 0 && best < dist[x] && best < atomicMin(&dist[x], best)) ch = 1;
+        for (int it0 = 0; it0 < nitems; it0 += ngrp) {   // (uniform trip count: the group reductions below are warp-wide shuffles)
+          const int it = it0 + grp;
+          int x = 0, a = 0, b = 0;
+          if (it < nitems) item_bounds(it, x, a, b);
+          unsigned long long best = T_INF;
+          for (int e0 = a + l8; e0 < b; e0 += 32) {
+            uint4 rc[4];
 #pragma unroll
-            for (int z = 0; z < 4; z++) cur[z] = nxt[z];
+            for (int q = 0; q < 4; q++) rc[q] = e0 + 8 * q < b ? __ldg(g.rec + e0 + 8 * q) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              if (rc[q].x == 0xffffffffu) continue;
+              const uint16_t ly = lid[rc[q].x];
+              if (ly == 0xffff) continue;
+              if (first && cls[ly] == INVALID) ia_put(atomicAdd(&sh.nia, 1), ((uint32_t)x << 16) | ly, e0 + 8 * q);
+              const unsigned long long dyb = dist[ly];
+              if (dyb == T_INF) continue;
+              const double w = __hiloint2double((int)rc[q].w, (int)rc[q].z);
+              const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
+              best = cand < best ? cand : best;
+            }
           }
+#pragma unroll
+          for (int o = 4; o; o >>= 1) { const unsigned long long u2 = __shfl_xor_sync(gm, best, o); best = u2 < best ? u2 : best; }
+          if (l8 == 0 && it < nitems && best < dist[x] && best < atomicMin(&dist[x], best)) ch = 1;
+        }
+        return ch;
+      };
+      relax_rows(true);
+      __syncthreads();
+      const int nia = sh.nia;
+      const bool full = nia > 4 * n;
+      for (int round = 1; round <= ninv + 1; round++) {
+        int ch = 0;
+        if (!full) {
+          for (int k = tid; k < nia; k += nt) {
+            uint32_t pr; int pos;
+            ia_get(k, pr, pos);
+            const int x = (int)(pr >> 16), ly = (int)(pr & 0xffffu);
+            const unsigned long long dyb = dist[ly];
+            if (dyb == T_INF) continue;
+            const uint4 rc = __ldg(g.rec + pos);
+            const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __hiloint2double((int)rc.w, (int)rc.z)));
+            if (cand < dist[x] && cand < atomicMin(&dist[x], cand)) ch = 1;
+          }
+        } else {
+          ch = relax_rows(false);
         }
         if (!__syncthreads_or(ch)) break;
       }
       // ---- 3. tree rule for the invalid vertices: smallest local id y (= smallest row position) with fl(d[y] + w) == d[x] ----
-      for (int k0 = 0; wid + k0 * nw < nitems; k0 += 32) {
-        int mx, ma, mb;
-        item_bounds(wid + (k0 + lane) * nw, mx, ma, mb);
-        const int cnt = min(32, (nitems - wid - k0 * nw + nw - 1) / nw);
-        for (int q = 0; q < cnt; q++) {
-          const int x = __shfl_sync(0xffffffffu, mx, q), a = __shfl_sync(0xffffffffu, ma, q), b = __shfl_sync(0xffffffffu, mb, q);
-          const unsigned long long dxb = dist[x];
-          if (dxb == T_INF) continue;
-          for (int e0 = a; e0 < b; e0 += 32) {
-            const int e = e0 + lane;
-            bool hit = false;
-            if (e < b) {
-              const uint4 rc = __ldg(g.rec + e);
-              const uint16_t ly = lid[rc.x];
-              if (ly != 0xffff) {
-                const unsigned long long dyb = dist[ly];
-                hit = dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __hiloint2double((int)rc.w, (int)rc.z))) == dxb;
-              }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (bal) {
-              if (lane == 0) atomicMin(&bpos[x], e0 + __ffs(bal) - 1);
-              break;
-            }
+      for (int it0 = 0; it0 < nitems; it0 += ngrp) {
+        const int it = it0 + grp;
+        int x = 0, a = 0, b = 0;
+        if (it < nitems) item_bounds(it, x, a, b);
+        const unsigned long long dxb = it < nitems ? dist[x] : T_INF;
+        if (dxb == T_INF) b = a;
+        int hit = 0x7fffffff;
+        for (int e0 = a; e0 < b; e0 += 32) {   // (uniform over the group: the exit test below is a group vote)
+          uint4 rc[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) rc[q] = e0 + l8 + 8 * q < b ? __ldg(g.rec + e0 + l8 + 8 * q) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+#pragma unroll
+          for (int q = 3; q >= 0; q--) {
+            if (rc[q].x == 0xffffffffu) continue;
+            const uint16_t ly = lid[rc[q].x];
+            if (ly == 0xffff) continue;
+            const unsigned long long dyb = dist[ly];
+            if (dyb != T_INF && (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __hiloint2double((int)rc[q].w, (int)rc[q].z))) == dxb)
+              hit = e0 + l8 + 8 * q;
           }
+          if (__ballot_sync(gm, hit != 0x7fffffff)) break;   // (the group's own vote: groups leave at different times)
         }
+#pragma unroll
+        for (int o = 4; o; o >>= 1) hit = min(hit, __shfl_xor_sync(gm, hit, o));
+        if (l8 == 0 && hit != 0x7fffffff) atomicMin(&bpos[x], hit);
       }
       __syncthreads();
       for (int i = tid; i < ninv; i += nt) {
@@ -474,6 +515,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         if (pos != 0x7fffffff) { parl[x] = lid[g.col[pos]]; tpw[x] = __dadd_rn(g.kappa[pos], 1.0); }
       }
       __syncthreads();
+      TPROF(8);
       // ---- 4. path sums: the table's for valid vertices, a walk in python order for the others   :30,35 ----
       for (int x = tid; x < n; x += nt) {
         double res;
@@ -496,6 +538,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         out[x] = res;
       }
       __syncthreads();
+      TPROF(9);
     }
     if (!two) for (int x = tid; x < n; x += nt) d2[x] = d1[x];
     __syncthreads();
@@ -530,6 +573,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
     if (norm) f = __ddiv_rn(f, p.descriptor == TLC_DESC_SUM ? ssum : smax);
     fval[x] = f;
   }
+  TPROF(10);
 }
 
 }  // namespace
@@ -567,6 +611,23 @@ void launch_filtration_table(const GraphView& g, const Params& p, const ChunkVie
   if (const char* env = getenv("TLC_TABLE_BLOCK")) block = atoi(env);  // (tuning experiments)
   cudaFuncSetAttribute((const void*)filtration_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   cudaFuncSetAttribute((const void*)filtration_table_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#ifdef T1_PROFILE
+  if (getenv("T1_PROFILE_DUMP")) {  // ticks of thread 0 per phase, summed over the CTAs since the last dump
+    unsigned long long h[16];
+    cudaMemcpyFromSymbol(h, g_t1prof, sizeof h);
+    static const char* nm[11] = {"prologue", "class_init", "class_rounds", "compaction", "chunks", "first_round", "later_rounds",
+                                 "tree_rule", "parents", "path_sums", "descriptors"};
+    unsigned long long tot = 0;
+    for (int i = 0; i < 11; i++) tot += h[i];
+    if (tot) {
+      fprintf(stderr, "[1t profile]");
+      for (int i = 0; i < 11; i++) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * (double)h[i] / (double)tot);
+      fprintf(stderr, " | total %.1f Mticks\n", (double)tot / 1e6);
+    }
+    memset(h, 0, sizeof h);
+    cudaMemcpyToSymbol(g_t1prof, h, sizeof h);
+  }
+#endif
   filtration_table_kernel<<<cnt, block, bytes, st>>>(p, c, t0, cap, g, vs.ball_cache, tb, W);
   count_launch();
 }
