@@ -315,7 +315,6 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
   int32_t* inv = c.vs0 + vo;      // list of the invalid vertices of the current root
   int32_t* extra = c.vs1 + vo;    // further row chunks of the long invalid rows: local vertex id << 12 | chunk
   int32_t* bpos = c.vs2 + vo;     // per vertex: smallest row position of a tree-parent candidate
-  double* tpw = reinterpret_cast<double*>(c.v64b + vo);  // weight of an invalid vertex's parent edge
   uint32_t* iap = reinterpret_cast<uint32_t*>(c.vord + vo);   // invalid-invalid adjacency: vertex << 16 | neighbour ...
   int32_t* iaq = c.vrank + vo;                                // ... and the row position of the entry; slots n .. 2n - 1:
   uint2* ia2 = reinterpret_cast<uint2*>(c.v64a + vo);
@@ -324,7 +323,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
   const bool roots_in = lu >= 0 && lv >= 0;
   const bool plain = (p.flags & TLC_F_SUM_PLAIN) != 0;
   const bool two = roots_in && !node_mode && lu != lv;
-  constexpr uint8_t UNKNOWN = 0, VALID = 1, INVALID = 2;
+  constexpr uint8_t UNKNOWN = 0, VALID = 1, INVALID = 2, UNREACH = 3;
 
   if (!roots_in) {
     // nx.NodeNotFound for every vertex -> dist = 100   riccidist2dgm.py:31-32,36-37
@@ -423,52 +422,74 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
       // slots (small vicinities that are mostly invalid) sends the root back to rounds over the rows.
       auto ia_put = [&](int k, uint32_t pr, int pos) {
         if (k < n) { iap[k] = pr; iaq[k] = pos; }
-        else if (k < 4 * n) { const int sgm = k / n - 1; (sgm == 0 ? ia2 : sgm == 1 ? ia3 : ia4)[k - (sgm + 1) * n] = make_uint2(pr, (uint32_t)pos); }
+        else if (k < 2 * n) ia2[k - n] = make_uint2(pr, (uint32_t)pos);
+        else if (k < 3 * n) ia3[k - 2 * n] = make_uint2(pr, (uint32_t)pos);
+        else if (k < 4 * n) ia4[k - 3 * n] = make_uint2(pr, (uint32_t)pos);
       };
       auto ia_get = [&](int k, uint32_t& pr, int& pos) {
-        if (k < n) { pr = iap[k]; pos = iaq[k]; }
-        else { const int sgm = k / n - 1; const uint2 v2 = (sgm == 0 ? ia2 : sgm == 1 ? ia3 : ia4)[k - (sgm + 1) * n]; pr = v2.x; pos = (int)v2.y; }
+        if (k < n) { pr = iap[k]; pos = iaq[k]; return; }
+        const uint2 v2 = k < 2 * n ? ia2[k - n] : k < 3 * n ? ia3[k - 2 * n] : ia4[k - 3 * n];
+        pr = v2.x; pos = (int)v2.y;
       };
+      // List slots without atomics: every warp owns a region of 4n / nw slots and counts its entries in a register (one
+      // warp vote per record slot; the single shared counter this replaces serialised 2 600 atomics per root -- 100 k cycles,
+      // most of the first round).  The later rounds: a warp walks its own region.
+      const int capw = (4 * n) / nw;
+      int cntw = 0;
       auto relax_rows = [&](bool first) -> int {
         int ch = 0;
-        for (int it0 = 0; it0 < nitems; it0 += ngrp) {   // (uniform trip count: the group reductions below are warp-wide shuffles)
-          const int it = it0 + grp;
-          int x = 0, a = 0, b = 0;
-          if (it < nitems) item_bounds(it, x, a, b);
-          unsigned long long best = T_INF;
-          for (int e0 = a + l8; e0 < b; e0 += 32) {
-            uint4 rc[4];
+        for (int kb = 0; kb * ngrp < nitems; kb += 8) {   // (uniform trip counts: the shuffles below are group-wide)
+          // the group's next eight items, their bounds fetched lane-parallel (vertex -> row start, degree: a dependent chain)
+          int mx = 0, ma = 0, mb = 0;
+          { const int itl = (kb + l8) * ngrp + grp; if (itl < nitems) item_bounds(itl, mx, ma, mb); }
+          for (int j = 0; j < 8; j++) {
+            const int x = __shfl_sync(gm, mx, j, 8), a = __shfl_sync(gm, ma, j, 8), b = __shfl_sync(gm, mb, j, 8);
+            int trips = (b - a + 31) >> 5;  // the longest of the warp's four chunks: the votes below are warp-wide
+            trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 8));
+            trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 16));
+            unsigned long long best = T_INF;
+            for (int t5 = 0; t5 < trips; t5++) {
+              const int e0 = a + l8 + 32 * t5;
+              uint4 rc[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) rc[q] = e0 + 8 * q < b ? __ldg(g.rec + e0 + 8 * q) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+              for (int q = 0; q < 4; q++) rc[q] = e0 + 8 * q < b ? __ldg(g.rec + e0 + 8 * q) : make_uint4(0xffffffffu, 0u, 0u, 0u);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              if (rc[q].x == 0xffffffffu) continue;
-              const uint16_t ly = lid[rc[q].x];
-              if (ly == 0xffff) continue;
-              if (first && cls[ly] == INVALID) ia_put(atomicAdd(&sh.nia, 1), ((uint32_t)x << 16) | ly, e0 + 8 * q);
-              const unsigned long long dyb = dist[ly];
-              if (dyb == T_INF) continue;
-              const double w = __hiloint2double((int)rc[q].w, (int)rc[q].z);
-              const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
-              best = cand < best ? cand : best;
+              for (int q = 0; q < 4; q++) {
+                uint16_t ly = 0xffff;
+                if (rc[q].x != 0xffffffffu) ly = lid[rc[q].x];
+                if (first) {
+                  const bool need = ly != 0xffff && cls[ly] == INVALID;
+                  const unsigned m = __ballot_sync(0xffffffffu, need);
+                  if (need) {
+                    const int slot = cntw + __popc(m & lanemask_lt());
+                    if (slot < capw) ia_put(wid * capw + slot, ((uint32_t)x << 16) | ly, e0 + 8 * q);
+                  }
+                  cntw += __popc(m);
+                }
+                if (ly == 0xffff) continue;
+                const unsigned long long dyb = dist[ly];
+                if (dyb == T_INF) continue;
+                const double w = __hiloint2double((int)rc[q].w, (int)rc[q].z);
+                const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
+                best = cand < best ? cand : best;
+              }
             }
-          }
 #pragma unroll
-          for (int o = 4; o; o >>= 1) { const unsigned long long u2 = __shfl_xor_sync(gm, best, o); best = u2 < best ? u2 : best; }
-          if (l8 == 0 && it < nitems && best < dist[x] && best < atomicMin(&dist[x], best)) ch = 1;
+            for (int o = 4; o; o >>= 1) { const unsigned long long u2 = __shfl_xor_sync(gm, best, o); best = u2 < best ? u2 : best; }
+            if (l8 == 0 && b > a && best < dist[x] && best < atomicMin(&dist[x], best)) ch = 1;
+          }
         }
         return ch;
       };
       relax_rows(true);
-      __syncthreads();
-      const int nia = sh.nia;
-      const bool full = nia > 4 * n;
+      const bool full = __syncthreads_or(cntw > capw ? 1 : 0) != 0;
+      TPROF(5);
       for (int round = 1; round <= ninv + 1; round++) {
         int ch = 0;
         if (!full) {
-          for (int k = tid; k < nia; k += nt) {
+          for (int k = lane; k < cntw; k += 32) {
             uint32_t pr; int pos;
-            ia_get(k, pr, pos);
+            ia_get(wid * capw + k, pr, pos);
             const int x = (int)(pr >> 16), ly = (int)(pr & 0xffffu);
             const unsigned long long dyb = dist[ly];
             if (dyb == T_INF) continue;
@@ -481,12 +502,19 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         }
         if (!__syncthreads_or(ch)) break;
       }
+      TPROF(6);
+#ifdef T1_PROFILE
+      if (lane == 0) atomicAdd(&g_t1prof[15], (unsigned long long)cntw);
+      if (tid == 0) { atomicAdd(&g_t1prof[11], (unsigned long long)(full ? 1 : 0)); atomicAdd(&g_t1prof[12], 1ull); atomicAdd(&g_t1prof[13], (unsigned long long)nitems); atomicAdd(&g_t1prof[14], (unsigned long long)sh.dinv); }
+#endif
       // ---- 3. tree rule for the invalid vertices: smallest local id y (= smallest row position) with fl(d[y] + w) == d[x] ----
-      for (int it0 = 0; it0 < nitems; it0 += ngrp) {
-        const int it = it0 + grp;
-        int x = 0, a = 0, b = 0;
-        if (it < nitems) item_bounds(it, x, a, b);
-        const unsigned long long dxb = it < nitems ? dist[x] : T_INF;
+      for (int kb = 0; kb * ngrp < nitems; kb += 8) {
+        int mx = 0, ma = 0, mb = 0;
+        { const int itl = (kb + l8) * ngrp + grp; if (itl < nitems) item_bounds(itl, mx, ma, mb); }
+        for (int j = 0; j < 8; j++) {
+        const int x = __shfl_sync(gm, mx, j, 8), a = __shfl_sync(gm, ma, j, 8);
+        int b = __shfl_sync(gm, mb, j, 8);
+        const unsigned long long dxb = b > a ? dist[x] : T_INF;
         if (dxb == T_INF) b = a;
         int hit = 0x7fffffff;
         for (int e0 = a; e0 < b; e0 += 32) {   // (uniform over the group: the exit test below is a group vote)
@@ -507,12 +535,27 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
 #pragma unroll
         for (int o = 4; o; o >>= 1) hit = min(hit, __shfl_xor_sync(gm, hit, o));
         if (l8 == 0 && hit != 0x7fffffff) atomicMin(&bpos[x], hit);
+        }
       }
       __syncthreads();
-      for (int i = tid; i < ninv; i += nt) {
-        const int x = inv[i];
-        const int pos = bpos[x];
-        if (pos != 0x7fffffff) { parl[x] = lid[g.col[pos]]; tpw[x] = __dadd_rn(g.kappa[pos], 1.0); }
+      TPROF(7);
+      // parents of the invalid vertices; from here on the distances are not needed any more and every vertex's 8-byte slot
+      // holds the weight of its tree edge instead (the table's for a valid vertex), so that the walks of step 4 stay in
+      // shared memory
+      for (int x = tid; x < n; x += nt) {
+        unsigned long long wb = 0;
+        if (x != root) {
+          if (cls[x] == VALID) wb = (unsigned long long)__double_as_longlong(Wrow[vert[x]]);
+          else {
+            const int pos = bpos[x];
+            if (dist[x] != T_INF && pos != 0x7fffffff) {
+              const uint4 rc = __ldg(g.rec + pos);
+              parl[x] = lid[rc.x];
+              wb = ((unsigned long long)rc.w << 32) | rc.z;
+            } else cls[x] = UNREACH;
+          }
+        }
+        dist[x] = wb;
       }
       __syncthreads();
       TPROF(8);
@@ -522,15 +565,14 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         const uint8_t cl = cls[x];
         if (x == root) res = 0.0;
         else if (cl == VALID) { res = Qrow[vert[x]]; hnt[x] = (int32_t)parl[x]; }
-        else if (dist[x] == T_INF) res = 100.0;  // nx.NetworkXNoPath -> 100 (disconnected vicinity; status 3 later)
+        else if (cl == UNREACH) res = 100.0;  // nx.NetworkXNoPath -> 100 (disconnected vicinity; status 3 later)
         else {
           hnt[x] = (int32_t)parl[x];
           PySumT ps{0.0, 0.0, 0};
           int y = x, guard = 0;
           while (y != root && guard++ <= n) {
             const int py = (int)parl[y];
-            const double w = cls[y] == INVALID ? tpw[y] : Wrow[vert[y]];  // (a valid vertex's parent edge is the table's)
-            pyt_add(ps, w, plain);
+            pyt_add(ps, __longlong_as_double((long long)dist[y]), plain);
             y = py;
           }
           res = pyt_get(ps, plain);
@@ -622,7 +664,8 @@ void launch_filtration_table(const GraphView& g, const Params& p, const ChunkVie
     if (tot) {
       fprintf(stderr, "[1t profile]");
       for (int i = 0; i < 11; i++) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * (double)h[i] / (double)tot);
-      fprintf(stderr, " | total %.1f Mticks\n", (double)tot / 1e6);
+      fprintf(stderr, " | total %.1f Mticks | roots %llu, in full mode %llu, items/root %.0f, records/root %.0f, list entries/root %.0f\n", (double)tot / 1e6,
+              h[12], h[11], (double)h[13] / (double)(h[12] ? h[12] : 1), (double)h[14] / (double)(h[12] ? h[12] : 1), (double)h[15] / (double)(h[12] ? h[12] : 1));
     }
     memset(h, 0, sizeof h);
     cudaMemcpyToSymbol(g_t1prof, h, sizeof h);
