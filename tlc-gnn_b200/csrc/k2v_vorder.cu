@@ -58,18 +58,34 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
   uint32_t* p1 = sort_smem ? sort_base + 3 * sort_cap : reinterpret_cast<uint32_t*>(c.vs1 + vo);
   // normalised filtrations live in [0, 1]: a 24-bit fixed-point image floor(f * 2^24) is monotone too and saves a radix
   // pass; collisions (values closer than 6e-8) are equal-key runs, fixed below exactly like equal floats
+  // (the strided passes of this kernel stage four independent loads per thread before they use them: a vicinity has ~10
+  //  vertices per thread and every pass would otherwise pay one memory latency per vertex)
   int out_of_unit = 0;
-  for (int x = tid; x < n; x += nt) { const double f = fval[x]; out_of_unit |= !(f >= 0.0 && f <= 1.0); }
+  for (int x0 = tid; x0 < n; x0 += 4 * nt) {
+    double f4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) f4[u] = x0 + u * nt < n ? fval[x0 + u * nt] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) out_of_unit |= !(f4[u] >= 0.0 && f4[u] <= 1.0);
+  }
   const bool unit = __syncthreads_or(out_of_unit) == 0;
-  for (int x = tid; x < n; x += nt) {
-    if (unit) {
-      const double q = floor(fval[x] * 16777216.0);
-      k0[x] = q >= 16777215.0 ? 16777215u : (uint32_t)q;
-    } else {
-      const uint32_t b = (uint32_t)__float_as_int(__double2float_rd(fval[x]));
-      k0[x] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  for (int x0 = tid; x0 < n; x0 += 4 * nt) {
+    double f4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) f4[u] = x0 + u * nt < n ? fval[x0 + u * nt] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int x = x0 + u * nt;
+      if (x >= n) continue;
+      if (unit) {
+        const double q = floor(f4[u] * 16777216.0);
+        k0[x] = q >= 16777215.0 ? 16777215u : (uint32_t)q;
+      } else {
+        const uint32_t b = (uint32_t)__float_as_int(__double2float_rd(f4[u]));
+        k0[x] = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+      }
+      p0[x] = x;
     }
-    p0[x] = x;
   }
   __syncthreads();
   const int r = block_radix_sort<uint32_t>(k0, p0, k1, p1, n, unit ? 24 : 32, sh);
@@ -106,25 +122,48 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
   __syncthreads();
   // exact keys in sorted order (block cuts, distinct-value flags)
   unsigned long long* ks = (r ? c.v64a : c.v64b) + vo;  // the key buffer not holding kf
-  for (int i = tid; i < n; i += nt) ks[i] = f64_to_ordered(fval[ps[i]]);
+  for (int i0 = tid; i0 < n; i0 += 4 * nt) {
+    uint32_t x4[4];
+    double f4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) x4[u] = i0 + u * nt < n ? ps[i0 + u * nt] : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; u++) f4[u] = i0 + u * nt < n ? fval[x4[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (i0 + u * nt < n) ks[i0 + u * nt] = f64_to_ordered(f4[u]);
+  }
   __syncthreads();
   int32_t* flag = c.vs2 + vo;
   const double fmin = fval[ps[0]];
   const double pmin = __dmul_rn(__dadd_rn(fmin, 1.0), 1e-6);
-  for (int i = tid; i < n; i += nt) {
-    const int32_t x = (int32_t)ps[i];
-    vord[i] = x;
-    vrank[x] = i;
-    int f = 1;
-    if (i > 0) {
-      // same block as the predecessor unless every key owned by it is strictly below every key owned here
-      // (the exact values in sorted order were just written to ks[] as ordered bit patterns: decode instead of gathering)
-      const double fp = ordered_to_f64(ks[i - 1]), fx = ordered_to_f64(ks[i]);
-      const double hi_prev = __dadd_rn(fp, __dmul_rn(__dadd_rn(fp, 1.0), 1e-6));
-      const double lo_here = __dadd_rn(fx, pmin);
-      f = hi_prev < lo_here ? 1 : 0;
+  for (int i0 = tid; i0 < n; i0 += 4 * nt) {
+    uint32_t x4[4];
+    unsigned long long kp4[4], kx4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * nt;
+      x4[u] = i < n ? ps[i] : 0u;
+      kx4[u] = i < n ? ks[i] : 0ull;
+      kp4[u] = (i < n && i > 0) ? ks[i - 1] : 0ull;
     }
-    flag[i] = f;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * nt;
+      if (i >= n) continue;
+      const int32_t x = (int32_t)x4[u];
+      vord[i] = x;
+      vrank[x] = i;
+      int f = 1;
+      if (i > 0) {
+        // same block as the predecessor unless every key owned by it is strictly below every key owned here
+        // (the exact values in sorted order were just written to ks[] as ordered bit patterns: decode instead of gathering)
+        const double fp = ordered_to_f64(kp4[u]), fx = ordered_to_f64(kx4[u]);
+        const double hi_prev = __dadd_rn(fp, __dmul_rn(__dadd_rn(fp, 1.0), 1e-6));
+        const double lo_here = __dadd_rn(fx, pmin);
+        f = hi_prev < lo_here ? 1 : 0;
+      }
+      flag[i] = f;
+    }
   }
   __syncthreads();
   // ---- 2. blocks ----
@@ -138,12 +177,28 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
   // block index of every LOCAL id, in shared memory when it fits (16-bit when nb < 65536)
   const bool in_smem = n <= smem_ints;
   int32_t* sblk = in_smem ? dyn : c.vcls + vo;
-  for (int i = tid; i < n; i += nt) {
-    const int bidx = flag[i] - 1 + own[i];
-    sblk[ps[i]] = bidx;
-    if (i > 0 && !own[i] && ks[i] != ks[i - 1]) atomicOr(&bfirst[bidx], (int32_t)0x80000000);
-    // essential maximum: first rank attaining the largest value
-    if (ks[i] == ks[n - 1] && (i == 0 || ks[i - 1] != ks[n - 1])) c.tmaxv[t] = (int32_t)ps[i];
+  const unsigned long long klast = ks[n - 1];
+  for (int i0 = tid; i0 < n; i0 += 4 * nt) {
+    int fl4[4], ow4[4];
+    uint32_t x4[4];
+    unsigned long long kp4[4], kx4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * nt;
+      const bool ok = i < n;
+      fl4[u] = ok ? flag[i] : 0; ow4[u] = ok ? own[i] : 0; x4[u] = ok ? ps[i] : 0u;
+      kx4[u] = ok ? ks[i] : 0ull; kp4[u] = (ok && i > 0) ? ks[i - 1] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * nt;
+      if (i >= n) continue;
+      const int bidx = fl4[u] - 1 + ow4[u];
+      sblk[x4[u]] = bidx;
+      if (i > 0 && !ow4[u] && kx4[u] != kp4[u]) atomicOr(&bfirst[bidx], (int32_t)0x80000000);
+      // essential maximum: first rank attaining the largest value
+      if (kx4[u] == klast && (i == 0 || kp4[u] != klast)) c.tmaxv[t] = (int32_t)x4[u];
+    }
   }
   __syncthreads();
   const int32_t* __restrict__ astart = c.astart + vo;

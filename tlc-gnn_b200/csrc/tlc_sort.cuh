@@ -33,7 +33,13 @@ __device__ int block_radix_sort(K* k0, uint32_t* p0, K* k1, uint32_t* p1, int n,
     for (int d = tid; d < 256; d += nt) sh.hist[d] = 0;
     if (tid == 0) sh.flag = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) atomicAdd(&sh.hist[digit_of(kin[i], shift)], 1);
+    for (int i0 = tid; i0 < n; i0 += 4 * nt) {  // (four loads in flight per thread)
+      K k4[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) k4[u] = i0 + u * nt < n ? kin[i0 + u * nt] : (K)0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (i0 + u * nt < n) atomicAdd(&sh.hist[digit_of(k4[u], shift)], 1);
+    }
     __syncthreads();
     for (int d = tid; d < 256; d += nt) if (sh.hist[d] == n) sh.flag = 1;  // digit constant: skip the pass
     __syncthreads();
@@ -52,13 +58,19 @@ __device__ int block_radix_sort(K* k0, uint32_t* p0, K* k1, uint32_t* p1, int n,
       for (int i = tid; i < nw * 256; i += nt) (&sh.whist[0][0])[i] = 0;
       __syncthreads();
       K key[SORT_ITEMS];
+      uint32_t pay[SORT_ITEMS];
       int rnk[SORT_ITEMS];
       const int wbase = t0 + wid * 32 * SORT_ITEMS;
+#pragma unroll
+      for (int it = 0; it < SORT_ITEMS; it++) {  // (keys and payloads of the tile in flight together)
+        const int i = wbase + it * 32 + lane;
+        key[it] = i < n ? kin[i] : (K)0;
+        pay[it] = i < n ? pin[i] : 0u;
+      }
 #pragma unroll
       for (int it = 0; it < SORT_ITEMS; it++) {
         const int i = wbase + it * 32 + lane;
         const bool ok = i < n;
-        key[it] = ok ? kin[i] : (K)0;
         const int d = ok ? digit_of(key[it], shift) : (256 + lane);  // inactive lanes never match
         const unsigned mask = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(mask) - 1;
@@ -81,7 +93,7 @@ __device__ int block_radix_sort(K* k0, uint32_t* p0, K* k1, uint32_t* p1, int n,
         if (i < n) {
           const int pos = sh.whist[wid][digit_of(key[it], shift)] + rnk[it];
           kout[pos] = key[it];
-          pout[pos] = pin[i];
+          pout[pos] = pay[it];
         }
       }
       __syncthreads();
