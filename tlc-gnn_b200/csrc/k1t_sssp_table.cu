@@ -13,10 +13,11 @@
 //     (D_r[y] <= d_S[y] and D_r[x] is minimal), and P_r[x], the smallest candidate of G, lies in S with d_S = D_r;
 //   * hence the path and its python-order sum are Q_r[x].
 // The other vertices of S (their branch leaves S: 10-20 % on the Computers-shaped 2-hop vicinities, 0.3 % on the largest)
-// get their distance from the same fixpoint restricted to them, the valid vertices acting as settled sources: rounds of
-// "pull" relaxations over THEIR graph rows only, then the tree rule and the path walk (through computed parents, then
-// through the table once the walk reaches a valid vertex).  Results are bit-identical to kernel 1b (tests: the parity
-// suite runs both; TLC_F_NO_TABLE selects kernel 1b).
+// get their distance from the same fixpoint restricted to them, the valid vertices acting as settled sources: ONE pass of
+// "pull" relaxations over THEIR graph rows (which also lists the adjacencies among the invalid vertices), further rounds
+// over that list only, then the tree rule and the path walk (parents and tree-edge weights of all vertices in shared
+// memory by then).  Results are bit-identical to kernel 1b (tests: the parity suite runs both; TLC_F_NO_TABLE selects
+// kernel 1b).
 //
 // Rows read per target drop from 2 x D_S (every row of the vicinity, once per root) to the rows of the invalid
 // vertices; the table rows of u and v (D, Q, W, P: 28 N bytes each) are streamed instead.
