@@ -95,13 +95,32 @@ class graph2pi():
         return self
 
     # -- helpers ---------------------------------------------------------------------------------
+    def _label_lut(self):
+        """label -> id table for non-negative integer labels that are not much larger than N (a searchsorted over the
+        call's 2E endpoints costs 0.7 - 1.5 ms per 4096 targets: as much as a tenth of the GPU step); else None"""
+        lut = getattr(self, "_lut", None)
+        if lut is None:
+            lab, new = self._int_labels
+            if len(lab) and lab[0] >= 0 and lab[-1] < 8 * len(lab) + 1024:
+                lut = np.full(int(lab[-1]) + 1, -1, dtype=np.int32)
+                lut[lab] = new
+            else:
+                lut = False
+            self._lut = lut
+        return None if lut is False else lut
+
     def _map_targets(self, total_edges):
         if self._int_labels is not None:
             try:
                 t = np.asarray(total_edges)
                 if t.ndim == 2 and t.shape[1] >= 2 and np.issubdtype(t.dtype, np.integer):
                     lab, new = self._int_labels
-                    t = t[:, :2].astype(np.int64)
+                    t = t[:, :2]
+                    lut = self._label_lut()
+                    if lut is not None:   # dense table label -> id (-1: not a node); ids 0..N-1 map to themselves
+                        ok = (t >= 0) & (t < len(lut))
+                        return np.where(ok, lut[np.where(ok, t, 0)], -1).astype(np.int32)
+                    t = t.astype(np.int64)
                     idx = np.clip(np.searchsorted(lab, t), 0, len(lab) - 1)
                     return np.where(lab[idx] == t, new[idx], -1).astype(np.int32)
             except Exception:
