@@ -230,7 +230,7 @@ struct TableShared {
   int32_t any;
 };
 #ifdef T1_PROFILE
-__device__ unsigned long long g_t1prof[16];
+__device__ unsigned long long g_t1prof[24];
 #define TPROF(i) do { if (tid == 0) { const long long tnow_ = clock64(); atomicAdd(&g_t1prof[i], (unsigned long long)(tnow_ - tprev_)); tprev_ = tnow_; } } while (0)
 #else
 #define TPROF(i) do { } while (0)
@@ -409,12 +409,15 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
       // pays a 32-lane reduction per row -- both measured slower).  Four loads in flight per lane, a 3-step reduction.
       const int l8 = lane & 7, grp = tid >> 3, ngrp = nt >> 3;
       const unsigned gm = 0xffu << (lane & 24);  // the lanes of this 8-lane group
-      auto item_bounds = [&](int i, int& x, int& a, int& b) {
-        const int pk = i < ninv ? (inv[i] << 12) : extra[i - ninv];
+      constexpr int ITEM_RESCAN = 1 << 30;  // item flag: its invalid neighbours did not all fit the list -> later rounds reread the chunk
+      auto item_bounds = [&](int i, int& x, int& a, int& b, bool flagged_only) {
+        const int raw = i < ninv ? inv[i] : extra[i - ninv];
+        const int pk = i < ninv ? ((raw & 0xffff) << 12) : (raw & (ITEM_RESCAN - 1));
         x = pk >> 12;
         const int ra = c.astart[vo + x];
         a = ra + (pk & 4095) * chunk;
         b = min(ra + c.adeg[vo + x], a + chunk);
+        if (flagged_only && !(raw & ITEM_RESCAN)) b = a;
       };
       // The FIRST round reads every invalid row once.  The valid neighbours' distances are final: their candidates never
       // need a second look.  The invalid neighbours go into a list of (vertex, neighbour, row position) entries -- the
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         for (int kb = 0; kb * ngrp < nitems; kb += 8) {   // (uniform trip counts: the shuffles below are group-wide)
           // the group's next eight items, their bounds fetched lane-parallel (vertex -> row start, degree: a dependent chain)
           int mx = 0, ma = 0, mb = 0;
-          { const int itl = (kb + l8) * ngrp + grp; if (itl < nitems) item_bounds(itl, mx, ma, mb); }
+          { const int itl = (kb + l8) * ngrp + grp; if (itl < nitems) item_bounds(itl, mx, ma, mb, !first); }
           for (int j = 0; j < 8; j++) {
             const int x = __shfl_sync(gm, mx, j, 8), a = __shfl_sync(gm, ma, j, 8), b = __shfl_sync(gm, mb, j, 8);
             int trips = (b - a + 31) >> 5;  // the longest of the warp's four chunks: the votes below are warp-wide
@@ -478,40 +481,74 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
 #pragma unroll
             for (int o = 4; o; o >>= 1) { const unsigned long long u2 = __shfl_xor_sync(gm, best, o); best = u2 < best ? u2 : best; }
             if (l8 == 0 && b > a && best < dist[x] && best < atomicMin(&dist[x], best)) ch = 1;
+            if (first && cntw > capw && l8 == 0 && b > a) {  // the warp's region is full: this chunk stays on the row path
+              const int itj = (kb + j) * ngrp + grp;
+              if (itj < ninv) inv[itj] |= ITEM_RESCAN; else extra[itj - ninv] |= ITEM_RESCAN;
+            }
           }
         }
         return ch;
       };
       relax_rows(true);
-      const bool full = __syncthreads_or(cntw > capw ? 1 : 0) != 0;
+      const bool full = __syncthreads_or(cntw > capw ? 1 : 0) != 0;  // some chunks are flagged for rereading
       TPROF(5);
+      const int nlist = min(cntw, capw);
+      // the first 128 entries of the warp's region stay in registers over the rounds (vertex pair + edge weight): a round is
+      // then shared-memory work only, not two dependent global loads per entry
+      uint32_t epr[4];
+      double ewt[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int k = lane + 32 * i;
+        epr[i] = 0xffffffffu; ewt[i] = 0.0;
+        if (k < nlist) {
+          int pos;
+          ia_get(wid * capw + k, epr[i], pos);
+          const uint4 rc = __ldg(g.rec + pos);
+          ewt[i] = __hiloint2double((int)rc.w, (int)rc.z);
+        }
+      }
+#ifdef T1_PROFILE
+      long long tlr0_ = clock64();
+      int nrounds_ = 0;
+#endif
       for (int round = 1; round <= ninv + 1; round++) {
         int ch = 0;
-        if (!full) {
-          for (int k = lane; k < cntw; k += 32) {
-            uint32_t pr; int pos;
-            ia_get(wid * capw + k, pr, pos);
-            const int x = (int)(pr >> 16), ly = (int)(pr & 0xffffu);
-            const unsigned long long dyb = dist[ly];
-            if (dyb == T_INF) continue;
-            const uint4 rc = __ldg(g.rec + pos);
-            const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __hiloint2double((int)rc.w, (int)rc.z)));
-            if (cand < dist[x] && cand < atomicMin(&dist[x], cand)) ch = 1;
-          }
-        } else {
-          ch = relax_rows(false);
+#ifdef T1_PROFILE
+        nrounds_++;
+#endif
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (epr[i] == 0xffffffffu) continue;
+          const int x = (int)(epr[i] >> 16), ly = (int)(epr[i] & 0xffffu);
+          const unsigned long long dyb = dist[ly];
+          if (dyb == T_INF) continue;
+          const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), ewt[i]));
+          if (cand < dist[x] && cand < atomicMin(&dist[x], cand)) ch = 1;
         }
+        for (int k = lane + 128; k < nlist; k += 32) {
+          uint32_t pr; int pos;
+          ia_get(wid * capw + k, pr, pos);
+          const int x = (int)(pr >> 16), ly = (int)(pr & 0xffffu);
+          const unsigned long long dyb = dist[ly];
+          if (dyb == T_INF) continue;
+          const uint4 rc = __ldg(g.rec + pos);
+          const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __hiloint2double((int)rc.w, (int)rc.z)));
+          if (cand < dist[x] && cand < atomicMin(&dist[x], cand)) ch = 1;
+        }
+        if (full) ch |= relax_rows(false);  // the flagged chunks, from their rows
         if (!__syncthreads_or(ch)) break;
       }
       TPROF(6);
 #ifdef T1_PROFILE
       if (lane == 0) atomicAdd(&g_t1prof[15], (unsigned long long)cntw);
+      if (tid == 0) { atomicAdd(&g_t1prof[17], (unsigned long long)nrounds_); if (full) atomicAdd(&g_t1prof[16], (unsigned long long)(clock64() - tlr0_)); }
       if (tid == 0) { atomicAdd(&g_t1prof[11], (unsigned long long)(full ? 1 : 0)); atomicAdd(&g_t1prof[12], 1ull); atomicAdd(&g_t1prof[13], (unsigned long long)nitems); atomicAdd(&g_t1prof[14], (unsigned long long)sh.dinv); }
 #endif
       // ---- 3. tree rule for the invalid vertices: smallest local id y (= smallest row position) with fl(d[y] + w) == d[x] ----
       for (int kb = 0; kb * ngrp < nitems; kb += 8) {
         int mx = 0, ma = 0, mb = 0;
-        { const int itl = (kb + l8) * ngrp + grp; if (itl < nitems) item_bounds(itl, mx, ma, mb); }
+        { const int itl = (kb + l8) * ngrp + grp; if (itl < nitems) item_bounds(itl, mx, ma, mb, false); }
         for (int j = 0; j < 8; j++) {
         const int x = __shfl_sync(gm, mx, j, 8), a = __shfl_sync(gm, ma, j, 8);
         int b = __shfl_sync(gm, mb, j, 8);
@@ -656,7 +693,7 @@ void launch_filtration_table(const GraphView& g, const Params& p, const ChunkVie
   cudaFuncSetAttribute((const void*)filtration_table_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #ifdef T1_PROFILE
   if (getenv("T1_PROFILE_DUMP")) {  // ticks of thread 0 per phase, summed over the CTAs since the last dump
-    unsigned long long h[16];
+    unsigned long long h[24];
     cudaMemcpyFromSymbol(h, g_t1prof, sizeof h);
     static const char* nm[11] = {"prologue", "class_init", "class_rounds", "compaction", "chunks", "first_round", "later_rounds",
                                  "tree_rule", "parents", "path_sums", "descriptors"};
@@ -665,8 +702,9 @@ void launch_filtration_table(const GraphView& g, const Params& p, const ChunkVie
     if (tot) {
       fprintf(stderr, "[1t profile]");
       for (int i = 0; i < 11; i++) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * (double)h[i] / (double)tot);
-      fprintf(stderr, " | total %.1f Mticks | roots %llu, in full mode %llu, items/root %.0f, records/root %.0f, list entries/root %.0f\n", (double)tot / 1e6,
+      fprintf(stderr, " | total %.1f Mticks | roots %llu, with flagged chunks %llu, items/root %.0f, records/root %.0f, list entries/root %.0f\n", (double)tot / 1e6,
               h[12], h[11], (double)h[13] / (double)(h[12] ? h[12] : 1), (double)h[14] / (double)(h[12] ? h[12] : 1), (double)h[15] / (double)(h[12] ? h[12] : 1));
+      fprintf(stderr, "[1t profile] later rounds per root %.2f; ticks of the later rounds spent in roots with flagged chunks: %.1f Mticks\n", (double)h[17] / (double)(h[12] ? h[12] : 1), (double)h[16] / 1e6);
     }
     memset(h, 0, sizeof h);
     cudaMemcpyToSymbol(g_t1prof, h, sizeof h);

@@ -168,7 +168,13 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
   __syncthreads();
   // ---- 2. blocks ----
   int32_t* own = reinterpret_cast<int32_t*>(r ? p0 : p1);  // the payload buffer not holding the result
-  for (int i = tid; i < n; i += nt) own[i] = flag[i];
+  for (int i0 = tid; i0 < n; i0 += 4 * nt) {
+    int f4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) f4[u] = i0 + u * nt < n ? flag[i0 + u * nt] : 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (i0 + u * nt < n) own[i0 + u * nt] = f4[u];
+  }
   __syncthreads();
   const int nb = block_exclusive_scan(flag, n, sh.scan);  // flag[i] = #starts before i
   for (int i = tid; i < n; i += nt) if (own[i]) bfirst[flag[i]] = i | 0x40000000;  // bit 30 cleared below where it fails
@@ -216,16 +222,29 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
     }
     const uint32_t* __restrict__ bm = bm_in_smem ? sbm : gbm;
     const int32_t* __restrict__ gcol = c.gcol;
-    for (int x = tid; x < n; x += nt) {
-      const int bx = sblk[x];
-      const int a = astart[x], dg = adeg[x];
-      const int h = hint[x], h0 = hint0 ? hint0[x] : -1;  // kernel 1b's tree parents: usually already in an earlier block
-      bool has = (h >= 0 && sblk[h] < bx) || (h0 >= 0 && sblk[h0] < bx);
-      for (int j = 0; j < dg && !has && bx > 0; j++) {
-        const int y = bitmap_rank(bm, c.W, gcol[a + j]);
-        has = y >= 0 && sblk[y] < bx;
+    for (int x0 = tid; x0 < n; x0 += 4 * nt) {
+      int a4[4], dg4[4], h4[4], h04[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {  // (the four vertices' row bounds and tree-parent hints in flight together)
+        const int x = x0 + u * nt;
+        const bool ok = x < n;
+        a4[u] = ok ? astart[x] : 0; dg4[u] = ok ? adeg[x] : 0;
+        h4[u] = ok ? hint[x] : -1; h04[u] = (ok && hint0) ? hint0[x] : -1;
       }
-      if (!has) atomicAnd(&bfirst[bx], (int32_t)~0x40000000);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int x = x0 + u * nt;
+        if (x >= n) continue;
+        const int bx = sblk[x];
+        const int a = a4[u], dg = dg4[u];
+        const int h = h4[u], h0 = h04[u];  // kernel 1b / 1t's tree parents: usually already in an earlier block
+        bool has = (h >= 0 && sblk[h] < bx) || (h0 >= 0 && sblk[h0] < bx);
+        for (int j = 0; j < dg && !has && bx > 0; j++) {
+          const int y = bitmap_rank(bm, c.W, gcol[a + j]);
+          has = y >= 0 && sblk[y] < bx;
+        }
+        if (!has) atomicAnd(&bfirst[bx], (int32_t)~0x40000000);
+      }
     }
     return;
   }
