@@ -421,7 +421,8 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
       };
       // The FIRST round reads every invalid row once.  The valid neighbours' distances are final: their candidates never
       // need a second look.  The invalid neighbours go into a list of (vertex, neighbour, row position) entries -- the
-      // graph among the invalid vertices, a few entries per vertex -- and the following rounds run over that list only
+      // graph among the invalid vertices, a few entries per vertex, every pair once (weights are symmetric, the later
+      // rounds relax an entry both ways) -- and the following rounds run over that list only
       // (measured: 3 rounds, the second changes 2 - 5 % of the vertices, the third none).  A list that outgrows its 4n
       // slots (small vicinities that are mostly invalid) sends the root back to rounds over the rows.
       auto ia_put = [&](int k, uint32_t pr, int pos) {
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
                 uint16_t ly = 0xffff;
                 if (rc[q].x != 0xffffffffu) ly = lid[rc[q].x];
                 if (first) {
-                  const bool need = ly != 0xffff && cls[ly] == INVALID;
+                  const bool need = ly != 0xffff && (int)ly > x && cls[ly] == INVALID;  // (a pair is listed once, by its smaller end)
                   const unsigned m = __ballot_sync(0xffffffffu, need);
                   if (need) {
                     const int slot = cntw + __popc(m & lanemask_lt());
@@ -471,9 +472,16 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
                   cntw += __popc(m);
                 }
                 if (ly == 0xffff) continue;
-                const unsigned long long dyb = dist[ly];
-                if (dyb == T_INF) continue;
                 const double w = __hiloint2double((int)rc[q].w, (int)rc[q].z);
+                const unsigned long long dyb = dist[ly];
+                if (!first && cls[ly] == INVALID) {  // a reread chunk also pushes: the pairs it would have listed go both ways
+                  const unsigned long long dxb = dist[x];
+                  if (dxb != T_INF) {
+                    const unsigned long long c2 = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dxb), w));
+                    if (c2 < dyb && c2 < atomicMin(&dist[ly], c2)) ch = 1;
+                  }
+                }
+                if (dyb == T_INF) continue;
                 const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
                 best = cand < best ? cand : best;
               }
@@ -521,20 +529,32 @@ __global__ void __launch_bounds__(1024) filtration_table_kernel(Params p, ChunkV
         for (int i = 0; i < 4; i++) {
           if (epr[i] == 0xffffffffu) continue;
           const int x = (int)(epr[i] >> 16), ly = (int)(epr[i] & 0xffffu);
-          const unsigned long long dyb = dist[ly];
-          if (dyb == T_INF) continue;
-          const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), ewt[i]));
-          if (cand < dist[x] && cand < atomicMin(&dist[x], cand)) ch = 1;
+          const unsigned long long dyb = dist[ly], dxb = dist[x];
+          if (dyb != T_INF) {
+            const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), ewt[i]));
+            if (cand < dxb && cand < atomicMin(&dist[x], cand)) ch = 1;
+          }
+          if (dxb != T_INF) {
+            const unsigned long long c2 = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dxb), ewt[i]));
+            if (c2 < dyb && c2 < atomicMin(&dist[ly], c2)) ch = 1;
+          }
         }
         for (int k = lane + 128; k < nlist; k += 32) {
           uint32_t pr; int pos;
           ia_get(wid * capw + k, pr, pos);
           const int x = (int)(pr >> 16), ly = (int)(pr & 0xffffu);
-          const unsigned long long dyb = dist[ly];
-          if (dyb == T_INF) continue;
+          const unsigned long long dyb = dist[ly], dxb = dist[x];
+          if (dyb == T_INF && dxb == T_INF) continue;
           const uint4 rc = __ldg(g.rec + pos);
-          const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), __hiloint2double((int)rc.w, (int)rc.z)));
-          if (cand < dist[x] && cand < atomicMin(&dist[x], cand)) ch = 1;
+          const double w = __hiloint2double((int)rc.w, (int)rc.z);
+          if (dyb != T_INF) {
+            const unsigned long long cand = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dyb), w));
+            if (cand < dxb && cand < atomicMin(&dist[x], cand)) ch = 1;
+          }
+          if (dxb != T_INF) {
+            const unsigned long long c2 = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)dxb), w));
+            if (c2 < dyb && c2 < atomicMin(&dist[ly], c2)) ch = 1;
+          }
         }
         if (full) ch |= relax_rows(false);  // the flagged chunks, from their rows
         if (!__syncthreads_or(ch)) break;
