@@ -160,3 +160,39 @@ def test_kd_emitter_batching_logic():
     for lo, hi in b:
         assert hi > lo and (cost[lo:hi].sum() <= 200 or hi - lo == 1)          # an oversized vicinity travels alone
     assert kd._batches(FakeGraph(n, m), tg, 2, 0, budget=10 ** 9) == [(0, len(n))]
+
+
+def test_mirror_label_mapping_paths():
+    """graph2pi._map_targets: node label -> dense id as the reference's dict_node lookup (riccidist2dgm.py:353: a label that
+    is not a node gives a zero row, here id -1) -- through the dense table (small non-negative labels), the searchsorted
+    path (huge / negative labels) and the per-element dict path (non-integer labels); all three agree with a plain dict."""
+    import sg2dgm.riccidist2dgm as mirror
+    rng = np.random.default_rng(3)
+    N = 500
+
+    def make(labels):
+        g = mirror.graph2pi.__new__(mirror.graph2pi)
+        lab = np.asarray(labels, dtype=np.int64)
+        o = np.argsort(lab, kind="stable")
+        g._int_labels = (lab[o], o.astype(np.int32))
+        g.N = N
+        g.dict_node = {int(l): i for i, l in enumerate(labels)}
+        return g
+
+    for labels, lo, hi, want_lut in ((np.arange(N), -5, N + 5, True),                       # identity
+                                     (rng.permutation(3 * N)[:N], -5, 3 * N + 5, True),       # small sparse labels
+                                     (rng.permutation(10 ** 7)[:N] * 1000, 0, 10 ** 10, False),  # huge labels: no table
+                                     (rng.permutation(4 * N)[:N] - 2 * N, -2 * N - 5, 2 * N + 5, False)):  # negative labels
+        g = make(labels)
+        assert (g._label_lut() is not None) == want_lut
+        pool = np.concatenate([np.asarray(labels), rng.integers(lo, hi, size=200)])
+        t = rng.choice(pool, size=(300, 2))
+        got = g._map_targets(t)
+        exp = np.array([[g.dict_node.get(int(a), -1), g.dict_node.get(int(b), -1)] for a, b in t], dtype=np.int32)
+        assert got.dtype == np.int32 and np.array_equal(got, exp)
+        assert np.array_equal(g._map_targets(t.astype(np.int32) if t.max() < 2 ** 31 and t.min() >= -2 ** 31 else t), exp)
+    # non-integer labels: the dict path
+    g = mirror.graph2pi.__new__(mirror.graph2pi)
+    g._int_labels = None
+    g.dict_node = {"a": 0, "b": 1, "c": 2}
+    assert g._map_targets([("a", "c"), ("b", "zz")]).tolist() == [[0, 2], [1, -1]]
