@@ -617,6 +617,29 @@ def run_cuda(args):
                     "stage_alg_gbytes_per_step": {k: v / 1e9 / args.steps for k, v in sab.items()},
                     "whole_path": {"compulsory_bytes_per_target": alg_bytes / max(1, live),
                                    "achieved_gbs": (alg_bytes / 1e9) / max(elapsed, 1e-12)}}
+        # image kernel (kernel 4): diagram points per target from a small detail call outside the timed region, flops from
+        # 50 float64 FMA + 12 erfc per point with non-zero weight
+        image_kernel = None
+        if world == 1 and args.mode == "edge":
+            try:
+                smp = batch_targets(ne, perm, 900, rank, world, min(8, B))
+                dd = g.vicinity_detail(smp, hop=args.hop, flags=flags)
+                kk = []
+                for i in range(len(smp)):
+                    a = g.per_target(dd, i)
+                    if a["status"] <= 1:
+                        kk.append(int(np.count_nonzero(a["pdeath"] > a["pbirth"])))
+                kbar = float(np.mean(kk)) if kk else 0.0
+                img_ms = stage_acc.get("image", 0.0) / max(1, args.steps)
+                pts = kbar * live / max(1, args.steps)
+                image_kernel = {"points_per_target": kbar, "sample": len(kk), "fma_per_point": 50, "erfc_per_point": 12,
+                                "ms_per_step": img_ms,
+                                "fma_tflops": (2.0 * 50 * pts / 1e12) / max(img_ms / 1e3, 1e-12),
+                                "erfc_per_s": (12 * pts) / max(img_ms / 1e3, 1e-12),
+                                "note": "points = pairs with death > birth (weight > 0) in a detail call over a sample of the "
+                                        "workload's targets; float64 CUDA-core work, 1 % of the step: no roofline claimed"}
+            except Exception as ex:  # never fail the headline over the side measurement
+                image_kernel = {"error": str(ex)[:200]}
         handoff = None
         if world == 1:
             try:
@@ -640,7 +663,8 @@ def run_cuda(args):
                 "handed_back_per_step": handed_back / args.steps, "kernel_S_last_step": ks_last,
                 "table_route_last_step": table_rows_last, "sssp_table_build_ms_one_time": table_build_ms, "edge_census": census,
                 "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "handoff": handoff, "secondary": secondary}
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "handoff": handoff, "image_kernel": image_kernel,
+                "secondary": secondary}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
