@@ -317,7 +317,7 @@ def test_structural_filtrations(filt):
     g.close()
 
 
-def test_handed_back_targets_on_the_graph_row_route():
+def test_handed_back_targets_on_the_graph_row_route(monkeypatch):
     """a near-tie block that needs more representatives than kernel 3v keeps (a clique of 24 common neighbours whose values
     differ by ~1e-10): the targets are handed back; on the graph-row batch call exactly those are redone on the
     materialised route and scattered back into the caller's rows."""
@@ -342,8 +342,14 @@ def test_handed_back_targets_on_the_graph_row_route():
     og = orc.OracleGraph(*csr)
     tg = np.concatenate([ne[:40], ne[-50:]]).astype(np.int32)
     o = og.run_batch(tg, hop=2, flags=orc.F_NORM)
+    # (kernel 2v's no-pair certificate settles the clique targets before any sweep: every clique vertex has a root as a far
+    #  lower neighbour.  Off for the hand-back check, on again below: the rows must not change.)
+    monkeypatch.setenv("TLC_NO_FAST_DIAGRAM", "1")
     pi, status, cnt = g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_DIRECT)
     cn = g.last_counts()
+    monkeypatch.delenv("TLC_NO_FAST_DIAGRAM")
+    pi_c, status_c, cnt_c = g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_DIRECT)
+    assert np.array_equal(pi_c, pi) and np.array_equal(status_c, status) and cnt_c == cnt
     assert cn["handed_back"] > 0 and 0 < cn["graph_row_route"] < cn["live"]      # some redone, the rest stayed on the route
     assert np.array_equal(status, o["status"]) and cnt == o["cnt_compute"] and rel_err(pi, o["pi"]) < IMG_TOL
     pi_m, status_m, cnt_m = g.vicinity_pi(tg, hop=2, flags=L.F_NORM | L.F_NO_DIRECT)

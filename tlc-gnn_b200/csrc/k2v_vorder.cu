@@ -43,6 +43,152 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
   int32_t* vrank = c.vrank + vo;
   int32_t* bfirst = c.bfirst + vo + t;
 
+  // ---- 0. certificate: a filtration whose only local minimum is the root plateau has NO ordinary pair ----
+  // With delta = 1e-8 call a vertex x (other than the roots)
+  //   A  if it has a neighbour y with f_y < f_x - delta;
+  //   B  if it is not A, has NO neighbour with f_x - delta <= f_y < f_x or f_x < f_y <= f_x + delta, and an exactly equal
+  //      neighbour; B is GROUNDED if a chain of exactly equal neighbours leads to an A vertex.
+  // If the roots carry 0, are adjacent (or one), and every other vertex is A or grounded B, the reference's sweep
+  // (accelerated_PD.py:40-68) emits no pair at all:
+  //   * the edge u-v has the smallest possible key 1e-6 and comes first;
+  //   * the first edge of an A vertex x, in (key, position) order, is a descent edge to its lowest neighbour y* -- key
+  //     fl(f_x + fl(fl(f_y* + 1) * 1e-6)) lies >= 90 ulps below the key of every edge in which x is the smaller or an
+  //     equal end -- and by induction over the keys y* already hangs on the roots' component: x joins as a singleton of
+  //     value f_x at an edge of larger value f_x, `old[large] < old[max_node]` (:65) is false;
+  //   * the edges among equal values F all carry ONE key, above the first edges of the A vertices of value F and >= 1e-14
+  //     below every edge from a B vertex of value F to a higher neighbour (delta apart); they merge components whose
+  //     minima are F or 0 at edges of larger value F: false again; after them every grounded B vertex is attached.
+  // The diagram is then the essential pair [min, max] alone and the vicinity is connected.  Distance-to-roots filtrations
+  // look like this (the headline shape: one point per diagram), so the sort, the block cuts and the sweep are skipped for
+  // such targets: kernel 3v sees tnb = -1.  Near-ties (the perturbed-key crossings of SURVEY.md F4) fail the tests above
+  // and take the full path.  Only on the graph-row route (batch calls; diagram / detail calls run everything), never with
+  // keep-zero pairs (KD flags).
+  if (c.dbm && !(p.flags & TLC_F_KEEP_ZERO) && !c.no_fast) {
+    __shared__ unsigned long long s_fmax;
+    __shared__ int s_arg, s_adj, s_ncand;
+    constexpr double DELTA = 1e-8;
+    const int lu = c.tlu[t], lv = c.tlv[t];
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    int bad = (lu < 0 || lv < 0) ? 1 : 0;
+    if (tid == 0) { s_fmax = 0ull; s_arg = 0x7fffffff; s_adj = (lu == lv) ? 1 : 0; s_ncand = 0; }
+    __syncthreads();
+    const int32_t* __restrict__ astart0 = c.astart + vo;
+    const int32_t* __restrict__ adeg0 = c.adeg + vo;
+    const int32_t* __restrict__ h1 = c.neg + vo;
+    const int32_t* __restrict__ h0 = c.vcls + vo;
+    const uint32_t* __restrict__ gbm0 = c.dbm + (size_t)t * 2 * c.W;
+    const int32_t* __restrict__ gcol0 = c.gcol;
+    int32_t* cand = c.vs1 + vo;   // vertices the tree-parent hints do not settle
+    int32_t* vcl = c.vs2 + vo;    // 1: A or grounded B, 2: B not grounded yet
+    if (!bad) {
+      unsigned long long mymax = 0ull;
+      for (int x0 = tid; x0 < n; x0 += 4 * nt) {
+        double f4[4];
+        int a4[4], b4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int x = x0 + u * nt;
+          f4[u] = x < n ? fval[x] : 0.0; a4[u] = x < n ? h1[x] : -1; b4[u] = x < n ? h0[x] : -1;
+        }
+        double fa4[4], fb4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { fa4[u] = a4[u] >= 0 ? fval[a4[u]] : 2.0; fb4[u] = b4[u] >= 0 ? fval[b4[u]] : 2.0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int x = x0 + u * nt;
+          if (x >= n) continue;
+          const double fx = f4[u];
+          const unsigned long long ko = f64_to_ordered(fx);
+          mymax = ko > mymax ? ko : mymax;
+          if (x == lu || x == lv) { if (fx != 0.0) bad = 1; vcl[x] = 1; continue; }
+          if (!(fx > 0.0)) { bad = 1; continue; }
+          const double lim = fx - DELTA;
+          if (fa4[u] < lim || fb4[u] < lim) vcl[x] = 1;
+          else { vcl[x] = 0; cand[atomicAdd(&s_ncand, 1)] = x; }
+        }
+      }
+      atomicMax(&s_fmax, mymax);
+      if (lu != lv) {  // the two roots must be adjacent
+        const int32_t gv = c.vert[vo + lv];
+        const int a = astart0[lu], dg = adeg0[lu];
+        int f = 0;
+        for (int j = tid; j < dg; j += nt) f |= gcol0[a + j] == gv;
+        if (f) s_adj = 1;
+      }
+    }
+    bad = __syncthreads_or(bad);
+    if (!bad && !s_adj) bad = 1;
+    if (!bad) {
+      // the candidates, a warp per row: A after all, B, or neither
+      const int ncand = s_ncand;
+      for (int i = wid; i < ncand; i += nw) {
+        const int x = cand[i];
+        const double fx = fval[x];
+        const int a = astart0[x], dg = adeg0[x];
+        int fl = 0;  // bit 0: lower by more than delta, 1: lower within delta, 2: equal, 3: higher within delta
+        for (int j = lane; j < dg; j += 32) {
+          const int y = bitmap_rank(gbm0, c.W, gcol0[a + j]);
+          if (y < 0) continue;
+          const double fy = fval[y];
+          if (fy < fx - DELTA) fl |= 1;
+          else if (fy < fx) fl |= 2;
+          else if (fy == fx) fl |= 4;
+          else if (fy <= fx + DELTA) fl |= 8;
+        }
+        for (int o = 16; o; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+        if (lane == 0) {
+          if (fl & 1) vcl[x] = 1;
+          else if ((fl & (2 | 8)) || !(fl & 4)) bad = 1;
+          else vcl[x] = 2;
+        }
+      }
+    }
+    bad = __syncthreads_or(bad);
+    if (!bad) {
+      // grounding of the B vertices along exactly equal neighbours
+      const int ncand = s_ncand;
+      for (int round = 0; round <= ncand; round++) {
+        int ch = 0, left = 0;
+        for (int i = wid; i < ncand; i += nw) {
+          const int x = cand[i];
+          if (vcl[x] != 2) continue;
+          const double fx = fval[x];
+          const int a = astart0[x], dg = adeg0[x];
+          int g1 = 0;
+          for (int j = lane; j < dg && !g1; j += 32) {
+            const int y = bitmap_rank(gbm0, c.W, gcol0[a + j]);
+            if (y >= 0 && fval[y] == fx && vcl[y] == 1) g1 = 1;
+          }
+          g1 = __any_sync(0xffffffffu, g1);
+          if (g1) { if (lane == 0) vcl[x] = 1; ch = 1; } else left = 1;
+        }
+        const int anych = __syncthreads_or(ch);
+        const int anyleft = __syncthreads_or(left);
+        if (!anyleft) break;
+        if (!anych) { bad = 1; break; }
+      }
+    }
+    bad = __syncthreads_or(bad);
+    if (!bad) {
+      const unsigned long long km = s_fmax;
+      for (int x = tid; x < n; x += nt) if (f64_to_ordered(fval[x]) == km) atomicMin(&s_arg, x);
+      __syncthreads();
+      if (tid == 0) {
+        const int lmin = min(lu, lv), lmax = s_arg;
+        const int64_t po = c.poff(t);
+        c.tnb[t] = -1;  // kernel 3v: nothing to sweep
+        c.tminv[t] = lmin; c.tmaxv[t] = lmax;
+        c.pkind[po] = TLC_K_ESS;               // [min_value, max_value]   accelerated_PD.py:110
+        c.pbv[po] = lmin; c.pdv[po] = lmax;
+        c.pbirth[po] = fval[lmin]; c.pdeath[po] = fval[lmax];
+        c.tnp[t] = 1;
+        c.tnneg[t] = 0; c.tnpos[t] = 0;
+      }
+      return;
+    }
+    __syncthreads();
+  }
+
   // ---- 1. vertex order ----
   // 32-bit pass: stable LSD radix sort on the order-preserving image of the value rounded DOWN to float (monotone,
   // so only vertices sharing a float can be out of place); then every run of equal floats is put into exact
@@ -273,7 +419,9 @@ void launch_vorder(const Params& p, const ChunkView& c, int t0, int cnt, int blo
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   cudaFuncSetAttribute((const void*)vorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (const char* env = getenv("TLC_VORDER_BLOCK")) block = atoi(env);  // (tuning experiments)
-  vorder_kernel<<<cnt, block, bytes, st>>>(p, c, t0, smem_ints, bm_in_smem, sort_cap);
+  ChunkView c2 = c;
+  c2.no_fast = getenv("TLC_NO_FAST_DIAGRAM") ? 1 : 0;  // (parity experiments: every target through the sort and the sweep)
+  vorder_kernel<<<cnt, block, bytes, st>>>(p, c2, t0, smem_ints, bm_in_smem, sort_cap);
   count_launch();
 }
 

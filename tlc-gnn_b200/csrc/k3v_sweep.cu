@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(Params p, Chunk
   RepBuf& rb = reps_all[wid];
   const bool keep0 = (p.flags & TLC_F_KEEP_ZERO) != 0;
   const int nb = c.tnb[t];
+  if (nb < 0) return;  // kernel 2v proved that the diagram is the essential pair alone and wrote it
   const unsigned FULL = 0xffffffffu;
 
   for (int r = lane; r < n; r += 32) parent[r] = (PT)r;

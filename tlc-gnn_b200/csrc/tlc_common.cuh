@@ -31,7 +31,8 @@ struct ChunkView {
   const int64_t* eoff;  // [T+1]
   const int64_t* aoff;  // [T]   start of the target's adjacency segment (capacity: sum of the vicinity's graph degrees)
   int32_t *tn, *tm, *tlu, *tlv, *tnp, *tnpos, *tnneg, *tncls;
-  int32_t *tnb, *tminv, *tmaxv;  // kernel 2v: #blocks of the vertex order, local ids of the essential pair
+  int32_t *tnb, *tminv, *tmaxv;  // kernel 2v: #blocks of the vertex order (-1: diagram already written, nothing to sweep), local ids of the essential pair
+  int32_t no_fast = 0;           // kernel 2v: 1 = never take the essential-pair-only shortcut
   uint8_t* tstatus;
   int* fb_counter;  // device counter: targets kernel 3v handed back
   uint8_t* tfb;  // 1: the vertex-ordered sweep (kernel 3v) did not run / bailed out -> edge-sorted kernels 2 + 3 do the ascending sweep
