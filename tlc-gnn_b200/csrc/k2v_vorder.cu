@@ -13,6 +13,8 @@
 // block; only inside a block do individual edge keys matter.
 //
 // One CTA per vicinity:
+//   0. the no-pair certificate (see step 0 in the kernel): where it holds the diagram is the essential pair alone, which is
+//      written here, and steps 1-3 as well as kernel 3v are skipped for the target
 //   1. stable LSD radix sort of the n vertices on the ordered image of their value rounded down to float,
 //      runs of equal floats fixed to exact (float64 value, id) order (ties keep ascending local id)                    -> vord[rank] = local id, vrank[local id] = rank
 //   2. block starts bfirst[b], with two flags kernel 3v decides on:
