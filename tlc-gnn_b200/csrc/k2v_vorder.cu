@@ -50,11 +50,12 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
   //   A  if it has a neighbour y with f_y < f_x - delta;
   //   B  if it is not A, has NO neighbour with f_x - delta <= f_y < f_x or f_x < f_y <= f_x + delta, and an exactly equal
   //      neighbour; B is GROUNDED if a chain of exactly equal neighbours leads to an A vertex.
-  // If the roots carry 0, are adjacent (or one), and every other vertex is A or grounded B, the reference's sweep
+  // If all values lie in [0, 1], the roots carry 0, are adjacent (or one), and every other vertex is A or grounded B, the
+  // reference's sweep
   // (accelerated_PD.py:40-68) emits no pair at all:
   //   * the edge u-v has the smallest possible key 1e-6 and comes first;
   //   * the first edge of an A vertex x, in (key, position) order, is a descent edge to its lowest neighbour y* -- key
-  //     fl(f_x + fl(fl(f_y* + 1) * 1e-6)) lies >= 90 ulps below the key of every edge in which x is the smaller or an
+  //     fl(f_x + fl(fl(f_y* + 1) * 1e-6)) lies >= 45 ulps below the key of every edge in which x is the smaller or an
   //     equal end -- and by induction over the keys y* already hangs on the roots' component: x joins as a singleton of
   //     value f_x at an edge of larger value f_x, `old[large] < old[max_node]` (:65) is false;
   //   * the edges among equal values F all carry ONE key, above the first edges of the A vertices of value F and >= 1e-14
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(512, 3) vorder_kernel(Params p, ChunkView c, i
     }
     bad = __syncthreads_or(bad);
     if (!bad && !s_adj) bad = 1;
+    if (!bad && s_fmax > f64_to_ordered(1.0)) bad = 1;  // (the ulp margins of the proof are for values in [0, 1]: normalised filtrations)
     if (!bad) {
       // the candidates, a warp per row: A after all, B, or neither
       const int ncand = s_ncand;
