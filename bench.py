@@ -119,6 +119,9 @@ def config_dict(args, world):
                           "targets) and the warm-up steps fill it; the timed steps reuse it, as every call after the first does",
             "sssp_tables": "warm where used (graph-row route, N <= 16384): the per-root shortest-path table rows (distance, tree "
                            "parent, path sum over the whole graph) are built once per root during the warm-up steps",
+            "no_pair_certificate": "on (graph-row route): kernel 2v proves per target, from the step's own filtration values, that "
+                                   "the ascending sweep emits no ordinary pair and then writes the essential pair without "
+                                   "sorting (DESIGN.md section 5a); every target that fails the test is sorted and swept",
             "parallelism": "targets sharded over %d GPU(s), CSR replicated; N > 1: every rank stores its fp32 image rows "
                            "straight into every rank's table (peer stores over NVLink) or, --exchange nccl, NCCL all-gather" % world}
 
